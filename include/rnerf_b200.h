@@ -1,0 +1,177 @@
+/*
+ * rnerf_b200.h -- C ABI of the B200-native Robust-NeRF render-and-train hot path.
+ *
+ * The reference (ShawnnnLiu/Robust-NeRF) is pure Python/PyTorch and has no FFI; the
+ * drop-in boundary is therefore its Python API.  This header is the
+ * boundary UNDER that API: one `extern "C"` entry point per kernel family, plain device
+ * pointers + sizes + a CUDA stream, no torch types.  Each entry cites the reference code
+ * (path:line relative to the reference repo) whose aten-op sequence it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - every function enqueues work on `stream` and returns immediately (no sync, no alloc);
+ *   - return value: RN_OK (0) or an rn_status error code; never throws;
+ *   - all float tensors are contiguous fp32 row-major unless stated; indices are int64
+ *     like the reference's (`image_indices`, `searchsorted` output).
+ */
+#ifndef RNERF_B200_H_
+#define RNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rn_stream_t; /* cudaStream_t */
+
+typedef enum {
+  RN_OK = 0,
+  RN_ERR_INVALID_ARG = 1,    /* null pointer / bad size / unsupported configuration   */
+  RN_ERR_CUDA = 2,           /* a CUDA runtime call or launch failed (see rn_last_cuda_error) */
+  RN_ERR_UNSUPPORTED_ARCH = 3, /* device is not sm_100 (tcgen05/TMEM/TMA required)     */
+  RN_ERR_DRIVER = 4          /* cuTensorMapEncodeTiled unavailable / failed            */
+} rn_status;
+
+int rn_version(void);
+const char* rn_status_string(int status);
+int rn_last_cuda_error(void);            /* cudaError_t of the last RN_ERR_CUDA, else 0 */
+int rn_device_sm_count(int* sm_count_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Network geometry (fixed: the reference's default ModelConfig, noisy_src/config.py:10-24;
+ * other values are rejected in Python with NotImplementedError -- no fallback path).
+ * ---------------------------------------------------------------------------------------- */
+#define RN_NUM_PARAM_TENSORS 24      /* state_dict order: pts_linears.{0..7}.{weight,bias},
+                                        sigma_linear, feature_linear, dir_linear, rgb_linear */
+#define RN_NUM_PARAMS 595844         /* outputs/lego_clean_20251206_210328/summary.json:46 */
+#define RN_MLP_FLOP_PER_POINT 1186816 /* SURVEY.md section 8(a) row A1 */
+
+/* ---- SE(3) pose parameters: CameraPoseParameters.get_poses, train_pose_opt.py:122-226 ---- */
+int rn_se3_poses_fwd(const float* initial_poses /*[n_total,4,4]*/, const float* rot_deltas /*[n_total,3]*/,
+                     const float* trans_deltas /*[n_total,3]*/, const int64_t* indices /*[n] or NULL = arange*/,
+                     int n, int n_total, int learn_rotation, int learn_translation,
+                     float* poses_out /*[n,4,4]*/, rn_stream_t stream);
+/* d_rot / d_trans are ACCUMULATED into (caller zero-fills); either may be NULL. */
+int rn_se3_poses_bwd(const float* initial_poses, const float* rot_deltas, const int64_t* indices,
+                     int n, int n_total, const float* g_poses /*[n,4,4]*/,
+                     float* d_rot /*[n_total,3]*/, float* d_trans /*[n_total,3]*/, rn_stream_t stream);
+
+/* ---- ray generation: rays.py:17-99, data_pose_opt.py:83-148,200-223 ---- */
+int rn_ray_directions(int H, int W, float focal, float cx, float cy, float* dirs /*[H,W,3]*/, rn_stream_t stream);
+int rn_get_rays(const float* directions /*[n,3]*/, const float* c2w /*[4,4]*/, int64_t n,
+                float* rays_o /*[n,3]*/, float* rays_d /*[n,3]*/, rn_stream_t stream);
+int rn_get_rays_bwd(const float* directions, const float* c2w, int64_t n, const float* g_o, const float* g_d,
+                    float* g_c2w /*[4,4], overwritten*/, float* g_directions /*[n,3] or NULL*/, rn_stream_t stream);
+/* pixel batch -> rays, poses[image_idx] gathered on the fly (net effect of get_rays_for_batch) */
+int rn_raygen_fwd(const int64_t* image_idx /*[B]*/, const float* pixel_uv /*[B,2] (u,v) as float*/, int64_t B,
+                  const float* poses /*[n_poses,4,4]*/, int n_poses, int H, int W, float focal, float cx, float cy,
+                  float* rays_o, float* rays_d, rn_stream_t stream);
+int rn_raygen_bwd(const int64_t* image_idx, const float* pixel_uv, int64_t B, const float* poses, int n_poses,
+                  int H, int W, float focal, float cx, float cy, const float* g_o, const float* g_d,
+                  float* g_poses /*[n_poses,4,4], overwritten; deterministic per-image reduction*/, rn_stream_t stream);
+/* fused: exp-map pose update + ray generation (north_star subsystem 1) and its backward into
+ * the rotation / translation parameters (train_pose_opt.py:340-341 in one launch each way). */
+int rn_raygen_se3_fwd(const int64_t* image_idx, const float* pixel_uv, int64_t B, const float* initial_poses,
+                      const float* rot_deltas, const float* trans_deltas, int n_poses, int learn_rotation,
+                      int learn_translation, int H, int W, float focal, float cx, float cy,
+                      float* rays_o, float* rays_d, rn_stream_t stream);
+int rn_raygen_se3_bwd(const int64_t* image_idx, const float* pixel_uv, int64_t B, const float* initial_poses,
+                      const float* rot_deltas, int n_poses, int learn_rotation, int H, int W, float focal,
+                      float cx, float cy, const float* g_o, const float* g_d,
+                      float* d_rot /*[n_poses,3] overwritten*/, float* d_trans /*[n_poses,3] overwritten*/,
+                      rn_stream_t stream);
+/* PixelSampler.sample_batch bookkeeping (data_pose_opt.py:56-76,188-198) without the tables:
+ * image = idx / (H*W), v = (idx % (H*W)) / W, u = idx % W; rgb gathered from images[N,H,W,3]. */
+int rn_pixel_gather(const int64_t* flat_idx /*[B]*/, int64_t B, int H, int W, const float* images /*or NULL*/,
+                    int64_t* image_idx_out, float* pixel_uv_out, float* target_rgb_out /*or NULL*/, rn_stream_t stream);
+
+/* ---- sampling: rays.py:145-333 ---- */
+/* z = lower + (upper-lower)*t_rand over the base depths z_base (linspace built by the caller,
+ * rays.py:185-195); t_rand NULL = no perturbation.  pts may be NULL. */
+int rn_stratified_fwd(const float* rays_o, const float* rays_d, int64_t B, const float* z_base /*[Nc]*/, int Nc,
+                      const float* t_rand /*[B,Nc] or NULL*/, float* z_out /*[B,Nc]*/, float* pts_out /*[B,Nc,3] or NULL*/,
+                      rn_stream_t stream);
+/* pts = o + d*z (rays.py:208,331) and its backward into o, d */
+int rn_points_fwd(const float* rays_o, const float* rays_d, const float* z /*[B,S]*/, int64_t B, int S,
+                  float* pts /*[B,S,3]*/, rn_stream_t stream);
+int rn_points_bwd(const float* g_pts /*[B,S,3]*/, const float* z, int64_t B, int S,
+                  float* g_o /*[B,3]*/, float* g_d /*[B,3]*/, rn_stream_t stream);
+/* sample_pdf (rays.py:213-279): warp-per-ray sequential-order cdf + binary search (right=True).
+ * u has row stride u_stride (0 = one shared row, the det linspace). inds_out may be NULL. */
+int rn_sample_pdf_fwd(const float* bins /*[B,nb]*/, const float* weights /*[B,nb-1]*/, int64_t B, int nb,
+                      const float* u, int64_t u_stride, int Nf, float* samples /*[B,Nf]*/,
+                      int64_t* inds_out /*[B,Nf] or NULL*/, rn_stream_t stream);
+/* sample_hierarchical (rays.py:282-333): mid-point bins, interior weights, inverse cdf, sorted
+ * merge with the coarse depths; z_all sorted ascending; pts_out may be NULL. */
+int rn_sample_hierarchical_fwd(const float* rays_o, const float* rays_d, const float* z_coarse /*[B,Nc]*/,
+                               const float* weights /*[B,Nc]*/, int64_t B, int Nc, const float* u, int64_t u_stride,
+                               int Nf, float* z_all /*[B,Nc+Nf]*/, float* pts_out /*[B,Nc+Nf,3] or NULL*/,
+                               int64_t* inds_out /*[B,Nf] or NULL*/, rn_stream_t stream);
+
+/* ---- alpha compositing: rendering.py:20-116 ---- */
+/* Inputs either (rgb[B,S,3], sigma[B,S]) post-activation like the reference, or raw4[B,S,4]
+ * = (rgb pre-sigmoid x3, sigma pre-ReLU) straight from rn_mlp_fwd (rgb = sigma = NULL then).
+ * noise: already scaled randn draw [B,S] or NULL.  t_min > 0 enables early termination
+ * (samples whose incoming transmittance < t_min get weight 0); 0 = exact reference semantics. */
+int rn_composite_fwd(const float* rgb, const float* sigma, const float* raw4, const float* z /*[B,S]*/,
+                     const float* rays_d /*[B,3]*/, const float* noise, int64_t B, int S, int white_background,
+                     float t_min, float* rgb_map /*[B,3]*/, float* depth_map /*[B]*/, float* acc_map /*[B]*/,
+                     float* weights /*[B,S]*/, rn_stream_t stream);
+/* g_depth / g_acc / g_weights / d_rays_d may be NULL. Outputs d_rgb[B,S,3] + d_sigma[B,S]
+ * (post-activation mode) or d_raw4[B,S,4] (raw mode). */
+int rn_composite_bwd(const float* rgb, const float* sigma, const float* raw4, const float* z, const float* rays_d,
+                     const float* noise, int64_t B, int S, int white_background, const float* g_rgb_map,
+                     const float* g_depth, const float* g_acc, const float* g_weights, float* d_rgb, float* d_sigma,
+                     float* d_raw4, float* d_rays_d /*[B,3]*/, rn_stream_t stream);
+/* MSE loss of train.py:89-99 on a rendered batch: loss_out[0] += mean((rgb_map-target)^2),
+ * g_rgb_map = 2*(rgb_map-target)/(3B) * loss_scale.  loss_out is accumulated (caller zero-fills). */
+int rn_mse_loss_fwd_bwd(const float* rgb_map, const float* target, int64_t B, float loss_scale,
+                        float* loss_out /*[1]*/, float* g_rgb_map /*[B,3]*/, rn_stream_t stream);
+
+/* ---- NeRF MLP: model.py:20-196 (PE fused in; bf16 tcgen05 GEMMs, fp32 accumulate) ---- */
+size_t rn_mlp_packed_weight_bytes(void);
+/* params_host: 24 DEVICE pointers in state_dict order, array itself in HOST memory */
+int rn_mlp_pack_weights(const float* const* params_host, void* packed, rn_stream_t stream);
+size_t rn_mlp_workspace_bytes(int64_t M, int training);
+/* raw_out[M,4] = (rgb pre-sigmoid x3, sigma pre-ReLU).  dirs[M/dir_group,3]: one view direction
+ * per dir_group consecutive points (dir_group = samples per ray in render_rays; 1 for the generic
+ * NeRF.forward(x, d)).  training=1 keeps every activation in `workspace` for rn_mlp_bwd. */
+int rn_mlp_fwd(const void* packed, const float* pts /*[M,3]*/, const float* dirs, int64_t M, int dir_group,
+               void* workspace, int training, float* raw_out, rn_stream_t stream);
+/* grad_flat[RN_NUM_PARAMS] in state_dict order (overwritten); g_pts / g_dirs may be NULL
+ * (clean-pose training needs neither). workspace is the one rn_mlp_fwd(training=1) filled. */
+int rn_mlp_bwd(const void* packed, const float* pts, const float* dirs, int64_t M, int dir_group, void* workspace,
+               const float* g_raw /*[M,4]*/, float* grad_flat, float* g_pts /*[M,3]*/, float* g_dirs /*[M/dir_group,3]*/,
+               rn_stream_t stream);
+/* head activations of model.py:181,194: rgb = sigmoid(raw[:, :3]), sigma = relu(raw[:, 3]) and backward */
+int rn_head_act_fwd(const float* raw4, int64_t M, float* rgb /*[M,3]*/, float* sigma /*[M,1]*/, rn_stream_t stream);
+int rn_head_act_bwd(const float* raw4, int64_t M, const float* g_rgb, const float* g_sigma, float* g_raw4, rn_stream_t stream);
+/* positional encoding alone (model.py:58-80), fp32 in/out, for PositionalEncoding.forward */
+int rn_posenc_fwd(const float* x /*[n,C]*/, int64_t n, int C, int num_freqs, float* out /*[n,C*(1+2L)]*/, rn_stream_t stream);
+int rn_posenc_bwd(const float* x, int64_t n, int C, int num_freqs, const float* g_out, float* g_x, rn_stream_t stream);
+
+/* ---- building block exposed for unit tests / profiling: one bf16 tcgen05 GEMM ----
+ * mode 0 (NT): D[M,N] = act(A[M,K] * B[N,K]^T + bias)            forward layer
+ * mode 1 (NN): D[M,N] = (A[M,K] * B[K,N]) (.) (mask[M,N] > 0)     data gradient
+ * mode 2 (TN): D[Mo,N] (fp32) = A[K,Mo]^T * B[K,N]                weight gradient (split-K inside)
+ * A, B, mask, D(mode 0/1) are bf16 with leading dimensions in ELEMENTS; ld % 8 == 0. */
+int rn_gemm_bf16(int mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+                 int64_t M, int N, int64_t K, const float* bias, int relu, const void* mask, int64_t ldmask,
+                 float* colsum_out /*mode 2: sum_k A[k,:] (bias gradient) or NULL*/, void* scratch, size_t scratch_bytes,
+                 rn_stream_t stream);
+size_t rn_gemm_scratch_bytes(void);
+
+/* ---- optimiser tail (train.py:115-117, train_pose_opt.py:398-409): clip_grad_norm_ + Adam ---- */
+/* One launch pair over a flat fp32 parameter/gradient/moment buffer.  `norm_groups` partitions the
+ * buffer into ranges clipped independently (joint clip = 1 group; pose-opt = one group per net). */
+int rn_clip_adam_step(float* params, float* grads /*scaled in place by the clip*/, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      const int64_t* group_offsets_host /*[n_groups+1]*/, const float* group_max_norm_host, int n_groups,
+                      float lr, float beta1, float beta2, float eps, int step, float* norms_out /*[n_groups]*/,
+                      rn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNERF_B200_H_ */

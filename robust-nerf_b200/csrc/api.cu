@@ -1,0 +1,115 @@
+// api.cu -- library bookkeeping (version, status strings, device query) and the optimiser tail
+// of the training step: clip_grad_norm_ + Adam fused over a flat parameter buffer
+// (noisy_src/train.py:115-117, noisy_src/train_pose_opt.py:398-409).
+#include "common.cuh"
+
+namespace rn {
+
+int g_last_cuda_error = 0;
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return kNumSMsDefault;
+  }
+  return cached;
+}
+
+constexpr int kMaxGroups = 8;
+struct Groups { int64_t off[kMaxGroups + 1]; float max_norm[kMaxGroups]; int n; };
+
+// one CTA per clip group, fixed reduction order -> deterministic norm
+__global__ void __launch_bounds__(1024)
+grad_norm_kernel(const float* __restrict__ g, Groups gr, float* __restrict__ norms) {
+  __shared__ float red[32];
+  const int grp = blockIdx.x;
+  float acc = 0.f;
+  for (int64_t i = gr.off[grp] + threadIdx.x; i < gr.off[grp + 1]; i += 1024) { const float v = g[i]; acc = fmaf(v, v, acc); }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 32; ++w) t += red[w];
+    norms[grp] = sqrtf(t);
+  }
+}
+
+// clip (torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)), grads scaled in
+// place) followed by torch.optim.Adam's default update.
+__global__ void clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 int64_t n, Groups gr, const float* __restrict__ norms, float lr, float b1, float b2,
+                                 float eps, float bc1, float bc2_sqrt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int grp = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxGroups; ++k) if (k < gr.n && i >= gr.off[k]) grp = k;
+    float coef = 1.0f;
+    if (gr.max_norm[grp] > 0.f) coef = fminf(1.0f, gr.max_norm[grp] / (norms[grp] + 1e-6f));
+    const float gi = g[i] * coef;
+    g[i] = gi;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" {
+
+int rn_version(void) { return 100; }
+
+const char* rn_status_string(int s) {
+  switch (s) {
+    case RN_OK: return "ok";
+    case RN_ERR_INVALID_ARG: return "invalid argument (null pointer, bad size or unsupported configuration)";
+    case RN_ERR_CUDA: return "CUDA runtime error (see rn_last_cuda_error)";
+    case RN_ERR_UNSUPPORTED_ARCH: return "device is not sm_100: tcgen05/TMEM/TMA kernels cannot run";
+    case RN_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+    default: return "unknown status";
+  }
+}
+
+int rn_last_cuda_error(void) { return g_last_cuda_error; }
+
+int rn_device_sm_count(int* out) {
+  RN_REQUIRE(out);
+  int dev = 0, n = 0;
+  RN_CUDA_CHECK(cudaGetDevice(&dev));
+  RN_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  *out = n;
+  return RN_OK;
+}
+
+int rn_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      const int64_t* group_offsets_host, const float* group_max_norm_host, int n_groups, float lr,
+                      float beta1, float beta2, float eps, int step, float* norms_out, rn_stream_t stream) {
+  RN_REQUIRE(params && grads && exp_avg && exp_avg_sq && norms_out && group_offsets_host && group_max_norm_host);
+  RN_REQUIRE(n > 0 && n_groups >= 1 && n_groups <= kMaxGroups && step >= 1);
+  Groups gr{};
+  gr.n = n_groups;
+  for (int i = 0; i <= n_groups; ++i) gr.off[i] = group_offsets_host[i];
+  for (int i = 0; i < n_groups; ++i) gr.max_norm[i] = group_max_norm_host[i];
+  RN_REQUIRE(gr.off[0] == 0 && gr.off[n_groups] == n);
+  cudaStream_t st = (cudaStream_t)stream;
+  grad_norm_kernel<<<n_groups, 1024, 0, st>>>(grads, gr, norms_out);
+  RN_LAUNCH_CHECK();
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  clip_adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, gr, norms_out, lr, beta1, beta2,
+                                                     eps, bc1, bc2_sqrt);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// common.cuh -- shared helpers for the rnerf_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/rnerf_b200.h"
+
+namespace rn {
+
+extern int g_last_cuda_error;
+
+inline int cuda_fail(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return RN_ERR_CUDA;
+}
+
+#define RN_CUDA_CHECK(expr)                          \
+  do {                                               \
+    cudaError_t _e = (expr);                         \
+    if (_e != cudaSuccess) return rn::cuda_fail(_e); \
+  } while (0)
+
+#define RN_LAUNCH_CHECK() RN_CUDA_CHECK(cudaGetLastError())
+
+#define RN_REQUIRE(cond)                     \
+  do {                                       \
+    if (!(cond)) return RN_ERR_INVALID_ARG;  \
+  } while (0)
+
+constexpr int kNumSMsDefault = 148;
+int num_sms();
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Grid size for a grid-stride kernel: a multiple of the SM count, capped by the work.
+inline int grid_for(int64_t work_items, int threads, int ctas_per_sm = 8) {
+  int64_t need = ceil_div(work_items, threads);
+  int64_t cap = (int64_t)num_sms() * ctas_per_sm;
+  int64_t g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// ---- network geometry (reference default ModelConfig) ----
+constexpr int kHidden = 256;
+constexpr int kPosFreqs = 10, kDirFreqs = 4;
+constexpr int kPosDim = 63, kDirDim = 27;
+constexpr int kPosPad = 64;       // x_enc padded to one 64-wide K chunk
+constexpr int kCatW = 320;        // [x_enc(64) | h(256)] and [feat(256) | d_enc(27) | 0]
+constexpr int kHalf = 128;
+
+// ---- device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+
+}  // namespace rn

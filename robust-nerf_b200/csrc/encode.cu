@@ -1,0 +1,430 @@
+// encode.cu -- everything of the NeRF MLP that is not a 256-wide GEMM:
+//   positional encoding (noisy_src/model.py:58-80; no pi factor, sin/cos with full range reduction),
+//   fused into the producer of the first layer's bf16 operand; the sigma (256->1) and rgb (128->3)
+//   heads of model.py:181,194 on CUDA cores in fp32; weight packing fp32 -> padded bf16;
+//   and the backward passes of all of them.
+#include "common.cuh"
+#include "mlp_layout.h"
+
+namespace rn {
+
+using namespace layout;
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// feat[0..3*(1+2L)) for one 3-vector, reference order: x, then per frequency sin(xyz), cos(xyz)
+template <int L>
+__device__ __forceinline__ void encode3(const float x[3], float* feat) {
+  feat[0] = x[0]; feat[1] = x[1]; feat[2] = x[2];
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const float f = (float)(1 << k);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float s, c;
+      sincosf(__fmul_rn(f, x[a]), &s, &c);     // accurate range reduction: arguments reach ~3000 rad
+      feat[3 + 6 * k + a] = s;
+      feat[3 + 6 * k + 3 + a] = c;
+    }
+  }
+}
+
+// pts[M,3] -> XC[:, 0:64] (bf16, col 63 = 0); dirs[M/group,3] -> FD[:, 256:320] (27 features + zeros)
+__global__ void __launch_bounds__(256)
+encode_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, int64_t M, int group,
+              __nv_bfloat16* __restrict__ XC, int ldx, __nv_bfloat16* __restrict__ FD, int ldf) {
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float feat[64];
+    const float x[3] = {__ldcs(pts + m * 3), __ldcs(pts + m * 3 + 1), __ldcs(pts + m * 3 + 2)};
+    encode3<kPosFreqs>(x, feat);
+    feat[63] = 0.f;
+    uint4* dst = reinterpret_cast<uint4*>(XC + m * ldx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      dst[i] = make_uint4(pack_bf16(feat[8 * i], feat[8 * i + 1]), pack_bf16(feat[8 * i + 2], feat[8 * i + 3]),
+                          pack_bf16(feat[8 * i + 4], feat[8 * i + 5]), pack_bf16(feat[8 * i + 6], feat[8 * i + 7]));
+    if (FD) {
+      const int64_t r = m / group;
+      const float d[3] = {__ldg(dirs + r * 3), __ldg(dirs + r * 3 + 1), __ldg(dirs + r * 3 + 2)};
+      float df[32];
+      encode3<kDirFreqs>(d, df);
+#pragma unroll
+      for (int i = 27; i < 32; ++i) df[i] = 0.f;
+      uint4* dd = reinterpret_cast<uint4*>(FD + m * ldf + 256);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dd[i] = make_uint4(pack_bf16(df[8 * i], df[8 * i + 1]), pack_bf16(df[8 * i + 2], df[8 * i + 3]),
+                           pack_bf16(df[8 * i + 4], df[8 * i + 5]), pack_bf16(df[8 * i + 6], df[8 * i + 7]));
+#pragma unroll
+      for (int i = 4; i < 8; ++i) dd[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+// generic fp32 PositionalEncoding.forward / backward (API parity; C components per vector)
+__global__ void posenc_fwd_kernel(const float* __restrict__ x, int64_t n, int C, int L, float* __restrict__ out) {
+  const int W = C * (1 + 2 * L);
+  const int64_t total = n * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int a = (int)(i - r * C);
+    const float v = x[i];
+    float* o = out + r * W;
+    o[a] = v;
+    for (int k = 0; k < L; ++k) {
+      float s, c;
+      sincosf(__fmul_rn((float)(1 << k), v), &s, &c);
+      o[C * (1 + 2 * k) + a] = s;
+      o[C * (2 + 2 * k) + a] = c;
+    }
+  }
+}
+__global__ void posenc_bwd_kernel(const float* __restrict__ x, int64_t n, int C, int L, const float* __restrict__ g,
+                                  float* __restrict__ gx) {
+  const int W = C * (1 + 2 * L);
+  const int64_t total = n * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int a = (int)(i - r * C);
+    const float v = x[i];
+    const float* go = g + r * W;
+    float acc = go[a];
+    for (int k = 0; k < L; ++k) {
+      const float f = (float)(1 << k);
+      float s, c;
+      sincosf(__fmul_rn(f, v), &s, &c);
+      acc += f * (c * go[C * (1 + 2 * k) + a] - s * go[C * (2 + 2 * k) + a]);
+    }
+    gx[i] = acc;
+  }
+}
+
+// backward of the fused encode: g_pts from dXE0 + dXE5 (bf16 [M,64]); g_dirs from dDE (bf16 [M,64])
+template <int L>
+__device__ __forceinline__ void encode3_bwd(const float x[3], const float* g /*3*(1+2L)*/, float gx[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) gx[a] = g[a];
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const float f = (float)(1 << k);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float s, c;
+      sincosf(__fmul_rn(f, x[a]), &s, &c);
+      gx[a] += f * (c * g[3 + 6 * k + a] - s * g[3 + 6 * k + 3 + a]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+encode_bwd_pts_kernel(const float* __restrict__ pts, int64_t M, const __nv_bfloat16* __restrict__ dXE0,
+                      const __nv_bfloat16* __restrict__ dXE5, float* __restrict__ g_pts) {
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float g[64];
+    const uint4* a = reinterpret_cast<const uint4*>(dXE0 + m * 64);
+    const uint4* b = reinterpret_cast<const uint4*>(dXE5 + m * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = a[i], v = b[i];
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        g[8 * i + 2 * e] = bf16_lo(uw[e]) + bf16_lo(vw[e]);
+        g[8 * i + 2 * e + 1] = bf16_hi(uw[e]) + bf16_hi(vw[e]);
+      }
+    }
+    const float x[3] = {pts[m * 3], pts[m * 3 + 1], pts[m * 3 + 2]};
+    float gx[3];
+    encode3_bwd<kPosFreqs>(x, g, gx);
+    g_pts[m * 3] = gx[0]; g_pts[m * 3 + 1] = gx[1]; g_pts[m * 3 + 2] = gx[2];
+  }
+}
+
+// one warp per direction group: g_dirs[r] = sum over the group's points of dPE^T dDE[m]
+__global__ void __launch_bounds__(256)
+encode_bwd_dirs_kernel(const float* __restrict__ dirs, int64_t R, int group, const __nv_bfloat16* __restrict__ dDE,
+                       float* __restrict__ g_dirs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    float g[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) g[i] = 0.f;
+    for (int p = lane; p < group; p += 32) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(dDE + (r * group + p) * 64);
+#pragma unroll
+      for (int i = 0; i < 13; ++i) { const uint32_t w = src[i]; g[2 * i] += bf16_lo(w); g[2 * i + 1] += bf16_hi(w); }
+      g[26] += bf16_lo(src[13]);
+    }
+#pragma unroll
+    for (int i = 0; i < 27; ++i) g[i] = warp_sum(g[i]);
+    if (lane == 0) {
+      const float d[3] = {dirs[r * 3], dirs[r * 3 + 1], dirs[r * 3 + 2]};
+      float gx[3];
+      encode3_bwd<kDirFreqs>(d, g, gx);
+      g_dirs[r * 3] = gx[0]; g_dirs[r * 3 + 1] = gx[1]; g_dirs[r * 3 + 2] = gx[2];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// heads: sigma_pre = H7 . w_sigma + b, rgb_pre = HC . W_rgb^T + b   (fp32 weights, bf16 activations)
+// 8 lanes per point.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+heads_fwd_kernel(const __nv_bfloat16* __restrict__ H7, const __nv_bfloat16* __restrict__ HC, int64_t M,
+                 const float* __restrict__ f32sec, float4* __restrict__ raw) {
+  __shared__ float s_w[256 + 384 + 8];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_w[i] = f32sec[kWSig + i];
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) s_w[256 + i] = f32sec[kWRgb + i];
+  if (threadIdx.x < 4) { s_w[640 + threadIdx.x] = f32sec[kBRgb + threadIdx.x]; s_w[644 + threadIdx.x] = f32sec[kBSig + threadIdx.x]; }
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) >> 3;
+  const int64_t iters = (M + gstride - 1) / gstride;
+  int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+  for (int64_t it = 0; it < iters; ++it, m += gstride) {
+    const bool valid = m < M;
+    float as = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (valid) {
+      const uint4* h = reinterpret_cast<const uint4*>(H7 + m * 256 + sub * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldcs(h + i);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = sub * 32 + i * 8 + 2 * e;
+          as = fmaf(bf16_lo(w[e]), s_w[j], as);
+          as = fmaf(bf16_hi(w[e]), s_w[j + 1], as);
+        }
+      }
+      const uint4* c = reinterpret_cast<const uint4*>(HC + m * 128 + sub * 16);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint4 u = __ldcs(c + i);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = sub * 16 + i * 8 + 2 * e;
+          const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+          a0 = fmaf(lo, s_w[256 + j], a0); a0 = fmaf(hi, s_w[256 + j + 1], a0);
+          a1 = fmaf(lo, s_w[384 + j], a1); a1 = fmaf(hi, s_w[384 + j + 1], a1);
+          a2 = fmaf(lo, s_w[512 + j], a2); a2 = fmaf(hi, s_w[512 + j + 1], a2);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      as += __shfl_xor_sync(0xffffffffu, as, o);
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (valid && sub == 0) raw[m] = make_float4(a0 + s_w[640], a1 + s_w[641], a2 + s_w[642], as + s_w[644]);
+  }
+}
+
+// backward of the heads.  CTA = 128 threads <-> the 128 columns of HC; each CTA walks a contiguous
+// slice of points.  Writes dHC (masked by HC > 0, bf16), column 256.. of dFS (d sigma_pre, bf16) and
+// per-CTA partial sums of dW_rgb / db_rgb (reduced in fixed order by heads_bwd_reduce_kernel).
+constexpr int kHeadsBwdPts = 512;
+__global__ void __launch_bounds__(128)
+heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restrict__ HC, int64_t M,
+                 const float* __restrict__ f32sec, __nv_bfloat16* __restrict__ dHC, __nv_bfloat16* __restrict__ dFS,
+                 int ldfs, float* __restrict__ partial /*[grid][388]*/) {
+  const int j = threadIdx.x;
+  const float w0 = f32sec[kWRgb + j], w1 = f32sec[kWRgb + 128 + j], w2 = f32sec[kWRgb + 256 + j];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b = 0.f;
+  const int64_t m0 = (int64_t)blockIdx.x * kHeadsBwdPts;
+  const int64_t m1 = m0 + kHeadsBwdPts < M ? m0 + kHeadsBwdPts : M;
+  for (int64_t m = m0; m < m1; ++m) {
+    const float4 g = __ldg(g_raw + m);
+    const float hc = __bfloat162float(HC[m * 128 + j]);
+    a0 = fmaf(g.x, hc, a0); a1 = fmaf(g.y, hc, a1); a2 = fmaf(g.z, hc, a2);
+    const float d = (hc > 0.f) ? (g.x * w0 + g.y * w1 + g.z * w2) : 0.f;
+    dHC[m * 128 + j] = __float2bfloat16_rn(d);
+    if (j < 16) dFS[m * ldfs + 256 + j] = __float2bfloat16_rn(j == 0 ? g.w : 0.f);
+    if (j < 3) b += (j == 0 ? g.x : (j == 1 ? g.y : g.z));
+  }
+  float* p = partial + (size_t)blockIdx.x * 388;
+  p[j] = a0; p[128 + j] = a1; p[256 + j] = a2;
+  if (j < 3) p[384 + j] = b;
+}
+__global__ void heads_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ gWrgb,
+                                        float* __restrict__ gBrgb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 387) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * 388 + i];
+  if (i < 384) gWrgb[i] = acc; else gBrgb[i - 384] = acc;
+}
+
+// model.py:181,194 activations for the NeRF.forward API
+__global__ void head_act_fwd_kernel(const float4* __restrict__ raw, int64_t M, float* __restrict__ rgb, float* __restrict__ sigma) {
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const float4 r = raw[m];
+    rgb[m * 3] = 1.0f / (1.0f + expf(-r.x)); rgb[m * 3 + 1] = 1.0f / (1.0f + expf(-r.y)); rgb[m * 3 + 2] = 1.0f / (1.0f + expf(-r.z));
+    sigma[m] = fmaxf(r.w, 0.f);
+  }
+}
+__global__ void head_act_bwd_kernel(const float4* __restrict__ raw, int64_t M, const float* __restrict__ g_rgb,
+                                    const float* __restrict__ g_sigma, float4* __restrict__ g_raw) {
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const float4 r = raw[m];
+    const float s0 = 1.0f / (1.0f + expf(-r.x)), s1 = 1.0f / (1.0f + expf(-r.y)), s2 = 1.0f / (1.0f + expf(-r.z));
+    float4 o;
+    o.x = g_rgb ? g_rgb[m * 3] * s0 * (1.f - s0) : 0.f;
+    o.y = g_rgb ? g_rgb[m * 3 + 1] * s1 * (1.f - s1) : 0.f;
+    o.z = g_rgb ? g_rgb[m * 3 + 2] * s2 * (1.f - s2) : 0.f;
+    o.w = (g_sigma && r.w > 0.f) ? g_sigma[m] : 0.f;
+    g_raw[m] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: 24 fp32 state_dict tensors -> padded bf16 matrices + fp32 section
+// ------------------------------------------------------------------------------------------
+struct PackSrc { const float* p[RN_NUM_PARAM_TENSORS]; };
+
+struct PackSeg { size_t dst; int rows_p, cols_p, src_rows, src_cols, src_idx, skip; };
+
+__constant__ PackSeg c_segs[11] = {
+    {kW0, 256, 64, 256, 63, 0, 0},   {kW1, 256, 256, 256, 256, 2, 0}, {kW2, 256, 256, 256, 256, 4, 0},
+    {kW3, 256, 256, 256, 256, 6, 0}, {kW4, 256, 256, 256, 256, 8, 0}, {kW5, 256, 320, 256, 319, 10, 1},
+    {kW6, 256, 256, 256, 256, 12, 0}, {kW7, 256, 256, 256, 256, 14, 0},
+    {kWFS, 256, 256, 256, 256, 18, 0},            // feature_linear.weight -> rows 0..255 of WFS
+    {kWFS + 256 * 256, 16, 256, 1, 256, 16, 0},   // sigma_linear.weight -> row 256 (+15 zero rows)
+    {kWD, 128, 320, 128, 283, 20, 0}};
+
+__global__ void pack_weights_kernel(PackSrc src, __nv_bfloat16* __restrict__ dst_bf16, float* __restrict__ dst_f32) {
+  const int seg = blockIdx.y;
+  if (seg < 11) {
+    const PackSeg sg = c_segs[seg];
+    const int total = sg.rows_p * sg.cols_p;
+    const float* s = src.p[sg.src_idx];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int r = i / sg.cols_p, c = i % sg.cols_p;
+      int sc = c;
+      if (sg.skip) sc = (c < 63) ? c : (c == 63 ? -1 : c - 1);   // [x_enc(63) | 0 | h(256)]
+      float v = 0.f;
+      if (r < sg.src_rows && sc >= 0 && sc < sg.src_cols) v = s[(size_t)r * sg.src_cols + sc];
+      dst_bf16[sg.dst + i] = __float2bfloat16_rn(v);
+    }
+  } else {
+    // fp32 section
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)kF32Elems; i += gridDim.x * blockDim.x) {
+      float v = 0.f;
+      if (i < (int)kBF) v = src.p[2 * (i / 256) + 1][i % 256];                 // trunk biases
+      else if (i < (int)kBD) v = src.p[19][i - kBF];                            // feature bias
+      else if (i < (int)kWSig) v = src.p[21][i - kBD];                          // dir bias
+      else if (i < (int)kBSig) v = src.p[16][i - kWSig];                        // sigma weight
+      else if (i < (int)kWRgb) v = (i == (int)kBSig) ? src.p[17][0] : 0.f;      // sigma bias
+      else if (i < (int)kBRgb) v = src.p[22][i - kWRgb];                        // rgb weight
+      else v = (i - (int)kBRgb < 3) ? src.p[23][i - kBRgb] : 0.f;               // rgb bias
+      dst_f32[i] = v;
+    }
+  }
+}
+
+}  // namespace rn
+
+using namespace rn;
+using namespace rn::layout;
+
+namespace rn {
+// used by mlp.cu
+int launch_encode(const float* pts, const float* dirs, int64_t M, int group, void* XC, int ldx, void* FD, int ldf,
+                  cudaStream_t st) {
+  encode_kernel<<<grid_for(M, 256), 256, 0, st>>>(pts, dirs, M, group, (__nv_bfloat16*)XC, ldx, (__nv_bfloat16*)FD, ldf);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+int launch_heads_fwd(const void* H7, const void* HC, int64_t M, const float* f32sec, float* raw, cudaStream_t st) {
+  heads_fwd_kernel<<<grid_for(M * 8, 256), 256, 0, st>>>((const __nv_bfloat16*)H7, (const __nv_bfloat16*)HC, M, f32sec,
+                                                          (float4*)raw);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+size_t heads_bwd_scratch_bytes(int64_t M) { return (size_t)ceil_div(M, kHeadsBwdPts) * 388 * sizeof(float); }
+int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,
+                     float* scratch, float* gWrgb, float* gBrgb, cudaStream_t st) {
+  const int nblk = (int)ceil_div(M, kHeadsBwdPts);
+  heads_bwd_kernel<<<nblk, 128, 0, st>>>((const float4*)g_raw, (const __nv_bfloat16*)HC, M, f32sec, (__nv_bfloat16*)dHC,
+                                         (__nv_bfloat16*)dFS, ldfs, scratch);
+  RN_LAUNCH_CHECK();
+  heads_bwd_reduce_kernel<<<4, 128, 0, st>>>(scratch, nblk, gWrgb, gBrgb);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+int launch_encode_bwd(const float* pts, const float* dirs, int64_t M, int group, const void* dXE0, const void* dXE5,
+                      const void* dDE, float* g_pts, float* g_dirs, cudaStream_t st) {
+  if (g_pts) {
+    encode_bwd_pts_kernel<<<grid_for(M, 256), 256, 0, st>>>(pts, M, (const __nv_bfloat16*)dXE0, (const __nv_bfloat16*)dXE5, g_pts);
+    RN_LAUNCH_CHECK();
+  }
+  if (g_dirs) {
+    const int64_t R = M / group;
+    encode_bwd_dirs_kernel<<<grid_for(R * 32, 256), 256, 0, st>>>(dirs, R, group, (const __nv_bfloat16*)dDE, g_dirs);
+    RN_LAUNCH_CHECK();
+  }
+  return RN_OK;
+}
+}  // namespace rn
+
+extern "C" {
+
+size_t rn_mlp_packed_weight_bytes(void) { return kPackedBytes; }
+
+int rn_mlp_pack_weights(const float* const* params_host, void* packed, rn_stream_t stream) {
+  RN_REQUIRE(params_host && packed);
+  PackSrc src;
+  for (int i = 0; i < RN_NUM_PARAM_TENSORS; ++i) {
+    RN_REQUIRE(params_host[i] != nullptr);
+    src.p[i] = params_host[i];
+  }
+  pack_weights_kernel<<<dim3(64, 12), 256, 0, (cudaStream_t)stream>>>(
+      src, (__nv_bfloat16*)packed, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + kBf16Bytes));
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_head_act_fwd(const float* raw4, int64_t M, float* rgb, float* sigma, rn_stream_t stream) {
+  RN_REQUIRE(raw4 && rgb && sigma && M >= 0);
+  if (M == 0) return RN_OK;
+  head_act_fwd_kernel<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)raw4, M, rgb, sigma);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_head_act_bwd(const float* raw4, int64_t M, const float* g_rgb, const float* g_sigma, float* g_raw4, rn_stream_t stream) {
+  RN_REQUIRE(raw4 && g_raw4 && M >= 0);
+  if (M == 0) return RN_OK;
+  head_act_bwd_kernel<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)raw4, M, g_rgb, g_sigma, (float4*)g_raw4);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_posenc_fwd(const float* x, int64_t n, int C, int L, float* out, rn_stream_t stream) {
+  RN_REQUIRE(x && out && n >= 0 && C >= 1 && L >= 0 && L <= 30);
+  if (n == 0) return RN_OK;
+  posenc_fwd_kernel<<<grid_for(n * C, 256), 256, 0, (cudaStream_t)stream>>>(x, n, C, L, out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_posenc_bwd(const float* x, int64_t n, int C, int L, const float* g_out, float* g_x, rn_stream_t stream) {
+  RN_REQUIRE(x && g_out && g_x && n >= 0 && C >= 1 && L >= 0 && L <= 30);
+  if (n == 0) return RN_OK;
+  posenc_bwd_kernel<<<grid_for(n * C, 256), 256, 0, (cudaStream_t)stream>>>(x, n, C, L, g_out, g_x);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+}  // extern "C"

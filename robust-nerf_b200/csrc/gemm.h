@@ -1,0 +1,27 @@
+// gemm.h -- host-side entry points of gemm_tcgen05.cu used by mlp.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace rn {
+struct TnInfo { int m_tiles, splits, N; float* scratch; };
+int check_arch();
+int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
+            const float* bias, int relu, cudaStream_t st);
+int gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
+            const void* mask, int64_t ldmask, cudaStream_t st);
+size_t gemm_tn_scratch_bytes();
+int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ldb, int N, int64_t K, float* scratch,
+                   size_t scratch_bytes, TnInfo* info, cudaStream_t st);
+int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int ncols, float* dst, int64_t dst_ld, float* colsum_dst,
+                   cudaStream_t st);
+
+int launch_encode(const float* pts, const float* dirs, int64_t M, int group, void* XC, int ldx, void* FD, int ldf, cudaStream_t st);
+int launch_heads_fwd(const void* H7, const void* HC, int64_t M, const float* f32sec, float* raw, cudaStream_t st);
+size_t heads_bwd_scratch_bytes(int64_t M);
+int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,
+                     float* scratch, float* gWrgb, float* gBrgb, cudaStream_t st);
+int launch_encode_bwd(const float* pts, const float* dirs, int64_t M, int group, const void* dXE0, const void* dXE5,
+                      const void* dDE, float* g_pts, float* g_dirs, cudaStream_t st);
+}  // namespace rn

@@ -1,0 +1,514 @@
+// gemm_tcgen05.cu -- the dense contraction of the NeRF MLP on 5th-gen tensor cores.
+//
+// Replaces the 12 addmm (+ReLU, +cat) of noisy_src/model.py:169-194 and the 24 mm of their
+// autograd backward.  One warp-specialised kernel, three operand-layout modes:
+//   NT  D[M,N]  = act(A[M,K] * B[N,K]^T + bias)            forward layer        (A, B K-major)
+//   NN  D[M,N]  = (A[M,K] * B[K,N]) .* (mask > 0)          data gradient        (B MN-major)
+//   TN  D[Mo,N] = A[K,Mo]^T * B[K,N]  (+ column sums of A) weight/bias gradient (A, B MN-major)
+// Operands are bf16, staged global->shared by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through an
+// mbarrier ring; the MMA is tcgen05.mma (cta_group::1, M=128, N<=256, K=16) issued by one elected
+// thread with fp32 accumulators in TMEM; the epilogue reads TMEM with tcgen05.ld, applies
+// bias/ReLU (or the ReLU mask), converts to bf16, stages the tile in swizzled shared memory and
+// writes it back with a TMA store.  NT/NN are persistent over 128-row tiles with a
+// double-buffered TMEM accumulator so tile i's epilogue overlaps tile i+1's MMAs; TN is split-K
+// over the point dimension with fp32 partial tiles reduced by a second (deterministic) kernel,
+// and gets the bias gradient for free from one extra N=16 MMA against a tile of ones.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "gemm.h"
+#include <cuda_bf16.h>
+#include <stdio.h>
+
+namespace rn {
+
+using namespace ptx;
+
+enum { MODE_NT = 0, MODE_NN = 1, MODE_TN = 2 };
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;               // one 128-byte swizzle span of bf16
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
+constexpr int kGemmThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kOnesBytes = 2048;          // 16 k-rows x 128 B of bf16 1.0 (TN bias-gradient trick)
+
+
+struct GemmArgs {
+  int m_tiles;            // NT/NN: 128-row tiles of D;  TN: 128-row tiles of Mo
+  int k_chunks;           // ceil(K / 64)
+  int k_total;            // K
+  const float* bias;      // NT (may be null)
+  int relu;               // NT
+  int has_mask;           // NN
+  float* partial;         // TN: [m_tiles*splits][128*(BN+1)] fp32
+  int splits;             // TN
+  int chunks_per_split;   // TN
+};
+
+template <int BN, int MODE>
+struct GemmCfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = (MODE == MODE_TN) ? kOnesBytes : (BN / 64) * 16384;
+  static constexpr int kBudget = 225 * 1024 - kStagingBytes - 2048 /*bias+barriers*/ - 1024 /*align slack*/;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kAccCols = (MODE == MODE_TN) ? (BN + 16) : 2 * BN;
+  static constexpr int kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 2048 + 1024;
+  static_assert(kStages >= 2, "pipeline too shallow");
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128, 192 or 256");
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmMask, GemmArgs args) {
+  using Cfg = GemmCfg<BN, MODE>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_stage = smem;
+  uint8_t* s_staging = smem + NS * Cfg::kStageBytes;
+  float* s_bias = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
+  uint64_t* full_bar = bars;                 // [NS]
+  uint64_t* empty_bar = bars + NS;           // [NS]
+  uint64_t* tmem_full = bars + 2 * NS;       // [2]
+  uint64_t* tmem_empty = bars + 2 * NS + 2;  // [2]
+  uint64_t* mask_bar = bars + 2 * NS + 4;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---------------- one-time setup ----------------
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    if (MODE != MODE_TN) prefetch_tmap(&tmD);
+    if (MODE == MODE_NN) prefetch_tmap(&tmMask);
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    mbar_init(mask_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (MODE == MODE_NT) {
+      for (int i = t; i < BN; i += kEpiThreads) s_bias[i] = args.bias ? args.bias[i] : 0.f;
+    }
+    if (MODE == MODE_TN) {
+      uint32_t* ones = reinterpret_cast<uint32_t*>(s_staging);
+      for (int i = t; i < kOnesBytes / 4; i += kEpiThreads) ones[i] = 0x3F803F80u;   // bf16 1.0 x2
+      fence_proxy_async_smem();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (MODE != MODE_TN) {
+    // =====================================================================================
+    // NT / NN: persistent over 128-row tiles
+    // =====================================================================================
+    if (warp == 0) {
+      if (lane == 0) {
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
+          for (int kc = 0; kc < args.k_chunks; ++kc) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* a_s = s_stage + s * Cfg::kStageBytes;
+            uint8_t* b_s = a_s + kABytes;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+            tma_load_2d(a_s, &tmA, &full_bar[s], kc * kBlockK, tile * kBlockM);
+            if (MODE == MODE_NT) {
+              tma_load_2d(b_s, &tmB, &full_bar[s], kc * kBlockK, 0);                 // [BN rows][64 k]
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)                                        // [64 k rows][64 n] boxes
+                tma_load_2d(b_s + j * 8192, &tmB, &full_bar[s], j * 64, kc * kBlockK);
+            }
+            if (++s == NS) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, MODE == MODE_NN ? 1 : 0);
+        int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
+          mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kc = 0; kc < args.k_chunks; ++kc) {
+            mbar_wait(&full_bar[s], ph);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(s_stage + s * Cfg::kStageBytes);
+            const uint32_t b_addr = a_addr + kABytes;
+            const int krem = args.k_total - kc * kBlockK;
+            const int ksteps = krem >= kBlockK ? 4 : (krem + 15) / 16;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t bdesc = (MODE == MODE_NT) ? make_smem_desc_sw128(b_addr + k * 32, 16, 1024)
+                                                      : make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
+            }
+            umma_commit(&empty_bar[s]);
+            if (kc == args.k_chunks - 1) umma_commit(&tmem_full[acc]);
+            if (++s == NS) { s = 0; ph ^= 1; }
+          }
+          acc ^= 1; if (acc == 0) acc_ph ^= 1;
+        }
+      }
+    } else {
+      // ---------------- epilogue warps ----------------
+      const int q = warp & 3;                       // TMEM lane quarter this warp may access
+      const int row = q * 32 + lane;                // row inside the 128-row tile
+      const bool issuer = (threadIdx.x == 64);
+      int acc = 0; uint32_t acc_ph = 0, mask_ph = 0;
+      for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
+        if (MODE == MODE_NN && args.has_mask) {
+          if (issuer) {
+            mbar_arrive_expect_tx(mask_bar, (BN / 64) * 16384);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(s_staging + j * 16384, &tmMask, mask_bar, j * 64, tile * kBlockM);
+          }
+          mbar_wait(mask_bar, mask_ph);
+          mask_ph ^= 1;
+        }
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tcgen05_fence_after();
+        const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_base + c * 32, v);
+          tmem_ld_wait();
+          uint8_t* box = s_staging + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int lchunk = (c & 1) * 4 + cc;
+            uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
+            uint32_t packed[4];
+            uint4 mk = make_uint4(0, 0, 0, 0);
+            if (MODE == MODE_NN && args.has_mask) mk = *dst;
+            const uint32_t mkw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x0 = __uint_as_float(v[cc * 8 + 2 * e]);
+              float x1 = __uint_as_float(v[cc * 8 + 2 * e + 1]);
+              if (MODE == MODE_NT) {
+                x0 += s_bias[c * 32 + cc * 8 + 2 * e];
+                x1 += s_bias[c * 32 + cc * 8 + 2 * e + 1];
+                if (args.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              } else if (args.has_mask) {
+                // mask holds post-ReLU activations (>= 0): bf16 bit pattern != 0 (and not -0) <=> > 0
+                if ((mkw[e] & 0x7FFFu) == 0u) x0 = 0.f;
+                if ((mkw[e] & 0x7FFF0000u) == 0u) x1 = 0.f;
+              }
+              __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
+              packed[e] = *reinterpret_cast<uint32_t*>(&p);
+            }
+            *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+        }
+        // accumulator drained -> hand it back to the MMA warp
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1; if (acc == 0) acc_ph ^= 1;
+        // staged tile -> global (TMA store clips rows beyond M)
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);
+        if (issuer) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_store_2d(&tmD, s_staging + j * 16384, j * 64, tile * kBlockM);
+          tma_store_commit();
+          tma_store_wait_read0();
+        }
+        named_bar_sync(1, kEpiThreads);
+      }
+      if (issuer) tma_store_wait_all0();
+    }
+  } else {
+    // =====================================================================================
+    // TN: split-K weight gradient, one 128 x BN output tile per CTA
+    // =====================================================================================
+    const int m_tile = blockIdx.x % args.m_tiles;
+    const int split = blockIdx.x / args.m_tiles;
+    const int c0 = split * args.chunks_per_split;
+    const int c1 = min(c0 + args.chunks_per_split, args.k_chunks);
+    if (warp == 0) {
+      if (lane == 0) {
+        int s = 0; uint32_t ph = 0;
+        for (int kc = c0; kc < c1; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_s = s_stage + s * Cfg::kStageBytes;
+          uint8_t* b_s = a_s + kABytes;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(a_s, &tmA, &full_bar[s], m_tile * kBlockM, kc * kBlockK);          // [64 pts][64 out]
+          tma_load_2d(a_s + 8192, &tmA, &full_bar[s], m_tile * kBlockM + 64, kc * kBlockK);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_s + j * 8192, &tmB, &full_bar[s], j * 64, kc * kBlockK);
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 1, 1);
+        constexpr uint32_t idesc1 = make_idesc_bf16(kBlockM, 16, 1, 1);
+        const uint32_t ones_addr = smem_u32(s_staging);
+        int s = 0; uint32_t ph = 0;
+        for (int kc = c0; kc < c1; ++kc) {
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(s_stage + s * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
+            const uint64_t odesc = make_smem_desc_sw128(ones_addr, 8192, 1024);
+            const uint32_t accum = (kc != c0 || k != 0);
+            umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
+            umma_bf16(tmem_base + BN, adesc, odesc, idesc1, accum);      // column sums of A (bias gradient)
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full[0]);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      float* out = args.partial + (size_t)blockIdx.x * (kBlockM * (BN + 1));
+      if (c1 > c0) {
+        mbar_wait(&tmem_full[0], 0);
+        tcgen05_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_base + c * 32, v);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)row * BN + c * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                 __uint_as_float(v[4 * e + 3]));
+        }
+        uint32_t v16[16];
+        tmem_ld_x16(t_base + BN, v16);
+        tmem_ld_wait();
+        out[(size_t)kBlockM * BN + row] = __uint_as_float(v16[0]);
+      } else {
+        for (int c = 0; c < BN; ++c) out[(size_t)row * BN + c] = 0.f;
+        out[(size_t)kBlockM * BN + row] = 0.f;
+      }
+      tcgen05_fence_before();
+    }
+  }
+
+  // ---------------- teardown ----------------
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// dst[r*ld + c] = sum_s partial[(m_tile*? ...)]  -- deterministic split-K reduction + scatter into the
+// (unpadded) parameter-gradient layout.  Row r of the padded output maps to dst row r - row0.
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int m_tiles, int splits, int BN,
+                                     int row0, int nrows, int ncols, float* __restrict__ dst, int64_t dst_ld,
+                                     float* __restrict__ colsum_dst) {
+  const int total = nrows * ncols;
+  const size_t blk = (size_t)kBlockM * (BN + 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + nrows; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    if (i < total) {
+      if (!dst) continue;
+      const int r = row0 + i / ncols, c = i % ncols;
+      const int mt = r / kBlockM, rr = r % kBlockM;
+      for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * m_tiles + mt) * blk + (size_t)rr * BN + c];
+      dst[(int64_t)(i / ncols) * dst_ld + c] = acc;
+    } else {
+      if (!colsum_dst) continue;
+      const int r = row0 + (i - total);
+      const int mt = r / kBlockM, rr = r % kBlockM;
+      for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * m_tiles + mt) * blk + (size_t)kBlockM * BN + rr];
+      colsum_dst[i - total] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [outer][inner] with leading dimension ld (elements), box [box_outer][64], SWIZZLE_128B
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return RN_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) != 0 || inner == 0 || outer == 0) return RN_ERR_INVALID_ARG;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RN_OK : RN_ERR_DRIVER;
+}
+
+template <int BN, int MODE>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tM,
+                       const GemmArgs& args, int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    RN_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  gemm_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tA, tB, tD, tM, args);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int check_arch() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RN_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return RN_ERR_CUDA;
+    cached = (major == 10) ? RN_OK : RN_ERR_UNSUPPORTED_ARCH;
+  }
+  return cached;
+}
+
+// D[M,N] = act(A[M,K] B[N,K]^T + bias)        (forward layer)
+int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
+            const float* bias, int relu, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != RN_OK) return rc;
+  RN_REQUIRE(M > 0 && K > 0 && K % 8 == 0 && (N == 256 || N == 128 || N == 64));
+  CUtensorMap tA, tB, tD;
+  if ((rc = make_tmap(&tA, A, K, M, lda, kBlockM)) != RN_OK) return rc;
+  if ((rc = make_tmap(&tB, B, K, N, ldb, N)) != RN_OK) return rc;
+  if ((rc = make_tmap(&tD, D, N, M, ldd, kBlockM)) != RN_OK) return rc;
+  GemmArgs a{};
+  a.m_tiles = (int)ceil_div(M, kBlockM); a.k_chunks = (int)ceil_div(K, kBlockK); a.k_total = K; a.bias = bias; a.relu = relu;
+  const int grid = a.m_tiles < num_sms() ? a.m_tiles : num_sms();
+  if (N == 256) return launch_gemm<256, MODE_NT>(tA, tB, tD, tD, a, grid, st);
+  if (N == 128) return launch_gemm<128, MODE_NT>(tA, tB, tD, tD, a, grid, st);
+  return launch_gemm<64, MODE_NT>(tA, tB, tD, tD, a, grid, st);
+}
+
+// D[M,N] = (A[M,K] B[K,N]) .* (mask[M,N] > 0)   (data gradient; mask may be null)
+int gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
+            const void* mask, int64_t ldmask, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != RN_OK) return rc;
+  RN_REQUIRE(M > 0 && K > 0 && K % 8 == 0 && (N == 256 || N == 64));
+  CUtensorMap tA, tB, tD, tM;
+  if ((rc = make_tmap(&tA, A, K, M, lda, kBlockM)) != RN_OK) return rc;
+  if ((rc = make_tmap(&tB, B, N, K, ldb, 64)) != RN_OK) return rc;
+  if ((rc = make_tmap(&tD, D, N, M, ldd, kBlockM)) != RN_OK) return rc;
+  tM = tD;
+  if (mask && (rc = make_tmap(&tM, mask, N, M, ldmask, kBlockM)) != RN_OK) return rc;
+  GemmArgs a{};
+  a.m_tiles = (int)ceil_div(M, kBlockM); a.k_chunks = (int)ceil_div(K, kBlockK); a.k_total = K; a.has_mask = mask != nullptr;
+  const int grid = a.m_tiles < num_sms() ? a.m_tiles : num_sms();
+  if (N == 256) return launch_gemm<256, MODE_NN>(tA, tB, tD, tM, a, grid, st);
+  return launch_gemm<64, MODE_NN>(tA, tB, tD, tM, a, grid, st);
+}
+
+size_t gemm_tn_scratch_bytes() { return (size_t)(num_sms() + 8) * kBlockM * 257 * sizeof(float); }
+
+// Weight / bias gradient: partial[split][m_tile] = A[Kslice, Mo]^T B[Kslice, N] (+ column sums of A),
+// then gemm_tn_reduce sums the splits in a fixed order and scatters rows [row0,row0+nrows) x first
+// ncols columns into dst (leading dimension dst_ld) and the column sums into colsum_dst.
+int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ldb, int N, int64_t K, float* scratch,
+                   size_t scratch_bytes, TnInfo* info, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != RN_OK) return rc;
+  RN_REQUIRE(K > 0 && Mo > 0 && (N == 256 || N == 64) && scratch && info);
+  CUtensorMap tA, tB;
+  if ((rc = make_tmap(&tA, A, Mo, K, lda, 64)) != RN_OK) return rc;
+  if ((rc = make_tmap(&tB, B, N, K, ldb, 64)) != RN_OK) return rc;
+  GemmArgs a{};
+  a.m_tiles = (int)ceil_div(Mo, kBlockM);
+  a.k_chunks = (int)ceil_div(K, kBlockK);
+  a.k_total = (int)(K > 0x7fffffff ? 0x7fffffff : K);
+  int splits = num_sms() / a.m_tiles;
+  if (splits > a.k_chunks) splits = a.k_chunks;
+  if (splits < 1) splits = 1;
+  a.chunks_per_split = (int)ceil_div(a.k_chunks, splits);
+  a.splits = (int)ceil_div(a.k_chunks, a.chunks_per_split);
+  a.partial = scratch;
+  RN_REQUIRE((size_t)a.splits * a.m_tiles * kBlockM * (N + 1) * sizeof(float) <= scratch_bytes);
+  const int grid = a.m_tiles * a.splits;
+  if (N == 256) rc = launch_gemm<256, MODE_TN>(tA, tB, tA, tA, a, grid, st);
+  else rc = launch_gemm<64, MODE_TN>(tA, tB, tA, tA, a, grid, st);
+  info->m_tiles = a.m_tiles; info->splits = a.splits; info->N = N; info->scratch = scratch;
+  return rc;
+}
+
+int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int ncols, float* dst, int64_t dst_ld, float* colsum_dst,
+                   cudaStream_t st) {
+  RN_REQUIRE(row0 >= 0 && nrows > 0 && ncols > 0 && ncols <= info.N && row0 + nrows <= info.m_tiles * kBlockM);
+  const int total = nrows * ncols + nrows;
+  splitk_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(info.scratch, info.m_tiles, info.splits, info.N, row0, nrows,
+                                                            ncols, dst, dst_ld, colsum_dst);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" {
+
+size_t rn_gemm_scratch_bytes(void) { return gemm_tn_scratch_bytes(); }
+
+int rn_gemm_bf16(int mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N,
+                 int64_t K, const float* bias, int relu, const void* mask, int64_t ldmask, float* colsum_out, void* scratch,
+                 size_t scratch_bytes, rn_stream_t stream) {
+  RN_REQUIRE(A && B && D);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == MODE_NT) return gemm_nt(A, lda, B, ldb, D, ldd, M, N, (int)K, bias, relu, st);
+  if (mode == MODE_NN) return gemm_nn(A, lda, B, ldb, D, ldd, M, N, (int)K, mask, ldmask, st);
+  if (mode == MODE_TN) {
+    TnInfo info;
+    int rc = gemm_tn_launch(A, lda, (int)M, B, ldb, N, K, (float*)scratch, scratch_bytes, &info, st);
+    if (rc != RN_OK) return rc;
+    return gemm_tn_reduce(info, 0, (int)M, N, (float*)D, ldd, colsum_out, st);
+  }
+  return RN_ERR_INVALID_ARG;
+}
+
+}  // extern "C"

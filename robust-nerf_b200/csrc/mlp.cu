@@ -1,0 +1,176 @@
+// mlp.cu -- host-side orchestration of the NeRF MLP forward / backward
+// (noisy_src/model.py:145-196 and its autograd backward) as a chain of tcgen05 GEMM launches over
+// bf16 activation buffers that stay resident in HBM between forward and backward.
+//
+// Forward (per network, M points):
+//   encode      pts -> XC[:, 0:64] (PE, bf16)   dirs -> FD[:, 256:320]
+//   L0          XC[:, 0:64]  x W0p^T  -> H0            (K=64)
+//   L1..L3      H(l-1)       x Wl^T   -> Hl
+//   L4          H3           x W4^T   -> XC[:, 64:320] (the skip concat is a column offset, no copy)
+//   L5          XC[:, 0:320] x W5p^T  -> H5            (K=320)
+//   L6, L7      ...                   -> H7
+//   feature     H7 x WFS[0:256]^T     -> FD[:, 0:256]  (no activation)
+//   dir         FD[:, 0:320] x WD^T   -> HC            (N=128, K=320)
+//   heads       (H7 . w_sigma, HC . W_rgb) -> raw[M,4]  (fp32 CUDA cores)
+// Backward mirrors it: heads_bwd, then per layer one TN GEMM (weight + bias gradient, split-K over
+// points) and one NN GEMM (data gradient with the ReLU mask of the layer input fused in).
+#include "common.cuh"
+#include "gemm.h"
+#include "mlp_layout.h"
+
+namespace rn {
+using namespace layout;
+typedef __nv_bfloat16 bf16;
+
+struct TrainWs {
+  bf16 *XC, *H[8], *FD, *HC, *dHC, *dFS, *dA, *dB, *dXE0, *dXE5, *dDE;
+  float* scratch;
+  size_t scratch_bytes;
+  float* heads_scratch;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t workspace_bytes(int64_t M, int training) {
+  const size_t elems = training ? (size_t)(kTrainFwdElems + kTrainBwdElems) : (size_t)kInferElems;
+  size_t b = align_up((size_t)M * elems * 2, 256);
+  if (training) b += align_up(gemm_tn_scratch_bytes(), 256) + align_up(heads_bwd_scratch_bytes(M), 256);
+  return b + 256;
+}
+
+static void carve_train(void* ws, int64_t M, TrainWs* w) {
+  bf16* p = reinterpret_cast<bf16*>(align_up(reinterpret_cast<uintptr_t>(ws), 256));
+  auto take = [&](int width) { bf16* r = p; p += (size_t)M * width; return r; };
+  w->XC = take(320);
+  w->H[0] = take(256); w->H[1] = take(256); w->H[2] = take(256); w->H[3] = take(256);
+  w->H[4] = w->XC + 64;                           // H4 lives in XC[:, 64:320] (ld 320)
+  w->H[5] = take(256); w->H[6] = take(256); w->H[7] = take(256);
+  w->FD = take(320); w->HC = take(128);
+  w->dHC = take(128); w->dFS = take(272); w->dA = take(256); w->dB = take(256);
+  w->dXE0 = take(64); w->dXE5 = take(64); w->dDE = take(64);
+  uint8_t* q = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(p), 256));
+  w->scratch = reinterpret_cast<float*>(q);
+  w->scratch_bytes = gemm_tn_scratch_bytes();
+  w->heads_scratch = reinterpret_cast<float*>(q + align_up(w->scratch_bytes, 256));
+}
+
+static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimension of H[l]
+
+#define RN_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != RN_OK) return _rc; \
+  } while (0)
+
+static int mlp_forward(const void* packed, const float* pts, const float* dirs, int64_t M, int group, void* ws,
+                       int training, float* raw, cudaStream_t st) {
+  const bf16* W = reinterpret_cast<const bf16*>(packed);
+  const float* F = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kBf16Bytes);
+  bf16 *XC, *H[8], *FD, *HC;
+  if (training) {
+    TrainWs w;
+    carve_train(ws, M, &w);
+    XC = w.XC; FD = w.FD; HC = w.HC;
+    for (int i = 0; i < 8; ++i) H[i] = w.H[i];
+  } else {
+    bf16* p = reinterpret_cast<bf16*>(align_up(reinterpret_cast<uintptr_t>(ws), 256));
+    XC = p; p += (size_t)M * 320;
+    bf16* HA = p; p += (size_t)M * 256;
+    bf16* HB = p; p += (size_t)M * 256;
+    FD = p; p += (size_t)M * 320;
+    HC = p;
+    H[0] = HA; H[1] = HB; H[2] = HA; H[3] = HB; H[4] = XC + 64; H[5] = HA; H[6] = HB; H[7] = HA;
+  }
+  RN_TRY(launch_encode(pts, dirs, M, group, XC, 320, FD, 320, st));
+  RN_TRY(gemm_nt(XC, 320, W + kW0, 64, H[0], 256, M, 256, 64, F + kB0, 1, st));
+  for (int l = 1; l < 8; ++l) {
+    const bf16* in = (l == 5) ? XC : H[l - 1];
+    const int K = (l == 5) ? 320 : 256;
+    const int ldin = (l == 5) ? 320 : ld_of(l - 1);
+    RN_TRY(gemm_nt(in, ldin, W + trunk_w(l), K, H[l], ld_of(l), M, 256, K, F + kB0 + 256 * l, 1, st));
+  }
+  RN_TRY(gemm_nt(H[7], 256, W + kWFS, 256, FD, 320, M, 256, 256, F + kBF, 0, st));
+  RN_TRY(gemm_nt(FD, 320, W + kWD, 320, HC, 128, M, 128, 320, F + kBD, 1, st));
+  RN_TRY(launch_heads_fwd(H[7], HC, M, F, raw, st));
+  return RN_OK;
+}
+
+static int mlp_backward(const void* packed, const float* pts, const float* dirs, int64_t M, int group, void* ws,
+                        const float* g_raw, float* G, float* g_pts, float* g_dirs, cudaStream_t st) {
+  const bf16* W = reinterpret_cast<const bf16*>(packed);
+  const float* F = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kBf16Bytes);
+  TrainWs w;
+  carve_train(ws, M, &w);
+  const bool need_in = (g_pts != nullptr) || (g_dirs != nullptr);
+  TnInfo ti;
+  // heads: dHC, dFS[:, 256:272], rgb_linear grads
+  RN_TRY(launch_heads_bwd(g_raw, w.HC, M, F, w.dHC, w.dFS, 272, w.heads_scratch, G + kG_WRgb, G + kG_BRgb, st));
+  // dir_linear: weight grads over [feat(256) | d_enc(27)] and bias
+  RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 256, M, w.scratch, w.scratch_bytes, &ti, st));
+  RN_TRY(gemm_tn_reduce(ti, 0, 128, 256, G + kG_WD, 283, G + kG_BD, st));
+  RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD + 256, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
+  RN_TRY(gemm_tn_reduce(ti, 0, 128, 27, G + kG_WD + 256, 283, nullptr, st));
+  // d feat = dHC x WD[:, 0:256]  -> dFS[:, 0:256]   (feature_linear has no activation: no mask)
+  RN_TRY(gemm_nn(w.dHC, 128, W + kWD, 320, w.dFS, 272, M, 256, 128, nullptr, 0, st));
+  if (g_dirs) RN_TRY(gemm_nn(w.dHC, 128, W + kWD + 256, 320, w.dDE, 64, M, 64, 128, nullptr, 0, st));
+  // feature_linear + sigma_linear (row 256 of dFS^T): weights, biases
+  RN_TRY(gemm_tn_launch(w.dFS, 272, 272, w.H[7], 256, 256, M, w.scratch, w.scratch_bytes, &ti, st));
+  RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + kG_WF, 256, G + kG_BF, st));
+  RN_TRY(gemm_tn_reduce(ti, 256, 1, 256, G + kG_WSig, 256, G + kG_BSig, st));
+  // dH7 = [dF | dsigma] x WFS, masked by H7 > 0
+  RN_TRY(gemm_nn(w.dFS, 272, W + kWFS, 256, w.dA, 256, M, 256, 272, w.H[7], 256, st));
+  bf16* dY = w.dA;
+  bf16* dN = w.dB;
+  for (int l = 7; l >= 1; --l) {
+    if (l == 5) {
+      // input = XC = [x_enc(64) | H4(256)]
+      RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC + 64, 320, 256, M, w.scratch, w.scratch_bytes, &ti, st));
+      RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5), st));
+      RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
+      RN_TRY(gemm_tn_reduce(ti, 0, 256, 63, G + trunk_gw(5), 319, nullptr, st));
+      RN_TRY(gemm_nn(dY, 256, W + kW5 + 64, 320, dN, 256, M, 256, 256, w.XC + 64, 320, st));
+      if (need_in) RN_TRY(gemm_nn(dY, 256, W + kW5, 320, w.dXE5, 64, M, 64, 256, nullptr, 0, st));
+    } else {
+      const bf16* in = w.H[l - 1];
+      const int ldin = ld_of(l - 1);
+      RN_TRY(gemm_tn_launch(dY, 256, 256, in, ldin, 256, M, w.scratch, w.scratch_bytes, &ti, st));
+      RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + trunk_gw(l), 256, G + trunk_gb(l), st));
+      RN_TRY(gemm_nn(dY, 256, W + trunk_w(l), 256, dN, 256, M, 256, 256, in, ldin, st));
+    }
+    bf16* t = dY; dY = dN; dN = t;
+  }
+  // layer 0: input = x_enc
+  RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
+  RN_TRY(gemm_tn_reduce(ti, 0, 256, 63, G + trunk_gw(0), 63, G + trunk_gb(0), st));
+  if (need_in) {
+    RN_TRY(gemm_nn(dY, 256, W + kW0, 64, w.dXE0, 64, M, 64, 256, nullptr, 0, st));
+    if (!g_pts) { /* dirs only */ }
+    RN_TRY(launch_encode_bwd(pts, dirs, M, group, w.dXE0, w.dXE5, w.dDE, g_pts, g_dirs, st));
+  }
+  return RN_OK;
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" {
+
+size_t rn_mlp_workspace_bytes(int64_t M, int training) { return M > 0 ? workspace_bytes(M, training) : 0; }
+
+int rn_mlp_fwd(const void* packed, const float* pts, const float* dirs, int64_t M, int dir_group, void* workspace,
+               int training, float* raw_out, rn_stream_t stream) {
+  RN_REQUIRE(packed && pts && dirs && workspace && raw_out && M >= 0 && dir_group >= 1 && M % dir_group == 0);
+  if (M == 0) return RN_OK;
+  RN_TRY(check_arch());
+  return mlp_forward(packed, pts, dirs, M, dir_group, workspace, training, raw_out, (cudaStream_t)stream);
+}
+
+int rn_mlp_bwd(const void* packed, const float* pts, const float* dirs, int64_t M, int dir_group, void* workspace,
+               const float* g_raw, float* grad_flat, float* g_pts, float* g_dirs, rn_stream_t stream) {
+  RN_REQUIRE(packed && pts && dirs && workspace && g_raw && grad_flat && M > 0 && dir_group >= 1 && M % dir_group == 0);
+  RN_TRY(check_arch());
+  return mlp_backward(packed, pts, dirs, M, dir_group, workspace, g_raw, grad_flat, g_pts, g_dirs, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// sampling.cu -- stratified sampling, inverse-CDF (hierarchical) resampling, point generation.
+//
+// Replaces noisy_src/rays.py:145-210 (sample_along_rays), :213-279 (sample_pdf) and
+// :282-333 (sample_hierarchical): ~35 aten launches (linspace/cat/rand-mul-add, sum, div, cumsum,
+// searchsorted, clamp, gather x2, where, sort, broadcast mul-add) become one launch each.
+//
+// sample_pdf / sample_hierarchical are warp-per-ray kernels: the ray's bins, cdf and merge buffer
+// live in shared memory, each lane inverts the cdf for Nf/32 draws with a binary search
+// (searchsorted right=True semantics), and the 32 lanes sort the merged depths with a bitonic
+// network.  The cdf is built with SEQUENTIAL fp32 adds (the order oracle/nerf_oracle.py defines) so
+// sample indices are bit-exact against the oracle; all interpolation arithmetic is unfused
+// (__fmul_rn/__fadd_rn) to reproduce the reference's separate mul/add roundings.
+//
+// HBM-bound: 20*Nc+24 B/ray (stratified), 24*Nc+20*Nf+24 B/ray (hierarchical incl. pts).
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace rn {
+
+// ------------------------------------------------------------------------------------------
+// stratified: z = lower + (upper - lower) * t_rand ; pts = o + d*z         (rays.py:197-208)
+// ------------------------------------------------------------------------------------------
+__global__ void stratified_kernel(const float* __restrict__ ro, const float* __restrict__ rd, int64_t B,
+                                  const float* __restrict__ zb, int Nc, const float* __restrict__ t_rand,
+                                  float* __restrict__ z_out, float* __restrict__ pts) {
+  const int64_t n = B * Nc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / Nc;
+    const int s = (int)(i - b * Nc);
+    float z = __ldg(zb + s);
+    if (t_rand) {
+      const float lower = (s == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, __ldg(zb + s - 1)));
+      const float upper = (s == Nc - 1) ? z : __fmul_rn(0.5f, __fadd_rn(__ldg(zb + s + 1), z));
+      z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldcs(t_rand + i)));
+    }
+    z_out[i] = z;
+    if (pts) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        pts[i * 3 + k] = __fadd_rn(__ldg(ro + b * 3 + k), __fmul_rn(__ldg(rd + b * 3 + k), z));
+    }
+  }
+}
+
+__global__ void points_fwd_kernel(const float* __restrict__ ro, const float* __restrict__ rd,
+                                  const float* __restrict__ z, int64_t B, int S, float* __restrict__ pts) {
+  const int64_t n = B * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / S;
+    const float zz = z[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      pts[i * 3 + k] = __fadd_rn(__ldg(ro + b * 3 + k), __fmul_rn(__ldg(rd + b * 3 + k), zz));
+  }
+}
+
+// g_o[b] = sum_s g_pts[b,s,:], g_d[b] = sum_s z[b,s] * g_pts[b,s,:]   (warp per ray)
+__global__ void points_bwd_kernel(const float* __restrict__ g_pts, const float* __restrict__ z, int64_t B, int S,
+                                  float* __restrict__ g_o, float* __restrict__ g_d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < B; b += nwarps) {
+    float ao[3] = {0.f, 0.f, 0.f}, ad[3] = {0.f, 0.f, 0.f};
+    for (int s = lane; s < S; s += 32) {
+      const float zz = z[b * S + s];
+      const float* g = g_pts + (b * S + s) * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const float v = g[k]; ao[k] += v; ad[k] = fmaf(zz, v, ad[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ao[k] = warp_sum(ao[k]); ad[k] = warp_sum(ad[k]); }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { g_o[b * 3 + k] = ao[k]; g_d[b * 3 + k] = ad[k]; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// warp-level pieces of sample_pdf
+// ------------------------------------------------------------------------------------------
+// s_w[0..nb-2] holds raw weights on entry; on exit s_cdf[0..nb-1] holds the cdf (s_cdf[0]=0).
+__device__ __forceinline__ void warp_build_cdf(float* s_w, float* s_cdf, int nb, int lane) {
+  const int nw = nb - 1;
+  for (int k = lane; k < nw; k += 32) s_w[k] = __fadd_rn(s_w[k], 1e-5f);      // rays.py:243
+  __syncwarp();
+  if (lane == 0) {
+    float tot = s_w[0];
+    for (int k = 1; k < nw; ++k) tot = __fadd_rn(tot, s_w[k]);                // sequential sum (oracle order)
+    s_cdf[0] = tot;                                                           // stash
+  }
+  __syncwarp();
+  const float tot = s_cdf[0];
+  __syncwarp();
+  for (int k = lane; k < nw; k += 32) s_w[k] = __fdiv_rn(s_w[k], tot);        // pdf, rays.py:246
+  __syncwarp();
+  if (lane == 0) {
+    float acc = 0.f;
+    s_cdf[0] = 0.f;
+    for (int k = 0; k < nw; ++k) { acc = __fadd_rn(acc, s_w[k]); s_cdf[k + 1] = acc; }  // sequential cumsum
+  }
+  __syncwarp();
+}
+
+// one draw: searchsorted(right=True) + clamp + gather + interpolation (rays.py:259-277)
+__device__ __forceinline__ float invert_cdf(const float* s_cdf, const float* s_bins, int nb, float u, int& ind) {
+  int lo = 0, hi = nb;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s_cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  ind = lo;
+  const int below = max(lo - 1, 0), above = min(lo, nb - 1);
+  const float cb = s_cdf[below], ca = s_cdf[above], bb = s_bins[below], ba = s_bins[above];
+  float denom = __fsub_rn(ca, cb);
+  if (denom < 1e-5f) denom = 1.0f;
+  const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+  return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+}
+
+// bitonic sort of s[0..P) (P power of two) by one warp, ascending
+__device__ __forceinline__ void warp_bitonic_sort(float* s, int P, int lane) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (P >> 1); t += 32) {
+        // t-th compare-exchange pair of this stage
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const bool up = ((i & k) == 0);
+        const float a = s[i], b = s[p];
+        if ((a > b) == up) { s[i] = b; s[p] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+constexpr int kWarpsPerCta = 8;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, int64_t B, int nb,
+                  const float* __restrict__ u, int64_t u_stride, int Nf, float* __restrict__ samples,
+                  int64_t* __restrict__ inds_out) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* s_bins = smem + (size_t)w * (3 * nb);
+  float* s_w = s_bins + nb;
+  float* s_cdf = s_w + nb;
+  for (int64_t b = blockIdx.x * (int64_t)kWarpsPerCta + w; b < B; b += (int64_t)gridDim.x * kWarpsPerCta) {
+    for (int k = lane; k < nb; k += 32) s_bins[k] = bins[b * nb + k];
+    for (int k = lane; k < nb - 1; k += 32) s_w[k] = weights[b * (nb - 1) + k];
+    __syncwarp();
+    warp_build_cdf(s_w, s_cdf, nb, lane);
+    for (int j = lane; j < Nf; j += 32) {
+      int ind;
+      const float v = invert_cdf(s_cdf, s_bins, nb, u[b * u_stride + j], ind);
+      samples[b * Nf + j] = v;
+      if (inds_out) inds_out[b * Nf + j] = ind;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict__ rd,
+                           const float* __restrict__ zc, const float* __restrict__ weights, int64_t B, int Nc,
+                           const float* __restrict__ u, int64_t u_stride, int Nf, int P,
+                           float* __restrict__ z_all, float* __restrict__ pts, int64_t* __restrict__ inds_out) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nb = Nc - 1, Nt = Nc + Nf;
+  float* s_bins = smem + (size_t)w * (3 * Nc + P);
+  float* s_w = s_bins + Nc;
+  float* s_cdf = s_w + Nc;
+  float* s_sort = s_cdf + Nc;
+  for (int64_t b = blockIdx.x * (int64_t)kWarpsPerCta + w; b < B; b += (int64_t)gridDim.x * kWarpsPerCta) {
+    // coarse depths -> sort buffer; mid-point bins; interior weights (rays.py:316-321)
+    for (int k = lane; k < Nc; k += 32) s_sort[k] = __ldcs(zc + b * Nc + k);
+    for (int k = Nt + lane; k < P; k += 32) s_sort[k] = CUDART_INF_F;
+    for (int k = lane; k < Nc - 2; k += 32) s_w[k] = __ldcs(weights + b * Nc + k + 1);
+    __syncwarp();
+    for (int k = lane; k < nb; k += 32) s_bins[k] = __fmul_rn(0.5f, __fadd_rn(s_sort[k + 1], s_sort[k]));
+    __syncwarp();
+    warp_build_cdf(s_w, s_cdf, nb, lane);
+    for (int j = lane; j < Nf; j += 32) {
+      int ind;
+      s_sort[Nc + j] = invert_cdf(s_cdf, s_bins, nb, __ldg(u + b * u_stride + j), ind);
+      if (inds_out) inds_out[b * Nf + j] = ind;
+    }
+    __syncwarp();
+    warp_bitonic_sort(s_sort, P, lane);                                       // rays.py:328 (values only)
+    for (int k = lane; k < Nt; k += 32) z_all[b * Nt + k] = s_sort[k];
+    if (pts) {
+      const float o0 = ro[b * 3], o1 = ro[b * 3 + 1], o2 = ro[b * 3 + 2];
+      const float d0 = rd[b * 3], d1 = rd[b * 3 + 1], d2 = rd[b * 3 + 2];
+      // 3*Nt contiguous floats per ray: lane-strided so the stores coalesce
+      for (int e = lane; e < 3 * Nt; e += 32) {
+        const int s = e / 3, k = e - 3 * s;
+        const float o = k == 0 ? o0 : (k == 1 ? o1 : o2), d = k == 0 ? d0 : (k == 1 ? d1 : d2);
+        pts[(b * Nt) * 3 + e] = __fadd_rn(o, __fmul_rn(d, s_sort[s]));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" {
+
+int rn_stratified_fwd(const float* ro, const float* rd, int64_t B, const float* zb, int Nc, const float* t_rand,
+                      float* z_out, float* pts, rn_stream_t stream) {
+  RN_REQUIRE(zb && z_out && B >= 0 && Nc >= 1 && (!pts || (ro && rd)));
+  if (B == 0) return RN_OK;
+  stratified_kernel<<<grid_for(B * Nc, 256), 256, 0, (cudaStream_t)stream>>>(ro, rd, B, zb, Nc, t_rand, z_out, pts);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_points_fwd(const float* ro, const float* rd, const float* z, int64_t B, int S, float* pts, rn_stream_t stream) {
+  RN_REQUIRE(ro && rd && z && pts && B >= 0 && S >= 1);
+  if (B == 0) return RN_OK;
+  points_fwd_kernel<<<grid_for(B * S, 256), 256, 0, (cudaStream_t)stream>>>(ro, rd, z, B, S, pts);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_points_bwd(const float* g_pts, const float* z, int64_t B, int S, float* g_o, float* g_d, rn_stream_t stream) {
+  RN_REQUIRE(g_pts && z && g_o && g_d && B >= 0 && S >= 1);
+  if (B == 0) return RN_OK;
+  points_bwd_kernel<<<grid_for(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(g_pts, z, B, S, g_o, g_d);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_sample_pdf_fwd(const float* bins, const float* weights, int64_t B, int nb, const float* u, int64_t u_stride,
+                      int Nf, float* samples, int64_t* inds_out, rn_stream_t stream) {
+  RN_REQUIRE(bins && weights && u && samples && B >= 0 && nb >= 2 && Nf >= 1 && nb <= 4096);
+  if (B == 0) return RN_OK;
+  const size_t smem = (size_t)kWarpsPerCta * 3 * nb * sizeof(float);
+  if (smem > 48 * 1024)
+    RN_CUDA_CHECK(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)(ceil_div(B, kWarpsPerCta) < (int64_t)num_sms() * 8 ? ceil_div(B, kWarpsPerCta) : (int64_t)num_sms() * 8);
+  sample_pdf_kernel<<<grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(bins, weights, B, nb, u, u_stride, Nf, samples,
+                                                                            inds_out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_sample_hierarchical_fwd(const float* ro, const float* rd, const float* zc, const float* weights, int64_t B, int Nc,
+                               const float* u, int64_t u_stride, int Nf, float* z_all, float* pts, int64_t* inds_out,
+                               rn_stream_t stream) {
+  RN_REQUIRE(zc && weights && u && z_all && B >= 0 && Nc >= 3 && Nf >= 1 && (!pts || (ro && rd)));
+  if (B == 0) return RN_OK;
+  int P = 2;
+  while (P < Nc + Nf) P <<= 1;
+  const size_t smem = (size_t)kWarpsPerCta * (3 * Nc + P) * sizeof(float);
+  RN_REQUIRE(smem <= 200 * 1024);
+  if (smem > 48 * 1024)
+    RN_CUDA_CHECK(cudaFuncSetAttribute(sample_hierarchical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)(ceil_div(B, kWarpsPerCta) < (int64_t)num_sms() * 8 ? ceil_div(B, kWarpsPerCta) : (int64_t)num_sms() * 8);
+  sample_hierarchical_kernel<<<grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(ro, rd, zc, weights, B, Nc, u, u_stride,
+                                                                                     Nf, P, z_all, pts, inds_out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+"""Training / full-image entry points of the hot path.
+
+* `train_step`, `train_step_with_poses`, `render_image`, `render_image_with_pose` keep the
+  reference's signatures and metric dictionaries (noisy_src/train.py:68-160,
+  noisy_src/train_pose_opt.py:290-470) -- thin callers over the kernel path.
+* `Trainer` is the B200-first step: parameters, gradients and Adam moments of both networks live
+  in flat fp32 buffers (the nn.Parameters are views, so state_dict / checkpoints are unchanged),
+  the batch is sharded data-parallel with ONE NCCL all-reduce per step over the flat gradient
+  buffer [grad coarse | grad fine | grad omega | grad delta_t] placed before the clip (so the
+  clip sees the global-batch gradient, like a single-GPU run), and clip_grad_norm_ + Adam is
+  one fused kernel over the same buffer.  No host synchronisation inside a step.
+* `render_views_sharded` shards test-view rendering by ray tile, no collective.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops, _lib as L
+from ._lib import call, ptr, stream_ptr
+from .config import RenderConfig
+from .model import NeRF
+from .rays import get_ray_directions, get_rays
+from .rendering import NeRFRenderer, render_rays
+from .parallel import allreduce_mean_, tiles_for_rank
+
+
+def compute_psnr(pred: torch.Tensor, target: torch.Tensor, max_val: float = 1.0) -> torch.Tensor:
+    """noisy_src/metrics.py:15-40."""
+    mse = torch.mean((pred - target) ** 2)
+    return 20.0 * torch.log10(torch.tensor(max_val, device=mse.device)) - 10.0 * torch.log10(mse)
+
+
+class _MSE(torch.autograd.Function):
+    """mean((rgb - target)^2) with its gradient produced in the same launch."""
+
+    @staticmethod
+    def forward(ctx, rgb_map, target):
+        loss = torch.zeros(1, device=rgb_map.device)
+        g = ops.mse_loss_and_grad(rgb_map, target, loss, 1.0, want_grad=True)
+        ctx.save_for_backward(g)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, go):
+        (g,) = ctx.saved_tensors
+        return g * go, None
+
+
+def mse_loss(rgb_map, target):
+    return _MSE.apply(rgb_map, target)
+
+
+def _losses(outputs, target_rgb):
+    loss_coarse = mse_loss(outputs["rgb_coarse"], target_rgb)
+    loss_fine = mse_loss(outputs["rgb_fine"], target_rgb) if "rgb_fine" in outputs else None
+    return loss_coarse, loss_fine
+
+
+def train_step(renderer: NeRFRenderer, optimizer: torch.optim.Optimizer, batch: Dict[str, torch.Tensor]) -> Dict[str, float]:
+    """Clean-pose step with the reference's semantics (noisy_src/train.py:68-119): joint clip at 1.0."""
+    optimizer.zero_grad()
+    outputs = renderer(batch["rays_o"], batch["rays_d"], is_train=True)
+    target = batch["target_rgb"]
+    loss_c, loss_f = _losses(outputs, target)
+    loss = loss_c if loss_f is None else loss_c + loss_f
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(renderer.parameters(), max_norm=1.0)
+    optimizer.step()
+    # one host sync for all metrics (the reference does five .item() calls)
+    vals = torch.stack([loss_c.detach(), (loss_f if loss_f is not None else loss_c).detach(), loss.detach()]).tolist()
+    psnr = lambda m: float("inf") if m == 0 else -10.0 * torch.log10(torch.tensor(m)).item()
+    metrics = {"loss_coarse": vals[0], "psnr_coarse": psnr(vals[0])}
+    if loss_f is not None:
+        metrics.update(loss_fine=vals[1], psnr_fine=psnr(vals[1]), psnr=psnr(vals[1]))
+    else:
+        metrics.update(loss_fine=None, psnr=metrics["psnr_coarse"])
+    metrics["loss"] = vals[2]
+    return metrics
+
+
+def train_step_with_poses(model_coarse: NeRF, model_fine: Optional[NeRF], camera_params, pixel_sampler,
+                          optimizer_nerf: torch.optim.Optimizer, optimizer_poses: Optional[torch.optim.Optimizer],
+                          pixel_batch, render_config: RenderConfig, optimize_poses: bool = True,
+                          rotation_reg_weight: float = 0.0, translation_reg_weight: float = 0.0) -> Dict[str, float]:
+    """Joint NeRF + pose step (noisy_src/train_pose_opt.py:290-411): per-net clip 1.0, pose clip 0.1."""
+    optimizer_nerf.zero_grad()
+    if optimizer_poses is not None and optimize_poses:
+        optimizer_poses.zero_grad()
+    rays_o, rays_d = pixel_sampler.get_rays_for_batch_fused(pixel_batch, camera_params)
+    outputs = render_rays(model_coarse, model_fine, rays_o, rays_d, render_config, is_train=True)
+    loss_c, loss_f = _losses(outputs, pixel_batch.target_rgb)
+    loss = loss_c if loss_f is None else loss_c + loss_f
+    extras = {}
+    if optimize_poses and (rotation_reg_weight > 0 or translation_reg_weight > 0):
+        reg = 0.0
+        if rotation_reg_weight > 0 and camera_params.learn_rotation:
+            r = torch.mean(camera_params.rotation_deltas ** 2)
+            reg = reg + rotation_reg_weight * r
+            extras["rotation_reg"] = r.detach()
+        if translation_reg_weight > 0 and camera_params.learn_translation:
+            t = torch.mean(camera_params.translation_deltas ** 2)
+            reg = reg + translation_reg_weight * t
+            extras["translation_reg"] = t.detach()
+        loss = loss + reg
+        extras["pose_reg_loss"] = reg.detach() if isinstance(reg, torch.Tensor) else torch.tensor(float(reg))
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model_coarse.parameters(), max_norm=1.0)
+    if model_fine is not None:
+        torch.nn.utils.clip_grad_norm_(model_fine.parameters(), max_norm=1.0)
+    if optimize_poses and optimizer_poses is not None:
+        torch.nn.utils.clip_grad_norm_(camera_params.parameters(), max_norm=0.1)
+    optimizer_nerf.step()
+    if optimizer_poses is not None and optimize_poses:
+        optimizer_poses.step()
+    names = ["loss_coarse", "loss_fine", "loss"] + list(extras)
+    vals = torch.stack([loss_c.detach(), (loss_f if loss_f is not None else loss_c).detach(), loss.detach()]
+                       + [v.to(loss.device) for v in extras.values()]).tolist()
+    m = dict(zip(names, vals))
+    psnr = lambda x: float("inf") if x == 0 else -10.0 * torch.log10(torch.tensor(x)).item()
+    m["psnr_coarse"] = psnr(m["loss_coarse"])
+    if loss_f is not None:
+        m["psnr_fine"] = psnr(m["loss_fine"])
+        m["psnr"] = m["psnr_fine"]
+    else:
+        m["loss_fine"] = None
+        m["psnr"] = m["psnr_coarse"]
+    return m
+
+
+@torch.no_grad()
+def render_image(renderer: NeRFRenderer, pose: torch.Tensor, H: int, W: int, focal: float,
+                 chunk_size: int = 1024 * 4) -> Dict[str, torch.Tensor]:
+    """noisy_src/train.py:122-160 (results are chunk-invariant in eval mode; larger chunks are faster)."""
+    directions = get_ray_directions(H, W, focal, device=pose.device)
+    rays_o, rays_d = get_rays(directions, pose)
+    out = renderer(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), chunk_size=chunk_size, is_train=False)
+    k = "fine" if "rgb_fine" in out else "coarse"
+    return {"rgb": out[f"rgb_{k}"].reshape(H, W, 3), "depth": out[f"depth_{k}"].reshape(H, W),
+            "acc": out[f"acc_{k}"].reshape(H, W)}
+
+
+@torch.no_grad()
+def render_image_with_pose(model_coarse: NeRF, model_fine: Optional[NeRF], pose: torch.Tensor, H: int, W: int,
+                           focal: float, render_config: RenderConfig, chunk_size: int = 1024 * 4) -> Dict[str, torch.Tensor]:
+    """noisy_src/train_pose_opt.py:414-470."""
+    return render_image(NeRFRenderer(model_coarse, model_fine, render_config), pose, H, W, focal, chunk_size)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200-first trainer
+# ------------------------------------------------------------------------------------------------
+def _flatten_into(params: Sequence[nn.Parameter], flat: torch.Tensor, gflat: torch.Tensor, off: int) -> int:
+    """Re-point every parameter (and its .grad) at a slice of the flat buffers; values preserved."""
+    for p in params:
+        n = p.numel()
+        flat[off:off + n].copy_(p.data.reshape(-1))
+        p.data = flat[off:off + n].view(p.shape)
+        p.grad = gflat[off:off + n].view(p.shape)
+        off += n
+    return off
+
+
+class Trainer:
+    """Fused render+train step with optional data parallelism.
+
+    clean mode  : step_rays(rays_o, rays_d, target)                 (train.py:68-119 semantics, joint clip 1.0)
+    pose mode   : step_pixels(pixel_batch, sampler, optimize_poses) (train_pose_opt.py:290-411 semantics:
+                  per-net clip 1.0, pose clip 0.1, separate Adam at pose_lr, optional L2 pose regulariser)
+    Under torch.distributed (one process per GPU) each rank passes its own shard of the batch; gradients are
+    averaged with one all-reduce over the flat buffer.
+    """
+
+    def __init__(self, model_coarse: NeRF, model_fine: Optional[NeRF], render_config: RenderConfig, lr: float = 5e-4,
+                 lr_decay_steps: float = 250000.0, camera_params=None, pose_lr: float = 1e-4,
+                 rotation_reg_weight: float = 0.0, translation_reg_weight: float = 0.0, process_group=None,
+                 betas=(0.9, 0.999), eps: float = 1e-8):
+        self.model_coarse, self.model_fine, self.cfg = model_coarse, model_fine, render_config
+        self.camera_params = camera_params
+        self.lr, self.pose_lr, self.lr_decay_steps = lr, pose_lr, lr_decay_steps
+        self.rot_reg, self.trans_reg = rotation_reg_weight, translation_reg_weight
+        self.betas, self.eps = betas, eps
+        self.group = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        nets = [model_coarse] + ([model_fine] if model_fine is not None else [])
+        dev = next(model_coarse.parameters()).device
+        self.device = dev
+        self.net_params: List[List[nn.Parameter]] = [m.kernel_params() for m in nets]
+        self.pose_params: List[nn.Parameter] = list(camera_params.parameters()) if camera_params is not None else []
+        n_net = sum(p.numel() for ps in self.net_params for p in ps)
+        n_pose = sum(p.numel() for p in self.pose_params)
+        self.n_net, self.n_pose = n_net, n_pose
+        total = n_net + n_pose
+        self.flat = torch.zeros(total, device=dev)
+        self.gflat = torch.zeros(total, device=dev)
+        self.exp_avg = torch.zeros(total, device=dev)
+        self.exp_avg_sq = torch.zeros(total, device=dev)
+        off = 0
+        self.net_offsets = [0]
+        for ps in self.net_params:
+            off = _flatten_into(ps, self.flat, self.gflat, off)
+            self.net_offsets.append(off)
+        off = _flatten_into(self.pose_params, self.flat, self.gflat, off)
+        self.norms = torch.zeros(8, device=dev)
+        self.iteration = 0
+        self.pose_steps = 0
+        self.nets = nets
+
+    # -- pieces --------------------------------------------------------------------------------
+    def _zero_grad(self):
+        self.gflat.zero_()
+        off = 0
+        for p in [q for ps in self.net_params for q in ps] + self.pose_params:
+            n = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.gflat.data_ptr() + 4 * off:
+                p.grad = self.gflat[off:off + n].view(p.shape)   # somebody called zero_grad(set_to_none=True)
+            off += n
+
+    def _allreduce(self):
+        allreduce_mean_(self.gflat, self.world, self.group)
+
+    def _adam(self, lo: int, hi: int, groups: Sequence[int], max_norms: Sequence[float], lr: float, step: int, norm_slot: int):
+        n = hi - lo
+        offs = (ctypes.c_int64 * len(groups))(*[g - lo for g in groups])
+        mx = (ctypes.c_float * len(max_norms))(*max_norms)
+        call("rn_clip_adam_step", self.flat[lo:hi].data_ptr(), self.gflat[lo:hi].data_ptr(), self.exp_avg[lo:hi].data_ptr(),
+             self.exp_avg_sq[lo:hi].data_ptr(), n, offs, mx, len(max_norms), float(lr), float(self.betas[0]),
+             float(self.betas[1]), float(self.eps), int(step), self.norms[norm_slot:].data_ptr(), stream_ptr())
+
+    def _optimise(self, separate_clip: bool, optimize_poses: bool):
+        self.iteration += 1
+        lr = self.lr * (0.1 ** ((self.iteration - 1) / self.lr_decay_steps))
+        if separate_clip and len(self.nets) == 2:
+            self._adam(0, self.n_net, self.net_offsets, [1.0, 1.0], lr, self.iteration, 0)
+        else:
+            self._adam(0, self.n_net, [0, self.n_net], [1.0], lr, self.iteration, 0)
+        if self.n_pose and optimize_poses:
+            self.pose_steps += 1
+            plr = self.pose_lr * (0.1 ** ((self.pose_steps - 1) / self.lr_decay_steps))
+            self._adam(self.n_net, self.n_net + self.n_pose, [self.n_net, self.n_net + self.n_pose], [0.1], plr,
+                       self.pose_steps, 4)
+        for m in self.nets:
+            m._packed.key = None          # parameters changed under the bf16 cache
+
+    def _backward(self, outputs, target, extra_loss=None):
+        loss_c, loss_f = _losses(outputs, target)
+        loss = loss_c if loss_f is None else loss_c + loss_f
+        if extra_loss is not None:
+            loss = loss + extra_loss
+        loss.backward()
+        return loss.detach()
+
+    # -- public steps -----------------------------------------------------------------------------
+    def step_rays(self, rays_o: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor, optimise: bool = True
+                  ) -> torch.Tensor:
+        self._zero_grad()
+        out = render_rays(self.model_coarse, self.model_fine, rays_o, rays_d, self.cfg, is_train=True)
+        loss = self._backward(out, target)
+        self._allreduce()
+        if optimise:
+            self._optimise(separate_clip=False, optimize_poses=False)
+        return loss
+
+    def step_pixels(self, pixel_batch, sampler, optimize_poses: bool = True, optimise: bool = True) -> torch.Tensor:
+        cam = self.camera_params
+        self._zero_grad()
+        rays_o, rays_d = sampler.get_rays_for_batch_fused(pixel_batch, cam)
+        out = render_rays(self.model_coarse, self.model_fine, rays_o, rays_d, self.cfg, is_train=True)
+        reg = None
+        if optimize_poses and (self.rot_reg > 0 or self.trans_reg > 0):
+            reg = 0.0
+            if self.rot_reg > 0 and cam.learn_rotation:
+                reg = reg + self.rot_reg * torch.mean(cam.rotation_deltas ** 2)
+            if self.trans_reg > 0 and cam.learn_translation:
+                reg = reg + self.trans_reg * torch.mean(cam.translation_deltas ** 2)
+        loss = self._backward(out, pixel_batch.target_rgb, reg)
+        self._allreduce()
+        if optimise:
+            self._optimise(separate_clip=True, optimize_poses=optimize_poses)
+        return loss
+
+
+@torch.no_grad()
+def render_views_sharded(model_coarse: NeRF, model_fine: Optional[NeRF], poses: torch.Tensor, H: int, W: int, focal: float,
+                         render_config: RenderConfig, tile_rays: int = 32768, rank: int = 0, world: int = 1,
+                         out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Test-view rendering sharded by ray tile: global tile t = view * tiles_per_view + k goes to rank
+    t % world; no collective.  Returns this rank's tiles written into a (n_views, H*W, 3) buffer
+    (zeros elsewhere) and the number of rays this rank rendered."""
+    n_views = poses.shape[0]
+    npix = H * W
+    tiles_per_view = (npix + tile_rays - 1) // tile_rays
+    directions = get_ray_directions(H, W, focal, device=poses.device).reshape(-1, 3)
+    if out is None:
+        out = torch.zeros(n_views, npix, 3, device=poses.device)
+    done = 0
+    for v in range(n_views):
+        mine = tiles_for_rank(v, tiles_per_view, rank, world)
+        if not mine:
+            continue
+        for k in mine:
+            a, b = k * tile_rays, min((k + 1) * tile_rays, npix)
+            ro, rd = get_rays(directions[a:b], poses[v])
+            res = render_rays(model_coarse, model_fine, ro, rd, render_config, is_train=False)
+            out[v, a:b] = res["rgb_fine"] if "rgb_fine" in res else res["rgb_coarse"]
+            done += b - a
+    return {"rgb": out, "rays_rendered": done}

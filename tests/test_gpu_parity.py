@@ -1,0 +1,516 @@
+"""GPU parity tests: every kernel family, through the Python API that wraps the C ABI, against the
+CPU oracle (oracle/nerf_oracle.py) and the committed golden vectors of the unmodified reference.
+
+Tolerances (north_star): bit-exact for indices / pixel bookkeeping / z-values; 1e-5 relative for
+fp32 rays, weights and compositing; bf16 tensor-core MLP within 1e-2 max-abs RGB and 0.05 dB PSNR.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def rn():
+    import robust_nerf_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def T(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t if dtype is None else t.to(dtype)
+
+
+def N(t):
+    return t.detach().float().cpu().numpy()
+
+
+def close(a, b, rtol=RTOL, atol=1e-6):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+def load_net(rn, weights, dev):
+    net = rn.NeRF().to(dev)
+    sd = net.state_dict()
+    for k, v in weights.items():
+        sd[k] = torch.from_numpy(v).to(dev)
+    net.load_state_dict(sd)
+    return net
+
+
+# ------------------------------------------------------------------------------------------------
+# native library is the thing that runs
+# ------------------------------------------------------------------------------------------------
+def test_native_library_loaded(rn):
+    from robust_nerf_b200 import _lib
+    lib = _lib.lib()
+    assert lib.rn_version() >= 100
+    with open("/proc/self/maps") as fh:
+        assert "librnerf_b200.so" in fh.read()
+
+
+def test_cpu_tensors_are_rejected(rn):
+    with pytest.raises(RuntimeError):
+        rn.raw2outputs(torch.rand(4, 8, 3), torch.rand(4, 8, 1), torch.rand(4, 8).sort(-1)[0], torch.rand(4, 3))
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM building block
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (384, 256, 256), (1000, 256, 320), (4096 + 77, 128, 320),
+                                   (300, 64, 256), (40000, 256, 256)])
+def test_gemm_nt(rn, dev, M, N, K):
+    from robust_nerf_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    for relu in (False, True):
+        D = ops.gemm_bf16(0, A, B, bias=bias, relu=relu)
+        ref = A.float() @ B.float().T + bias
+        if relu:
+            ref = ref.relu()
+        torch.cuda.synchronize()
+        err = (D.float() - ref).abs().max().item()
+        assert err < 0.03 * max(1.0, ref.abs().max().item() / 4), (relu, err)
+
+
+def test_gemm_nt_strided_views(rn, dev):
+    """operands / outputs that are column slices of wider buffers (the skip-concat layout)."""
+    from robust_nerf_b200 import ops
+    M = 777
+    XC = torch.randn(M, 320, device=dev).bfloat16()
+    W = (torch.randn(256, 64, device=dev) / 8).bfloat16()
+    out_buf = torch.zeros(M, 320, device=dev, dtype=torch.bfloat16)
+    ops.gemm_bf16(0, XC[:, :64], W, bias=None, relu=True, out=out_buf[:, 64:])
+    ref = (XC[:, :64].float() @ W.float().T).relu()
+    torch.cuda.synchronize()
+    assert (out_buf[:, 64:].float() - ref).abs().max().item() < 0.05
+    assert out_buf[:, :64].abs().max().item() == 0.0           # TMA store did not touch other columns
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (1000, 256, 272), (515, 64, 256), (3000, 256, 128)])
+def test_gemm_nn_with_mask(rn, dev, M, N, K):
+    from robust_nerf_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 3 + N + K)
+    A = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    B = (torch.randn(K, N, generator=g) / K ** 0.5).to(dev).bfloat16()
+    mask = torch.randn(M, N, generator=g).relu().to(dev).bfloat16()
+    ref = A.float() @ B.float()
+    D0 = ops.gemm_bf16(1, A, B)
+    D1 = ops.gemm_bf16(1, A, B, mask=mask)
+    torch.cuda.synchronize()
+    assert (D0.float() - ref).abs().max().item() < 0.05
+    assert (D1.float() - ref * (mask.float() > 0)).abs().max().item() < 0.05
+
+
+@pytest.mark.parametrize("K,Mo,N", [(64, 256, 256), (1000, 128, 256), (5000, 272, 256), (4096, 256, 64),
+                                    (100000, 256, 256)])
+def test_gemm_tn_weight_gradient(rn, dev, K, Mo, N):
+    from robust_nerf_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(K + Mo + N)
+    A = torch.randn(K, Mo, generator=g).to(dev).bfloat16()
+    B = torch.randn(K, N, generator=g).to(dev).bfloat16()
+    D, colsum = ops.gemm_bf16(2, A, B)
+    ref = A.float().T @ B.float()
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (D - ref).abs().max().item() < 2e-3 * scale + 1e-2
+    cs = A.float().sum(0)
+    assert (colsum - cs).abs().max().item() < 2e-3 * cs.abs().max().item() + 1e-2
+    D2, _ = ops.gemm_bf16(2, A, B)
+    torch.cuda.synchronize()
+    assert torch.equal(D, D2)                                   # split-K reduction is deterministic
+
+
+# ------------------------------------------------------------------------------------------------
+# poses and ray generation
+# ------------------------------------------------------------------------------------------------
+def test_ray_directions_and_get_rays(rn, dev):
+    g = load_golden("rays")
+    d = rn.get_ray_directions(20, 16, 13.7)
+    assert torch.equal(d.cpu(), torch.from_numpy(g["dirs"]))                       # bit-exact
+    dc = rn.get_ray_directions(20, 16, 13.7, center=(7.25, 11.5))
+    assert torch.equal(dc.cpu(), torch.from_numpy(g["dirs_center"]))
+    focal = 0.5 * 800 / np.tan(0.5 * 0.6911112070083618)
+    d800 = rn.get_ray_directions(800, 800, focal)
+    assert torch.equal(d800[417].cpu(), torch.from_numpy(g["d800_row"]))
+    o, dd = rn.get_rays(d, T(g["pose"], dev))
+    assert torch.equal(o.cpu(), torch.from_numpy(g["rays_o"]))
+    close(N(dd), g["rays_d"], atol=1e-7)
+    ob, db = rn.get_rays_batch(6, 5, 4.2, T(load_golden("lego_poses")["ground_truth_poses"][:3], dev))
+    close(N(db), g["batch_d"], atol=1e-7)
+    assert ob.shape == (3, 6, 5, 3)
+
+
+def test_camera_pose_parameters(rn, dev):
+    g = load_golden("pose")
+    cam = rn.CameraPoseParameters(T(g["init"], dev))
+    assert set(cam.state_dict().keys()) == {"initial_poses", "rotation_deltas", "translation_deltas"}
+    assert cam.rotation_deltas.abs().max().item() == 0.0
+    with torch.no_grad():
+        cam.rotation_deltas.copy_(T(g["rot"], dev))
+        cam.translation_deltas.copy_(T(g["trans"], dev))
+    P = cam.get_all_poses()
+    close(N(P), g["poses"], atol=1e-6)
+    (P * T(g["g_poses"], dev)).sum().backward()
+    close(N(cam.rotation_deltas.grad), g["d_rot"], rtol=1e-4, atol=1e-5)
+    close(N(cam.translation_deltas.grad), g["d_trans"], atol=1e-7)
+    assert cam.rotation_deltas.grad[0].abs().max().item() == 0.0                   # quirk 11
+    assert cam.rotation_deltas.grad[1].abs().max().item() == 0.0
+    close(N(cam.get_poses(T(g["sub_idx"], dev))), g["poses_sub"], atol=1e-6)
+    e = cam.compute_pose_errors(T(load_golden("lego_poses")["ground_truth_poses"], dev))
+    np.testing.assert_allclose([e["rotation_error_mean"], e["translation_error_mean"]], g["pose_errors"][[0, 3]], rtol=1e-4)
+    R = cam.axis_angle_to_rotation_matrix(T(g["rot"], dev))
+    close(N(R), O.axis_angle_to_rotation_matrix(g["rot"]), atol=1e-6)
+    frozen = rn.CameraPoseParameters(T(g["init"], dev), learn_rotation=False, learn_translation=False)
+    assert len(list(frozen.parameters())) == 0
+    assert torch.equal(frozen.get_all_poses()[:, :3, :], T(g["init"], dev)[:, :3, :])
+
+
+def test_pixel_sampler_and_raygen(rn, dev):
+    g = load_golden("pose")
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    rng = np.random.default_rng(1234)
+    images = torch.rand(100, H, W, 3)
+    data = rn.BlenderData(images=images.to(dev), poses=T(g["init"], dev), H=H, W=W, focal=focal)
+    ds, sampler = rn.create_pixel_dataset(data)
+    pb = sampler.batch_from_indices(T(g["flat_idx"], dev))
+    assert torch.equal(pb.image_indices.cpu(), torch.from_numpy(g["image_indices"]))   # bit-exact bookkeeping
+    assert torch.equal(pb.pixel_coords.cpu(), torch.from_numpy(g["pixel_coords"]))
+    assert torch.equal(pb.target_rgb.cpu(), images.reshape(-1, 3)[torch.from_numpy(g["flat_idx"])])
+    assert pb.image_indices.dtype == torch.int64 and pb.pixel_coords.dtype == torch.float32
+    # tables the reference materialises (data_pose_opt.py:56-76) are reproduced by index arithmetic
+    assert torch.equal(ds.image_indices[torch.from_numpy(g["flat_idx"]).to(dev)].cpu(), torch.from_numpy(g["image_indices"]))
+    assert torch.equal(ds.pixel_coords[torch.from_numpy(g["flat_idx"]).to(dev)].cpu(), torch.from_numpy(g["pixel_coords"]))
+    cam = rn.CameraPoseParameters(T(g["init"], dev))
+    with torch.no_grad():
+        cam.rotation_deltas.copy_(T(g["rot"], dev))
+        cam.translation_deltas.copy_(T(g["trans"], dev))
+    for fused in (False, True):
+        cam.zero_grad()
+        if fused:
+            ro, rd = sampler.get_rays_for_batch_fused(pb, cam)
+        else:
+            ro, rd = sampler.get_rays_for_batch(pb, cam.get_all_poses())
+        close(N(ro), g["px_rays_o"], atol=1e-6)
+        close(N(rd), g["px_rays_d"], atol=1e-6)
+        ((ro * T(g["g_o"], dev)).sum() + (rd * T(g["g_d"], dev)).sum()).backward()
+        close(N(cam.rotation_deltas.grad), g["px_d_rot"], rtol=1e-3, atol=1e-4)
+        close(N(cam.translation_deltas.grad), g["px_d_trans"], rtol=1e-4, atol=1e-5)
+    # reference-style call with one pose per unique image (quirk 15)
+    uniq = torch.unique(pb.image_indices)
+    ro2, rd2 = ds.get_rays_from_pixels(pb, cam.get_all_poses()[uniq])
+    close(N(rd2), g["px_rays_d"], atol=1e-6)
+    # sample_batch draws with the reference's torch.randint call
+    torch.manual_seed(7)
+    pb2 = rn.PixelSampler(ds, 512).sample_batch()
+    torch.manual_seed(7)
+    idx = torch.randint(0, ds.n_pixels, (512,), device=dev)
+    img, pc = O.pixel_bookkeeping(idx.cpu().numpy(), H, W)
+    assert np.array_equal(pb2.image_indices.cpu().numpy(), img) and np.array_equal(pb2.pixel_coords.cpu().numpy(), pc)
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,kw", [("det", dict(perturb=False)), ("pert", dict(perturb=True)),
+                                    ("lindisp", dict(perturb=True, lindisp=True))])
+def test_sample_along_rays(rn, dev, tag, kw):
+    g = load_golden("stratified")
+    tr = g.get(f"trand_{tag}")
+    pts, z = rn.sample_along_rays(T(g["rays_o"], dev), T(g["rays_d"], dev), 2.0, 6.0, 64,
+                                  t_rand=None if tr is None else T(tr, dev), **kw)
+    assert pts.shape == (24, 64, 3) and z.shape == (24, 64)
+    if tag == "lindisp":
+        close(N(z), g[f"z_{tag}"], atol=1e-6)
+    else:
+        # CUDA linspace may differ from the CPU one by an ulp; the kernel arithmetic itself is bit-exact
+        zb = O.stratified_z(2.0, 6.0, 64, (24,), kw["perturb"], False, tr)
+        close(N(z), zb, rtol=0, atol=5e-7)
+        from robust_nerf_b200 import ops
+        zdev, _ = ops.stratified(
+            T(g["rays_o"], dev), T(g["rays_d"], dev), T(O.stratified_z(2.0, 6.0, 64, (), False), dev),
+            None if tr is None else T(tr, dev))
+        assert torch.equal(zdev.cpu(), torch.from_numpy(g[f"z_{tag}"]))            # bit-exact given the same base
+    close(N(pts), g[f"pts_{tag}"], atol=2e-6)
+
+
+def test_sample_along_rays_shapes_and_rng(rn, dev):
+    ro, rd = torch.randn(5, 7, 3, device=dev), torch.randn(5, 7, 3, device=dev)
+    torch.manual_seed(3)
+    pts, z = rn.sample_along_rays(ro, rd, 2.0, 6.0, 33, perturb=True)
+    torch.manual_seed(3)
+    t = torch.rand(5, 7, 33, device=dev)                       # same call as rays.py:204
+    pts2, z2 = rn.sample_along_rays(ro, rd, 2.0, 6.0, 33, perturb=True, t_rand=t)
+    assert pts.shape == (5, 7, 33, 3) and torch.equal(z, z2) and torch.equal(pts, pts2)
+    assert (z[..., 1:] >= z[..., :-1]).all()
+
+
+def test_sample_pdf_indices_bit_exact(rn, dev):
+    from robust_nerf_b200 import ops
+    g = load_golden("sample_pdf")
+    z, w = g["z"], g["weights"]
+    mids = (np.float32(0.5) * (z[..., 1:] + z[..., :-1])).astype(np.float32)
+    for det, u in ((True, O.linspace_f32(0, 1, 128)), (False, g["u_rand"])):
+        s_ref, i_ref, _ = O.sample_pdf(mids, w[..., 1:-1], 128, det=det, u=None if det else u, return_inds=True)
+        s, i = ops.sample_pdf(T(mids, dev), T(w[..., 1:-1].copy(), dev), T(u, dev), return_inds=True)
+        assert i.dtype == torch.int64
+        assert np.array_equal(i.cpu().numpy(), i_ref)                               # bit-exact indices
+        assert np.array_equal(s.cpu().numpy(), s_ref)                               # and samples
+    out = rn.sample_pdf(T(mids, dev), T(w[..., 1:-1].copy(), dev), 128, det=False, u=T(g["u_rand"], dev))
+    err = np.abs(N(out) - g["pdf_rand"])
+    assert (err > 2e-5 + 1e-5 * np.abs(g["pdf_rand"])).mean() < 2e-3                # vs the reference itself
+
+
+@pytest.mark.parametrize("Nc,Nf,B", [(64, 128, 24), (128, 256, 100), (16, 32, 7), (5, 3, 33)])
+def test_sample_hierarchical(rn, dev, Nc, Nf, B):
+    from robust_nerf_b200 import ops
+    rng = np.random.default_rng(Nc * 1000 + Nf)
+    ro = rng.standard_normal((B, 3)).astype(np.float32)
+    rd = rng.standard_normal((B, 3)).astype(np.float32)
+    z = np.sort(rng.uniform(2, 6, (B, Nc)).astype(np.float32), -1)
+    w = (rng.uniform(0, 1, (B, Nc)) ** 4).astype(np.float32)
+    w[0] = 0
+    for det in (True, False):
+        u = O.linspace_f32(0, 1, Nf) if det else rng.uniform(0, 1, (B, Nf)).astype(np.float32)
+        pts_ref, z_ref, i_ref = O.sample_hierarchical(ro, rd, z, w, Nf, det=det, u=None if det else u, return_inds=True)
+        z_all, pts, inds = ops.sample_hierarchical(T(ro, dev), T(rd, dev), T(z, dev), T(w, dev), T(u, dev), return_inds=True)
+        assert np.array_equal(inds.cpu().numpy(), i_ref)
+        assert np.array_equal(z_all.cpu().numpy(), z_ref)                           # sorted merge, bit-exact
+        close(N(pts), pts_ref, atol=2e-6)
+        assert (z_all[:, 1:] >= z_all[:, :-1]).all()
+    g = load_golden("sample_pdf")
+    if Nc == 64:
+        p, zf = rn.sample_hierarchical(T(g["rays_o"], dev), T(g["rays_d"], dev), T(g["z"], dev), T(g["weights"], dev), 128,
+                                       det=False, u=T(g["hier_u"], dev))
+        assert (np.abs(N(zf) - g["hier_z_rand"]) > 2e-5 + 1e-5 * np.abs(g["hier_z_rand"])).mean() < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,white", [("white", True), ("black", False)])
+def test_raw2outputs_golden(rn, dev, tag, white):
+    g = load_golden("raw2outputs")
+    rgb, sig = T(g["rgb"], dev).requires_grad_(True), T(g["sigma"], dev).requires_grad_(True)
+    rd = T(g["rays_d"], dev).requires_grad_(True)
+    out = rn.raw2outputs(rgb, sig, T(g["z"], dev), rd, 0.0, white)
+    for k in ("rgb_map", "depth_map", "acc_map", "weights"):
+        close(N(out[k]), g[f"{tag}_{k}"], atol=2e-6)
+    ((out["rgb_map"] * T(g[f"{tag}_g_map"], dev)).sum() + (out["depth_map"] * T(g[f"{tag}_g_depth"], dev)).sum()
+     + (out["acc_map"] * T(g[f"{tag}_g_acc"], dev)).sum() + (out["weights"] * T(g[f"{tag}_g_w"], dev)).sum()).backward()
+    close(N(rgb.grad), g[f"{tag}_d_rgb"], atol=2e-6)
+    close(N(sig.grad), g[f"{tag}_d_sigma"], rtol=2e-4, atol=2e-5)
+    close(N(rd.grad), g[f"{tag}_d_rays_d"], rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("B,S", [(1, 1), (3, 31), (100, 64), (257, 192), (64, 384), (9, 500)])
+def test_raw2outputs_shapes_vs_oracle(rn, dev, B, S):
+    rng = np.random.default_rng(B * 1000 + S)
+    rgb = rng.uniform(0, 1, (B, S, 3)).astype(np.float32)
+    sig = (rng.uniform(-1, 1, (B, S, 1)) * rng.choice([0.1, 10, 300], (B, 1, 1))).astype(np.float32)
+    z = np.sort(rng.uniform(2, 6, (B, S)).astype(np.float32), -1)
+    rd = rng.standard_normal((B, 3)).astype(np.float32)
+    ref = O.raw2outputs(rgb, sig, z, rd, keep_cache=True)
+    trgb, tsig = T(rgb, dev).requires_grad_(True), T(sig, dev).requires_grad_(True)
+    out = rn.raw2outputs(trgb, tsig, T(z, dev), T(rd, dev))
+    for k in ("rgb_map", "depth_map", "acc_map", "weights"):
+        close(N(out[k]), ref[k], atol=2e-6)
+    g_map = rng.standard_normal((B, 3)).astype(np.float32)
+    d_rgb, d_sig, _ = O.raw2outputs_backward(ref["_cache"], g_map)
+    (out["rgb_map"] * T(g_map, dev)).sum().backward()
+    close(N(trgb.grad), d_rgb, atol=2e-6)
+    scale = max(np.abs(d_sig).max(), 1e-6)
+    np.testing.assert_allclose(N(tsig.grad)[..., 0] / scale, d_sig / scale, atol=2e-4)
+
+
+def test_composite_early_termination_and_noise(rn, dev):
+    rng = np.random.default_rng(5)
+    B, S = 40, 192
+    rgb = T(rng.uniform(0, 1, (B, S, 3)).astype(np.float32), dev)
+    sig = T((rng.uniform(0, 1, (B, S, 1)) * 50).astype(np.float32), dev)
+    z = T(np.sort(rng.uniform(2, 6, (B, S)).astype(np.float32), -1), dev)
+    rd = T(rng.standard_normal((B, 3)).astype(np.float32), dev)
+    exact = rn.raw2outputs(rgb, sig, z, rd)
+    early = rn.raw2outputs(rgb, sig, z, rd, early_stop_T=1e-4)
+    assert (exact["rgb_map"] - early["rgb_map"]).abs().max().item() < 2e-4
+    assert (early["weights"][:, -32:] == 0).all()               # opaque rays: tail skipped
+    noise = rng.standard_normal((B, S)).astype(np.float32)
+    ref = O.raw2outputs(N(rgb), N(sig), N(z), N(rd), noise=noise)
+    got = rn.raw2outputs(rgb, sig, z, rd, raw_noise_std=1.0, noise=T(noise, dev))
+    close(N(got["rgb_map"]), ref["rgb_map"], atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# NeRF MLP
+# ------------------------------------------------------------------------------------------------
+def test_positional_encoding(rn, dev):
+    g = load_golden("pe")
+    for L, key in ((10, "pe10"), (4, "pe4")):
+        pe = rn.PositionalEncoding(L).to(dev)
+        x = T(g["x"], dev).requires_grad_(True)
+        out = pe(x)
+        close(N(out), g[key], atol=2e-6)
+        gout = np.random.default_rng(L).standard_normal(out.shape).astype(np.float32)
+        (out * T(gout, dev)).sum().backward()
+        ref = O.positional_encoding_backward(g["x"], L, gout)
+        np.testing.assert_allclose(N(x.grad), ref, rtol=1e-4, atol=1e-3)
+    assert pe.output_dim == 9 and tuple(pe.freq_bands.shape) == (4,)
+
+
+def test_nerf_state_dict_contract(rn, dev):
+    net = rn.NeRF()
+    shapes = O.param_shapes(O.ModelConfig())
+    sd = net.state_dict()
+    assert list(sd.keys())[:2] == ["pos_encoder.freq_bands", "dir_encoder.freq_bands"]
+    for k, s in shapes.items():
+        assert tuple(sd[k].shape) == s, k
+    assert sum(p.numel() for p in net.parameters()) == 595844
+    assert [n for n, _ in net.named_parameters()] == O.param_names(O.ModelConfig())
+    with pytest.raises(NotImplementedError):
+        rn.NeRF(rn.ModelConfig(hidden_dim=128))
+    c, f = rn.create_nerf()
+    assert isinstance(c, rn.NeRF) and isinstance(f, rn.NeRF) and c is not f
+
+
+@pytest.mark.parametrize("tag", ["plain", "sharp"])
+def test_nerf_forward_backward_golden(rn, dev, tag):
+    g = load_golden(f"nerf_{tag}")
+    w = O.make_weights(7, sharpen=(tag == "sharp"))
+    net = load_net(rn, w, dev)
+    x, d = T(g["pts"], dev).requires_grad_(True), T(g["dirs"], dev).requires_grad_(True)
+    rgb, sigma = net(x, d)
+    assert rgb.shape == (384, 3) and sigma.shape == (384, 1)
+    assert rgb.min() >= 0 and rgb.max() <= 1 and sigma.min() >= 0
+    assert np.abs(N(rgb) - g["rgb"]).max() < 1e-2                                  # north_star: 1e-2 max-abs RGB
+    sscale = max(np.abs(g["sigma"]).max(), 1.0)
+    assert np.abs(N(sigma) - g["sigma"]).max() < 2e-2 * sscale
+    (rgb * T(g["g_rgb"], dev)).sum().add((sigma * T(g["g_sigma"], dev)).sum()).backward()
+    ref_rgb, ref_sigma, cache = O.nerf_forward(w, g["pts"], g["dirs"], keep_cache=True)
+    grads, dx, dd = O.nerf_backward(w, cache, g["g_rgb"], g["g_sigma"], need_input_grad=True)
+    for k, p in net.named_parameters():
+        ref = grads[k]
+        rel = np.linalg.norm(N(p.grad) - ref) / max(np.linalg.norm(ref), 1e-12)
+        assert rel < 4e-2, (k, rel)                                                # bf16 operands: ~2^-8 per product
+    for a, b in ((x.grad, dx), (d.grad, dd)):
+        rel = np.linalg.norm(N(a) - b) / max(np.linalg.norm(b), 1e-12)
+        assert rel < 6e-2, rel
+
+
+def test_nerf_batch_sizes(rn, dev):
+    w = O.make_weights(3)
+    net = load_net(rn, w, dev)
+    rng = np.random.default_rng(0)
+    with torch.no_grad():
+        for M in (1, 127, 128, 129, 1024, 5000):
+            pts = rng.uniform(-3, 3, (M, 3)).astype(np.float32)
+            dirs = rng.standard_normal((M, 3)).astype(np.float32)
+            dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+            rgb, sigma = net(T(pts, dev), T(dirs, dev))
+            r_ref, s_ref = O.nerf_forward(w, pts, dirs)
+            assert np.abs(N(rgb) - r_ref).max() < 1e-2, M
+            assert np.abs(N(sigma) - s_ref).max() < 2e-2, M
+    with pytest.raises(RuntimeError):
+        net(T(pts, dev), None)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole pipeline
+# ------------------------------------------------------------------------------------------------
+def _psnr(a, b):
+    return -10.0 * np.log10(max(float(((a - b) ** 2).mean()), 1e-20))
+
+
+@pytest.mark.parametrize("tag", ["plain", "sharp"])
+def test_render_rays_eval_and_train(rn, dev, tag):
+    g = load_golden(f"render_{tag}")
+    sharp = tag == "sharp"
+    wc, wf = O.make_weights(21, sharpen=sharp), O.make_weights(22, sharpen=sharp)
+    nc, nf = load_net(rn, wc, dev), load_net(rn, wf, dev)
+    cfg = rn.RenderConfig()
+    ro, rd = T(g["rays_o"], dev), T(g["rays_d"], dev)
+    with torch.no_grad():
+        ev = rn.render_rays(nc, nf, ro, rd, cfg, is_train=False)
+    for k in ("rgb_coarse", "rgb_fine"):
+        assert np.abs(N(ev[k]) - g["eval_" + k]).max() < 1e-2, k
+    for k in ("acc_coarse", "acc_fine"):
+        assert np.abs(N(ev[k]) - g["eval_" + k]).max() < 2e-2, k
+    tgt = T(g["target"], dev)
+    out = rn.render_rays(nc, nf, ro, rd, cfg, is_train=True, t_rand=T(g["t_rand"], dev), u=T(g["u"], dev))
+    assert np.abs(N(out["rgb_fine"]) - g["train_rgb_fine"]).max() < 1e-2
+    loss = ((out["rgb_coarse"] - tgt) ** 2).mean() + ((out["rgb_fine"] - tgt) ** 2).mean()
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 2e-2 * float(g["loss"]) + 1e-4
+    ref = O.train_step_grads(wc, wf, g["rays_o"], g["rays_d"], g["target"], t_rand=g["t_rand"], u=g["u"])
+    for net, grads in ((nc, ref["grads_coarse"]), (nf, ref["grads_fine"])):
+        num = sum(float(((N(p.grad) - grads[k]) ** 2).sum()) for k, p in net.named_parameters())
+        den = sum(float((grads[k] ** 2).sum()) for k in grads)
+        assert (num / den) ** 0.5 < (0.15 if sharp else 0.05), (num / den) ** 0.5
+
+
+def test_render_psnr_delta_vs_oracle(rn, dev):
+    """PSNR of our render against a fixed target must be within 0.05 dB of the oracle's (north_star)."""
+    wc, wf = O.make_weights(31, sharpen=True), O.make_weights(32, sharpen=True)
+    nc, nf = load_net(rn, wc, dev), load_net(rn, wf, dev)
+    rng = np.random.default_rng(9)
+    H = W = 800
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    pix = rng.integers(0, H * W, 512)
+    dirs = O.get_ray_directions(H, W, focal).reshape(-1, 3)[pix]
+    ro, rd = O.get_rays(dirs, load_golden("lego_poses")["ground_truth_poses"][11])
+    ref = O.render_rays(wc, wf, ro, rd, is_train=False)
+    with torch.no_grad():
+        out = rn.NeRFRenderer(nc, nf, rn.RenderConfig())(T(ro, dev), T(rd, dev), chunk_size=200, is_train=False)
+    target = rng.uniform(0, 1, (512, 3)).astype(np.float32)
+    assert out["rgb_fine"].shape == (512, 3)
+    assert np.abs(N(out["rgb_fine"]) - ref["rgb_fine"]).max() < 1e-2
+    assert abs(_psnr(N(out["rgb_fine"]), target) - _psnr(ref["rgb_fine"], target)) <= 0.05
+    # renders are chunk-invariant in eval mode
+    with torch.no_grad():
+        out2 = rn.NeRFRenderer(nc, nf, rn.RenderConfig())(T(ro, dev), T(rd, dev), chunk_size=4096, is_train=False)
+    assert (out2["rgb_fine"] - out["rgb_fine"]).abs().max().item() < 1e-5
+
+
+def test_reference_smoke_tests_port(rn, dev):
+    """noisy_src/test_baseline.py:12-146 with the import swapped (shapes and ranges)."""
+    pe = rn.PositionalEncoding(num_freqs=10, include_input=True)
+    assert pe(torch.randn(100, 3, device=dev)).shape == (100, 63)
+    model = rn.NeRF(rn.ModelConfig()).to(dev)
+    pts, dirs = torch.randn(1024, 3, device=dev), torch.randn(1024, 3, device=dev)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    rgb, sigma = model(pts, dirs)
+    assert rgb.shape == (1024, 3) and sigma.shape == (1024, 1) and rgb.min() >= 0 and rgb.max() <= 1 and sigma.min() >= 0
+    directions = rn.get_ray_directions(100, 100, 50.0)
+    assert directions.shape == (100, 100, 3)
+    c2w = torch.eye(4, device=dev)
+    c2w[:3, 3] = torch.tensor([0, 0, 4.0], device=dev)
+    rays_o, rays_d = rn.get_rays(directions.to(dev), c2w)
+    assert rays_o.shape == (100, 100, 3) and rays_d.shape == (100, 100, 3)
+    ro, rd = rays_o.reshape(-1, 3)[:100], rays_d.reshape(-1, 3)[:100]
+    pts, z_vals = rn.sample_along_rays(ro, rd, near=2.0, far=6.0, num_samples=64, perturb=True)
+    assert pts.shape == (100, 64, 3) and z_vals.shape == (100, 64)
+    pts_fine, z_fine = rn.sample_hierarchical(ro, rd, z_vals, torch.rand(100, 64, device=dev), num_samples_fine=128)
+    assert pts_fine.shape == (100, 192, 3)
+    out = rn.raw2outputs(torch.rand(100, 64, 3, device=dev), torch.rand(100, 64, 1, device=dev) * 10,
+                         torch.linspace(2, 6, 64, device=dev).unsqueeze(0).expand(100, -1), rd)
+    assert out["rgb_map"].shape == (100, 3) and out["depth_map"].shape == (100,) and out["weights"].shape == (100, 64)
+    coarse, fine = rn.create_nerf(rn.ModelConfig())
+    renderer = rn.NeRFRenderer(coarse.to(dev), fine.to(dev), rn.RenderConfig(num_samples=32, num_samples_fine=64))
+    o = torch.zeros(50, 3, device=dev)
+    o[:, 2] = 4.0
+    d = torch.randn(50, 3, device=dev)
+    with torch.no_grad():
+        res = renderer(o, d / d.norm(dim=-1, keepdim=True), chunk_size=25, is_train=False)
+    assert "rgb_coarse" in res and res["rgb_fine"].shape == (50, 3)
