@@ -281,43 +281,54 @@ def make_weights(seed: int, cfg: Optional[ModelConfig] = None, sharpen: bool = F
     return out
 
 
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """Round fp32 to the nearest bfloat16 (ties to even), returned as fp32.  Used by the
+    `emulate_bf16` mode, which restates WHERE the CUDA path rounds (weights, PE features, every
+    stored activation and back-propagated gradient) so ReLU masks coincide and the kernels can be
+    checked tightly; accumulation stays fp32 like the tensor cores'."""
+    u = np.ascontiguousarray(x, dtype=F32).view(np.uint32)
+    r = ((u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)).astype(np.uint32)
+    return r.view(F32).reshape(np.shape(x))
+
+
 def _sigmoid(x):
     return (F32(1.0) / (F32(1.0) + np.exp(-x))).astype(F32)
 
 
 def nerf_forward(params: Dict[str, np.ndarray], x, d, cfg: Optional[ModelConfig] = None,
-                 keep_cache: bool = False):
+                 keep_cache: bool = False, emulate_bf16: bool = False):
     """noisy_src/model.py:145-196.  Returns rgb (N,3), sigma (N,1)[, cache]."""
     cfg = cfg or ModelConfig()
+    r = bf16_round if emulate_bf16 else (lambda a: a)
     x = _f32(x)
-    x_enc = positional_encoding(x, cfg.pos_freqs)
+    x_enc = r(positional_encoding(x, cfg.pos_freqs))
     h = x_enc
-    cache = {"x": x, "x_enc": x_enc, "ins": [], "pre": []}
+    cache = {"x": x, "x_enc": x_enc, "ins": [], "pre": [], "emulate": emulate_bf16}
     for i in range(cfg.num_hidden_layers):
-        W, b = params[f"pts_linears.{i}.weight"], params[f"pts_linears.{i}.bias"]
+        W, b = r(params[f"pts_linears.{i}.weight"]), params[f"pts_linears.{i}.bias"]
         cache["ins"].append(h)
         pre = (h @ W.T + b).astype(F32)
-        h = np.maximum(pre, F32(0.0))
-        cache["pre"].append(pre)
+        h = r(np.maximum(pre, F32(0.0)))
+        cache["pre"].append(h if emulate_bf16 else pre)   # mask = stored activation > 0
         if i in cfg.skips:
             h = np.concatenate([x_enc, h], -1)
     sig_pre = (h @ params["sigma_linear.weight"].T + params["sigma_linear.bias"]).astype(F32)
     sigma = np.maximum(sig_pre, F32(0.0))
-    feats = (h @ params["feature_linear.weight"].T + params["feature_linear.bias"]).astype(F32)
+    feats = r((h @ r(params["feature_linear.weight"]).T + params["feature_linear.bias"]).astype(F32))
     if cfg.use_view_dirs:
         if d is None:
             raise ValueError("reference crashes for d=None with use_view_dirs (model.py:187-193)")
         d = _f32(d)
-        d_enc = positional_encoding(d, cfg.dir_freqs)
+        d_enc = r(positional_encoding(d, cfg.dir_freqs))
         hc_in = np.concatenate([feats, d_enc], -1)
     else:
         d_enc, hc_in = None, feats
-    hc_pre = (hc_in @ params["dir_linear.weight"].T + params["dir_linear.bias"]).astype(F32)
-    hc = np.maximum(hc_pre, F32(0.0))
+    hc_pre = (hc_in @ r(params["dir_linear.weight"]).T + params["dir_linear.bias"]).astype(F32)
+    hc = r(np.maximum(hc_pre, F32(0.0)))
     rgb_pre = (hc @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]).astype(F32)
     rgb = _sigmoid(rgb_pre)
     if keep_cache:
-        cache.update(h_last=h, sig_pre=sig_pre, d=d, hc_in=hc_in, hc_pre=hc_pre, hc=hc, rgb=rgb)
+        cache.update(h_last=h, sig_pre=sig_pre, d=d, hc_in=hc_in, hc_pre=hc if emulate_bf16 else hc_pre, hc=hc, rgb=rgb)
         return rgb, sigma, cache
     return rgb, sigma
 
@@ -326,40 +337,41 @@ def nerf_backward(params, cache, g_rgb, g_sigma, cfg: Optional[ModelConfig] = No
                   need_input_grad: bool = False):
     """Manual backward of nerf_forward.  Returns (param grads dict, dx, dd)."""
     cfg = cfg or ModelConfig()
+    r = bf16_round if cache.get("emulate") else (lambda a: a)
     g = {}
     rgb = cache["rgb"]
     g_rgb_pre = (_f32(g_rgb) * rgb * (F32(1.0) - rgb)).astype(F32)
     g["rgb_linear.weight"] = (g_rgb_pre.T @ cache["hc"]).astype(F32)
     g["rgb_linear.bias"] = g_rgb_pre.sum(0).astype(F32)
     g_hc = (g_rgb_pre @ params["rgb_linear.weight"]).astype(F32)
-    g_hc_pre = (g_hc * (cache["hc_pre"] > 0)).astype(F32)
+    g_hc_pre = r((g_hc * (cache["hc_pre"] > 0)).astype(F32))
     g["dir_linear.weight"] = (g_hc_pre.T @ cache["hc_in"]).astype(F32)
     g["dir_linear.bias"] = g_hc_pre.sum(0).astype(F32)
-    g_hc_in = (g_hc_pre @ params["dir_linear.weight"]).astype(F32)
+    g_hc_in = r((g_hc_pre @ r(params["dir_linear.weight"])).astype(F32))
     H = cfg.hidden_dim
     g_feats = g_hc_in[:, :H]
     g_d_enc = g_hc_in[:, H:] if cfg.use_view_dirs else None
     h_last = cache["h_last"]
     g["feature_linear.weight"] = (g_feats.T @ h_last).astype(F32)
     g["feature_linear.bias"] = g_feats.sum(0).astype(F32)
-    g_sig_pre = (_f32(g_sigma).reshape(-1, 1) * (cache["sig_pre"] > 0)).astype(F32)
+    g_sig_pre = r((_f32(g_sigma).reshape(-1, 1) * (cache["sig_pre"] > 0)).astype(F32))
     g["sigma_linear.weight"] = (g_sig_pre.T @ h_last).astype(F32)
     g["sigma_linear.bias"] = g_sig_pre.sum(0).astype(F32)
-    g_h = (g_feats @ params["feature_linear.weight"] + g_sig_pre @ params["sigma_linear.weight"]).astype(F32)
+    g_h = (g_feats @ r(params["feature_linear.weight"]) + g_sig_pre @ r(params["sigma_linear.weight"])).astype(F32)
     pos_dim = cache["x_enc"].shape[-1]
     g_x_enc = np.zeros_like(cache["x_enc"])
     for i in reversed(range(cfg.num_hidden_layers)):
         if i in cfg.skips:
-            g_x_enc += g_h[:, :pos_dim]
+            g_x_enc += r(g_h[:, :pos_dim])
             g_h = g_h[:, pos_dim:]
-        g_pre = (g_h * (cache["pre"][i] > 0)).astype(F32)
+        g_pre = r((g_h * (cache["pre"][i] > 0)).astype(F32))
         g[f"pts_linears.{i}.weight"] = (g_pre.T @ cache["ins"][i]).astype(F32)
         g[f"pts_linears.{i}.bias"] = g_pre.sum(0).astype(F32)
         if i > 0 or need_input_grad:
-            g_h = (g_pre @ params[f"pts_linears.{i}.weight"]).astype(F32)
+            g_h = (g_pre @ r(params[f"pts_linears.{i}.weight"])).astype(F32)
     dx = dd = None
     if need_input_grad:
-        g_x_enc += g_h
+        g_x_enc += r(g_h)
         dx = positional_encoding_backward(cache["x"], cfg.pos_freqs, g_x_enc)
         if cfg.use_view_dirs:
             dd = positional_encoding_backward(cache["d"], cfg.dir_freqs, g_d_enc)
