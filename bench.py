@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the render-and-train hot path (BASELINE.json metric: train rays/s, fwd+bwd,
+800x800 lego-shaped synthetic scene).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm (oracle port on host cores)
+
+A step = one pass of the hot path over one batch: BASELINE.json configs[1], the clean-pose NeRF
+training step on a 4096-ray batch per GPU (render 64 coarse + 128 fine samples, MSE coarse+fine,
+backward, one all-reduce of the flat gradient buffer when N > 1, joint clip at 1.0, Adam).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 4096
+NC, NF = 64, 128
+POINTS_PER_RAY = NC + (NC + NF)                     # coarse net + fine net evaluations
+FLOP_PER_POINT_FWD = 1186816
+TRAIN_FLOP_PER_RAY = 3 * FLOP_PER_POINT_FWD * POINTS_PER_RAY   # 911,474,688 (fwd + dgrad + wgrad)
+METRIC = "train rays/s (fwd+bwd+clip+Adam), 4096-ray batch/GPU, 64+128 samples, 800x800 lego-shaped synthetic scene"
+WORKLOAD = "configs[1]: clean-pose NeRF training step, 4096-ray batch, synthetic 800x800 lego-shaped scene (100 views)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": float(d["bf16_tflops_sustained"]), "gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1400.0, "gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/rn_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port timed on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_rate(sample_rays: int, steps: int, warmup: int):
+    """rays/s of the numpy oracle's full training step (render fwd, loss, bwd, joint clip, Adam) on a
+    bounded sample of the 4096-ray batch."""
+    import numpy as np
+    from oracle import nerf_oracle as O
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    wc, wf = O.make_weights(21), O.make_weights(22)
+    poses = np.load(os.path.join(ROOT, "robust-nerf_b200", "data", "lego_train_poses.npy"))
+    H = W = 800
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    state, times = {}, []
+    for it in range(warmup + steps):
+        img = rng.integers(0, 100, sample_rays)
+        uv = np.stack([rng.integers(0, W, sample_rays), rng.integers(0, H, sample_rays)], -1).astype(np.float32)
+        ro, rd = O.get_rays_from_pixels(img, uv, poses, H, W, focal)
+        target = rng.uniform(0, 1, (sample_rays, 3)).astype(np.float32)
+        t_rand = rng.uniform(0, 1, (sample_rays, NC)).astype(np.float32)
+        u = rng.uniform(0, 1, (sample_rays, NF)).astype(np.float32)
+        t0 = time.perf_counter()
+        out = O.train_step_grads(wc, wf, ro, rd, target, t_rand=t_rand, u=u)
+        O.clip_and_adam([wc, wf], [out["grads_coarse"], out["grads_fine"]], state)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean_t = sum(times) / len(times)
+    return sample_rays / mean_t, cores, mean_t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 512
+    rate, cores, t = cpu_train_step_rate(sample, max(1, args.steps), max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step_sampled": sample, "samples": f"{NC}+{NF}"},
+        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample}-ray slice of the 4096-ray training step per timed step (numpy oracle port of the "
+                                   "reference's PyTorch path: fwd + bwd + joint clip + Adam)"},
+        "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 through torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import robust_nerf_b200 as rn
+    from robust_nerf_b200 import _lib
+    lib = _lib.lib()
+
+    # ---- synthetic scene: 100 views 800x800, random images, lego camera layout ----
+    H = W = 800
+    scene = rn.make_scene(H, W, 100, seed=0, device=dev)
+    torch.manual_seed(42)                      # reference default seed (config.py:83)
+    coarse, fine = rn.create_nerf(rn.ModelConfig())
+    coarse, fine = coarse.to(dev), fine.to(dev)
+    cfg = rn.RenderConfig()
+    trainer = rn.Trainer(coarse, fine, cfg, lr=5e-4)
+    ds, sampler = rn.create_pixel_dataset(scene)
+
+    # clean-pose mode: batches of precomputed rays (RaySampler semantics, noisy_src/data.py:297-309)
+    POOL = 8
+    g = torch.Generator(device="cpu").manual_seed(42 + rank)
+    dev_batches, host_batches = [], []
+    for _ in range(POOL):
+        idx = torch.randint(0, ds.n_pixels, (RAYS_PER_GPU,), generator=g).to(dev)
+        pb = sampler.batch_from_indices(idx)
+        with torch.no_grad():
+            ro, rd = sampler.get_rays_for_batch(pb, scene.poses)
+        dev_batches.append((ro.contiguous(), rd.contiguous(), pb.target_rgb.contiguous()))
+        host_batches.append(tuple(t.cpu().pin_memory() for t in dev_batches[-1]))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W_, K_ = max(3, args.warmup), max(1, args.steps)
+
+    # ---- device-resident timing (value) with live GEMM event timing (roofline) ----
+    for i in range(W_):
+        trainer.step_rays(*dev_batches[i % POOL])
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    lib.rn_prof_enable(1)
+    n0 = lib.rn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K_):
+        loss = trainer.step_rays(*dev_batches[i % POOL])
+    e1.record()
+    barrier()
+    launches = int(lib.rn_launch_count() - n0)
+    lib.rn_prof_enable(0)
+    ms3, fl3, ln3 = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_int * 3)()
+    lib.rn_prof_collect(ms3, fl3, ln3)
+    t_ms = reduce_max(e0.elapsed_time(e1))
+    clock_info = clocks.stop() if rank == 0 else None
+    ms_per_step = t_ms / K_
+    value = world * RAYS_PER_GPU * K_ / (t_ms * 1e-3)
+    loss_val = float(loss.item())
+
+    # ---- end to end: pinned host batches -> device, step, loss back to the host, every step ----
+    loss_host = torch.zeros(1).pin_memory()
+    for i in range(3):
+        b = [t.to(dev, non_blocking=True) for t in host_batches[i % POOL]]
+        loss_host.copy_(trainer.step_rays(*b).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e0.record()
+    for i in range(K_):
+        b = [t.to(dev, non_blocking=True) for t in host_batches[i % POOL]]
+        loss_host.copy_(trainer.step_rays(*b).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the step's loss
+        _ = float(loss_host[0])
+    e1.record()
+    barrier()
+    t_e2e = reduce_max(e0.elapsed_time(e1))
+    e2e_value = world * RAYS_PER_GPU * K_ / (t_e2e * 1e-3)
+
+    # ---- extras (not part of the contract line's headline): render throughput, pose-opt step ----
+    extra = {}
+    if rank == 0 and not args.no_extras:
+        with torch.no_grad():
+            dirs = rn.get_ray_directions(H, W, scene.focal, device=dev).reshape(-1, 3)
+            ro, rd = rn.get_rays(dirs[:131072], scene.poses[0])
+            for _ in range(2):
+                rn.render_rays(coarse, fine, ro, rd, cfg, is_train=False)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                rn.render_rays(coarse, fine, ro, rd, cfg, is_train=False)
+            e1.record()
+            torch.cuda.synchronize()
+            extra["render_mrays_per_s_1gpu"] = 3 * 131072 / (e0.elapsed_time(e1) * 1e-3) / 1e6
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        peaks = measured_peaks()
+        gemm_ms_per_step = (ms3[0] + ms3[1] + ms3[2]) / K_
+        algo_flops_per_step = TRAIN_FLOP_PER_RAY * RAYS_PER_GPU
+        achieved = algo_flops_per_step / (gemm_ms_per_step * 1e-3) / 1e12 if gemm_ms_per_step > 0 else None
+        n_gemm = ln3[0] + ln3[1] + ln3[2]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        per_mode = {}
+        for i, nm in enumerate(("nt_forward", "nn_dgrad", "tn_wgrad")):
+            if ln3[i]:
+                per_mode[nm] = {"launches_per_step": ln3[i] / K_, "ms_per_step": ms3[i] / K_,
+                                "executed_tflops": fl3[i] / (ms3[i] * 1e-3) / 1e12}
+        cpu_rate, cores, cpu_t = (None, None, None)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_rate, cores, cpu_t = cpu_train_step_rate(256, 2, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": K_, "warmup": W_,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": RAYS_PER_GPU, "global_batch_rays": world * RAYS_PER_GPU,
+                       "samples": f"{NC}+{NF}", "mlp": "8x256, PE L=10/4, bf16 tcgen05 operands, fp32 accumulate",
+                       "parallelism": f"dp{world} (one all-reduce of the flat gradient buffer per step)" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: 7.7 GB of activations streamed per step vs 126 MB L2, no flush needed",
+                       "loss": loss_val},
+            "clocks": clock_info,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": RAYS_PER_GPU * 9 * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": t_e2e / K_},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "rn::gemm_kernel<BN,MODE> (tcgen05 NT/NN/TN GEMMs of the MLP)",
+                         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic,
+                         "peak_source": peaks["source"],
+                         "algorithmic_flops_per_step": algo_flops_per_step, "gemm_launches_per_step": n_gemm / K_,
+                         "gemm_ms_per_step": gemm_ms_per_step, "gemm_share_of_step": gemm_ms_per_step / ms_per_step,
+                         "per_mode": per_mode},
+            "cpu_baseline": None if cpu_rate is None else {
+                "value": cpu_rate, "unit": "rays/s", "cores": cores, "kind": "port",
+                "sample": f"256-ray slice of the same training step, 2 timed steps after 1 warm-up ({cpu_t:.1f} s/step), numpy oracle port"},
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

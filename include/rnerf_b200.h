@@ -38,6 +38,13 @@ int rn_version(void);
 const char* rn_status_string(int status);
 int rn_last_cuda_error(void);            /* cudaError_t of the last RN_ERR_CUDA, else 0 */
 int rn_device_sm_count(int* sm_count_host);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
+unsigned long long rn_launch_count(void);
+/* measurement hooks: when enabled, every tcgen05 GEMM launch is bracketed by CUDA events on its
+ * stream; rn_prof_collect synchronises and returns, per mode (0 NT fwd, 1 NN dgrad, 2 TN wgrad),
+ * the summed kernel milliseconds, executed FLOPs (2*M*N*K incl. padding) and launch counts. */
+int rn_prof_enable(int on);
+int rn_prof_collect(double* ms3_host, double* flops3_host, int* launches3_host);
 
 /* ------------------------------------------------------------------------------------------
  * Network geometry (fixed: the reference's default ModelConfig, noisy_src/config.py:10-24;

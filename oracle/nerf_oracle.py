@@ -443,7 +443,7 @@ def raw2outputs_backward(cache, g_rgb_map, g_depth=None, g_acc=None, g_weights=N
 
 def render_rays(params_c, params_f, rays_o, rays_d, rcfg: Optional[RenderConfig] = None,
                 mcfg: Optional[ModelConfig] = None, is_train=True, t_rand=None, u=None,
-                noise_c=None, noise_f=None, keep_cache=False):
+                noise_c=None, noise_f=None, keep_cache=False, emulate_bf16=False):
     """noisy_src/rendering.py:119-240."""
     rcfg, mcfg = rcfg or RenderConfig(), mcfg or ModelConfig()
     rays_o, rays_d = _f32(rays_o), _f32(rays_d)
@@ -453,7 +453,7 @@ def render_rays(params_c, params_f, rays_o, rays_d, rcfg: Optional[RenderConfig]
     B, Nc = rays_o.shape[0], rcfg.num_samples
     pts_c, z_c = sample_along_rays(rays_o, rays_d, rcfg.near, rcfg.far, Nc, perturb, t_rand=t_rand)
     vd = np.broadcast_to(viewdirs[:, None, :], (B, Nc, 3)).reshape(-1, 3)
-    fc = nerf_forward(params_c, pts_c.reshape(-1, 3), vd, mcfg, keep_cache=keep_cache)
+    fc = nerf_forward(params_c, pts_c.reshape(-1, 3), vd, mcfg, keep_cache=keep_cache, emulate_bf16=emulate_bf16)
     out_c = raw2outputs(fc[0].reshape(B, Nc, 3), fc[1].reshape(B, Nc, 1), z_c, rays_d,
                         noise=noise_c if is_train else None,
                         white_background=rcfg.white_background, keep_cache=keep_cache)
@@ -465,7 +465,7 @@ def render_rays(params_c, params_f, rays_o, rays_d, rcfg: Optional[RenderConfig]
                                          rcfg.num_samples_fine, det=not is_train, u=u)
         Nt = z_f.shape[-1]
         vd = np.broadcast_to(viewdirs[:, None, :], (B, Nt, 3)).reshape(-1, 3)
-        ff = nerf_forward(params_f, pts_f.reshape(-1, 3), vd, mcfg, keep_cache=keep_cache)
+        ff = nerf_forward(params_f, pts_f.reshape(-1, 3), vd, mcfg, keep_cache=keep_cache, emulate_bf16=emulate_bf16)
         out_f = raw2outputs(ff[0].reshape(B, Nt, 3), ff[1].reshape(B, Nt, 1), z_f, rays_d,
                             noise=noise_f if is_train else None,
                             white_background=rcfg.white_background, keep_cache=keep_cache)
@@ -481,13 +481,13 @@ def render_rays(params_c, params_f, rays_o, rays_d, rcfg: Optional[RenderConfig]
 
 
 def train_step_grads(params_c, params_f, rays_o, rays_d, target, rcfg=None, mcfg=None,
-                     t_rand=None, u=None, need_ray_grad=False):
+                     t_rand=None, u=None, need_ray_grad=False, emulate_bf16=False):
     """Loss of noisy_src/train.py:88-99 (mse_coarse + mse_fine) and its gradients w.r.t.
     both nets' parameters (and rays_o / rays_d when `need_ray_grad`)."""
     rcfg, mcfg = rcfg or RenderConfig(), mcfg or ModelConfig()
     rays_o, rays_d, target = map(_f32, (rays_o, rays_d, target))
     res = render_rays(params_c, params_f, rays_o, rays_d, rcfg, mcfg, True, t_rand, u,
-                      keep_cache=True)
+                      keep_cache=True, emulate_bf16=emulate_bf16)
     cache = res["_cache"]
     B = rays_o.shape[0]
     n = F32(B * 3)

@@ -28,6 +28,9 @@ _SIGS = {
     "rn_status_string": (c_char_p, [c_int]),
     "rn_last_cuda_error": (c_int, []),
     "rn_device_sm_count": (c_int, [POINTER(c_int)]),
+    "rn_launch_count": (ctypes.c_ulonglong, []),
+    "rn_prof_enable": (c_int, [c_int]),
+    "rn_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     "rn_se3_poses_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "rn_se3_poses_bwd": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
     "rn_ray_directions": (c_int, [c_int, c_int, c_float, c_float, c_float, _P, _P]),

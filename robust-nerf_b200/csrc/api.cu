@@ -6,6 +6,7 @@
 namespace rn {
 
 int g_last_cuda_error = 0;
+unsigned long long g_launch_count = 0;
 
 int num_sms() {
   static int cached = 0;
@@ -81,6 +82,8 @@ const char* rn_status_string(int s) {
 }
 
 int rn_last_cuda_error(void) { return g_last_cuda_error; }
+
+unsigned long long rn_launch_count(void) { return g_launch_count; }
 
 int rn_device_sm_count(int* out) {
   RN_REQUIRE(out);

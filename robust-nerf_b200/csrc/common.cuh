@@ -8,6 +8,7 @@
 namespace rn {
 
 extern int g_last_cuda_error;
+extern unsigned long long g_launch_count;   // kernels launched through this library (bench.py: gpu_launches)
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = (int)e;
@@ -20,7 +21,11 @@ inline int cuda_fail(cudaError_t e) {
     if (_e != cudaSuccess) return rn::cuda_fail(_e); \
   } while (0)
 
-#define RN_LAUNCH_CHECK() RN_CUDA_CHECK(cudaGetLastError())
+#define RN_LAUNCH_CHECK()          \
+  do {                             \
+    ++rn::g_launch_count;          \
+    RN_CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
 
 #define RN_REQUIRE(cond)                     \
   do {                                       \

@@ -21,6 +21,8 @@
 #include "gemm.h"
 #include <cuda_bf16.h>
 #include <stdio.h>
+#include <utility>
+#include <vector>
 
 namespace rn {
 
@@ -384,6 +386,28 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
   return r == CUDA_SUCCESS ? RN_OK : RN_ERR_DRIVER;
 }
 
+// ---- optional per-launch CUDA-event timing (bench.py roofline: live kernel durations on the
+// launching stream inside the timed region) ----
+struct ProfRec { cudaEvent_t a, b; int mode; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+static double g_prof_next_flops = 0.0;
+
+static void prof_begin(int mode, cudaStream_t st, int* slot) {
+  *slot = -1;
+  if (!g_prof_on || g_prof.size() >= 16384) return;
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (!g_prof_pool.empty()) { ev = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) return;
+  cudaEventRecord(ev.first, st);
+  g_prof.push_back({ev.first, ev.second, mode, g_prof_next_flops});
+  *slot = (int)g_prof.size() - 1;
+}
+static void prof_end(int slot, cudaStream_t st) {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+}
+
 template <int BN, int MODE>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tM,
                        const GemmArgs& args, int grid, cudaStream_t st) {
@@ -393,7 +417,10 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     RN_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
+  int slot;
+  prof_begin(MODE, st, &slot);
   gemm_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tA, tB, tD, tM, args);
+  prof_end(slot, st);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
@@ -422,6 +449,7 @@ int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int
   GemmArgs a{};
   a.m_tiles = (int)ceil_div(M, kBlockM); a.k_chunks = (int)ceil_div(K, kBlockK); a.k_total = K; a.bias = bias; a.relu = relu;
   const int grid = a.m_tiles < num_sms() ? a.m_tiles : num_sms();
+  g_prof_next_flops = 2.0 * (double)M * N * K;
   if (N == 256) return launch_gemm<256, MODE_NT>(tA, tB, tD, tD, a, grid, st);
   if (N == 128) return launch_gemm<128, MODE_NT>(tA, tB, tD, tD, a, grid, st);
   return launch_gemm<64, MODE_NT>(tA, tB, tD, tD, a, grid, st);
@@ -442,6 +470,7 @@ int gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int
   GemmArgs a{};
   a.m_tiles = (int)ceil_div(M, kBlockM); a.k_chunks = (int)ceil_div(K, kBlockK); a.k_total = K; a.has_mask = mask != nullptr;
   const int grid = a.m_tiles < num_sms() ? a.m_tiles : num_sms();
+  g_prof_next_flops = 2.0 * (double)M * N * K;
   if (N == 256) return launch_gemm<256, MODE_NN>(tA, tB, tD, tM, a, grid, st);
   return launch_gemm<64, MODE_NN>(tA, tB, tD, tM, a, grid, st);
 }
@@ -471,6 +500,7 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
   a.partial = scratch;
   RN_REQUIRE((size_t)a.splits * a.m_tiles * kBlockM * (N + 1) * sizeof(float) <= scratch_bytes);
   const int grid = a.m_tiles * a.splits;
+  g_prof_next_flops = 2.0 * (double)K * N * Mo;
   if (N == 256) rc = launch_gemm<256, MODE_TN>(tA, tB, tA, tA, a, grid, st);
   else rc = launch_gemm<64, MODE_TN>(tA, tB, tA, tA, a, grid, st);
   info->m_tiles = a.m_tiles; info->splits = a.splits; info->N = N; info->scratch = scratch;
@@ -494,6 +524,28 @@ using namespace rn;
 extern "C" {
 
 size_t rn_gemm_scratch_bytes(void) { return gemm_tn_scratch_bytes(); }
+
+int rn_prof_enable(int on) {
+  g_prof_on = on != 0;
+  return RN_OK;
+}
+
+// Synchronises the device, then sums the recorded GEMM launches by mode (0 NT, 1 NN, 2 TN):
+// total milliseconds, executed (padded) FLOPs and launch counts; clears the record.
+int rn_prof_collect(double* ms3_host, double* flops3_host, int* launches3_host) {
+  RN_REQUIRE(ms3_host && flops3_host && launches3_host);
+  RN_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < 3; ++i) { ms3_host[i] = 0.0; flops3_host[i] = 0.0; launches3_host[i] = 0; }
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms3_host[r.mode] += ms; flops3_host[r.mode] += r.flops; launches3_host[r.mode] += 1;
+    }
+    g_prof_pool.push_back({r.a, r.b});
+  }
+  g_prof.clear();
+  return RN_OK;
+}
 
 int rn_gemm_bf16(int mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N,
                  int64_t K, const float* bias, int relu, const void* mask, int64_t ldmask, float* colsum_out, void* scratch,
