@@ -153,6 +153,10 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
 
+    # libraries (NCCL with NCCL_DEBUG=VERSION, ...) may print to stdout: keep fd 1 clean for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -313,7 +317,10 @@ def run_gpu(args):
                 "sample": f"256-ray slice of the same training step, 2 timed steps after 1 warm-up ({cpu_t:.1f} s/step), numpy oracle port"},
             "extra": extra,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

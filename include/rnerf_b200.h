@@ -175,7 +175,8 @@ size_t rn_gemm_scratch_bytes(void);
  * buffer into ranges clipped independently (joint clip = 1 group; pose-opt = one group per net). */
 int rn_clip_adam_step(float* params, float* grads /*scaled in place by the clip*/, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const int64_t* group_offsets_host /*[n_groups+1]*/, const float* group_max_norm_host, int n_groups,
-                      float lr, float beta1, float beta2, float eps, int step, float* norms_out /*[n_groups]*/,
+                      float lr, float beta1, float beta2, float eps, int step,
+                      float* norms_out /*scratch+output, 8 + 8*64 floats; [0..n_groups) = gradient norms*/,
                       rn_stream_t stream);
 
 #ifdef __cplusplus

@@ -24,35 +24,50 @@ int num_sms() {
 constexpr int kMaxGroups = 8;
 struct Groups { int64_t off[kMaxGroups + 1]; float max_norm[kMaxGroups]; int n; };
 
-// one CTA per clip group, fixed reduction order -> deterministic norm
-__global__ void __launch_bounds__(1024)
-grad_norm_kernel(const float* __restrict__ g, Groups gr, float* __restrict__ norms) {
-  __shared__ float red[32];
-  const int grp = blockIdx.x;
+constexpr int kNormChunks = 64;      // CTAs per clip group
+
+// grid (kNormChunks, n_groups): fixed-order partial sums of squares -> part[group][chunk]
+__global__ void __launch_bounds__(256)
+grad_sumsq_kernel(const float* __restrict__ g, Groups gr, float* __restrict__ part) {
+  __shared__ float red[8];
+  const int grp = blockIdx.y;
+  const int64_t lo = gr.off[grp], hi = gr.off[grp + 1];
+  const int64_t per = (hi - lo + kNormChunks - 1) / kNormChunks;
+  const int64_t a = lo + per * blockIdx.x, b = (a + per < hi) ? a + per : hi;
   float acc = 0.f;
-  for (int64_t i = gr.off[grp] + threadIdx.x; i < gr.off[grp + 1]; i += 1024) { const float v = g[i]; acc = fmaf(v, v, acc); }
+  for (int64_t i = a + threadIdx.x; i < b; i += 256) { const float v = g[i]; acc = fmaf(v, v, acc); }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
-    for (int w = 0; w < 32; ++w) t += red[w];
-    norms[grp] = sqrtf(t);
+    for (int w = 0; w < 8; ++w) t += red[w];
+    part[grp * kNormChunks + blockIdx.x] = t;
   }
 }
 
 // clip (torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)), grads scaled in
-// place) followed by torch.optim.Adam's default update.
-__global__ void clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                 int64_t n, Groups gr, const float* __restrict__ norms, float lr, float b1, float b2,
-                                 float eps, float bc1, float bc2_sqrt) {
+// place) followed by torch.optim.Adam's default update.  Every CTA re-reduces the (tiny) partial
+// sums in the same fixed order, so all threads see the same norm without another launch.
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 int64_t n, Groups gr, const float* __restrict__ part, float* __restrict__ norms, float lr, float b1,
+                 float b2, float eps, float bc1, float bc2_sqrt) {
+  __shared__ float s_coef[kMaxGroups];
+  if (threadIdx.x < gr.n) {
+    float t = 0.f;
+    for (int c = 0; c < kNormChunks; ++c) t += part[threadIdx.x * kNormChunks + c];
+    const float nrm = sqrtf(t);
+    if (blockIdx.x == 0) norms[threadIdx.x] = nrm;
+    const float mx = gr.max_norm[threadIdx.x];
+    s_coef[threadIdx.x] = mx > 0.f ? fminf(1.0f, mx / (nrm + 1e-6f)) : 1.0f;
+  }
+  __syncthreads();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int grp = 0;
 #pragma unroll
     for (int k = 1; k < kMaxGroups; ++k) if (k < gr.n && i >= gr.off[k]) grp = k;
-    float coef = 1.0f;
-    if (gr.max_norm[grp] > 0.f) coef = fminf(1.0f, gr.max_norm[grp] / (norms[grp] + 1e-6f));
-    const float gi = g[i] * coef;
+    const float gi = g[i] * s_coef[grp];
     g[i] = gi;
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
@@ -105,12 +120,13 @@ int rn_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_av
   for (int i = 0; i < n_groups; ++i) gr.max_norm[i] = group_max_norm_host[i];
   RN_REQUIRE(gr.off[0] == 0 && gr.off[n_groups] == n);
   cudaStream_t st = (cudaStream_t)stream;
-  grad_norm_kernel<<<n_groups, 1024, 0, st>>>(grads, gr, norms_out);
+  float* part = norms_out + kMaxGroups;     // norms_out must hold kMaxGroups + kMaxGroups*64 floats
+  grad_sumsq_kernel<<<dim3(kNormChunks, n_groups), 256, 0, st>>>(grads, gr, part);
   RN_LAUNCH_CHECK();
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-  clip_adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, gr, norms_out, lr, beta1, beta2,
-                                                     eps, bc1, bc2_sqrt);
+  clip_adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, gr, part, norms_out, lr, beta1,
+                                                     beta2, eps, bc1, bc2_sqrt);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -174,96 +174,89 @@ encode_bwd_dirs_kernel(const float* __restrict__ dirs, int64_t R, int group, con
 }
 
 // ------------------------------------------------------------------------------------------
-// heads: sigma_pre = H7 . w_sigma + b, rgb_pre = HC . W_rgb^T + b   (fp32 weights, bf16 activations)
-// 8 lanes per point.
+// heads backward (the forward heads are fused into the GEMM epilogues, gemm_tcgen05.cu).
+// thread <-> (point, 8-column group of HC): coalesced 16 B loads/stores, 16 threads per point.
+//   dHC[m, j]      = (HC[m, j] > 0) * sum_c g_raw[m, c] * W_rgb[c, j]                (bf16)
+//   dFS[m, 256..]  = (d sigma_pre, 0, ...)                                            (bf16)
+//   dW_rgb[c, j]  += g_raw[m, c] * HC[m, j],  db_rgb[c] += g_raw[m, c]   per-thread partials, reduced
+//                    in a fixed order: block tree here, heads_bwd_reduce_kernel across CTAs.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-heads_fwd_kernel(const __nv_bfloat16* __restrict__ H7, const __nv_bfloat16* __restrict__ HC, int64_t M,
-                 const float* __restrict__ f32sec, float4* __restrict__ raw) {
-  __shared__ float s_w[256 + 384 + 8];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_w[i] = f32sec[kWSig + i];
-  for (int i = threadIdx.x; i < 384; i += blockDim.x) s_w[256 + i] = f32sec[kWRgb + i];
-  if (threadIdx.x < 4) { s_w[640 + threadIdx.x] = f32sec[kBRgb + threadIdx.x]; s_w[644 + threadIdx.x] = f32sec[kBSig + threadIdx.x]; }
-  __syncthreads();
-  const int sub = threadIdx.x & 7;
-  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) >> 3;
-  const int64_t iters = (M + gstride - 1) / gstride;
-  int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
-  for (int64_t it = 0; it < iters; ++it, m += gstride) {
-    const bool valid = m < M;
-    float as = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (valid) {
-      const uint4* h = reinterpret_cast<const uint4*>(H7 + m * 256 + sub * 32);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 u = __ldcs(h + i);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = sub * 32 + i * 8 + 2 * e;
-          as = fmaf(bf16_lo(w[e]), s_w[j], as);
-          as = fmaf(bf16_hi(w[e]), s_w[j + 1], as);
-        }
-      }
-      const uint4* c = reinterpret_cast<const uint4*>(HC + m * 128 + sub * 16);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint4 u = __ldcs(c + i);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = sub * 16 + i * 8 + 2 * e;
-          const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
-          a0 = fmaf(lo, s_w[256 + j], a0); a0 = fmaf(hi, s_w[256 + j + 1], a0);
-          a1 = fmaf(lo, s_w[384 + j], a1); a1 = fmaf(hi, s_w[384 + j + 1], a1);
-          a2 = fmaf(lo, s_w[512 + j], a2); a2 = fmaf(hi, s_w[512 + j + 1], a2);
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      as += __shfl_xor_sync(0xffffffffu, as, o);
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (valid && sub == 0) raw[m] = make_float4(a0 + s_w[640], a1 + s_w[641], a2 + s_w[642], as + s_w[644]);
-  }
-}
+constexpr int kHeadsBwdThreads = 256;
+constexpr int kHeadsBwdCtasPerSm = 4;
 
-// backward of the heads.  CTA = 128 threads <-> the 128 columns of HC; each CTA walks a contiguous
-// slice of points.  Writes dHC (masked by HC > 0, bf16), column 256.. of dFS (d sigma_pre, bf16) and
-// per-CTA partial sums of dW_rgb / db_rgb (reduced in fixed order by heads_bwd_reduce_kernel).
-constexpr int kHeadsBwdPts = 512;
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kHeadsBwdThreads)
 heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restrict__ HC, int64_t M,
                  const float* __restrict__ f32sec, __nv_bfloat16* __restrict__ dHC, __nv_bfloat16* __restrict__ dFS,
                  int ldfs, float* __restrict__ partial /*[grid][388]*/) {
-  const int j = threadIdx.x;
-  const float w0 = f32sec[kWRgb + j], w1 = f32sec[kWRgb + 128 + j], w2 = f32sec[kWRgb + 256 + j];
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b = 0.f;
-  const int64_t m0 = (int64_t)blockIdx.x * kHeadsBwdPts;
-  const int64_t m1 = m0 + kHeadsBwdPts < M ? m0 + kHeadsBwdPts : M;
-  for (int64_t m = m0; m < m1; ++m) {
+  __shared__ float s_red[kHeadsBwdThreads / 16][16][25];
+  const int cg = threadIdx.x & 15;            // column group: columns 8*cg .. 8*cg+7
+  const int pl = threadIdx.x >> 4;            // point lane inside the CTA
+  float w[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[c][e] = f32sec[kWRgb + c * 128 + cg * 8 + e];
+  float acc[3][8], bacc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+  const int64_t pstride = (int64_t)gridDim.x * (kHeadsBwdThreads / 16);
+  for (int64_t m = (int64_t)blockIdx.x * (kHeadsBwdThreads / 16) + pl; m < M; m += pstride) {
     const float4 g = __ldg(g_raw + m);
-    const float hc = __bfloat162float(HC[m * 128 + j]);
-    a0 = fmaf(g.x, hc, a0); a1 = fmaf(g.y, hc, a1); a2 = fmaf(g.z, hc, a2);
-    const float d = (hc > 0.f) ? (g.x * w0 + g.y * w1 + g.z * w2) : 0.f;
-    dHC[m * 128 + j] = __float2bfloat16_rn(d);
-    if (j < 16) dFS[m * ldfs + 256 + j] = __float2bfloat16_rn(j == 0 ? g.w : 0.f);
-    if (j < 3) b += (j == 0 ? g.x : (j == 1 ? g.y : g.z));
+    const uint4 hv = __ldcs(reinterpret_cast<const uint4*>(HC + m * 128 + cg * 8));
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    uint32_t outw[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      const float h0 = bf16_lo(hw[e2]), h1 = bf16_hi(hw[e2]);
+      acc[0][2 * e2] = fmaf(g.x, h0, acc[0][2 * e2]); acc[0][2 * e2 + 1] = fmaf(g.x, h1, acc[0][2 * e2 + 1]);
+      acc[1][2 * e2] = fmaf(g.y, h0, acc[1][2 * e2]); acc[1][2 * e2 + 1] = fmaf(g.y, h1, acc[1][2 * e2 + 1]);
+      acc[2][2 * e2] = fmaf(g.z, h0, acc[2][2 * e2]); acc[2][2 * e2 + 1] = fmaf(g.z, h1, acc[2][2 * e2 + 1]);
+      const float d0 = h0 > 0.f ? (g.x * w[0][2 * e2] + g.y * w[1][2 * e2] + g.z * w[2][2 * e2]) : 0.f;
+      const float d1 = h1 > 0.f ? (g.x * w[0][2 * e2 + 1] + g.y * w[1][2 * e2 + 1] + g.z * w[2][2 * e2 + 1]) : 0.f;
+      outw[e2] = pack_bf16(d0, d1);
+    }
+    *reinterpret_cast<uint4*>(dHC + m * 128 + cg * 8) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    if (cg == 0) {
+      bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z;
+      *reinterpret_cast<uint4*>(dFS + m * ldfs + 256) = make_uint4(pack_bf16(g.w, 0.f), 0, 0, 0);
+    } else if (cg == 1) {
+      *reinterpret_cast<uint4*>(dFS + m * ldfs + 264) = make_uint4(0, 0, 0, 0);
+    }
   }
+  // fixed-order reduction over the 16 point lanes of the CTA
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_red[pl][cg][c * 8 + e] = acc[c][e];
+  s_red[pl][cg][24] = (cg == 0) ? 0.f : 0.f;
+  __syncthreads();
   float* p = partial + (size_t)blockIdx.x * 388;
-  p[j] = a0; p[128 + j] = a1; p[256 + j] = a2;
-  if (j < 3) p[384 + j] = b;
+  for (int o = threadIdx.x; o < 384; o += kHeadsBwdThreads) {
+    const int c = o / 128, j = o % 128;
+    float a = 0.f;
+    for (int l = 0; l < kHeadsBwdThreads / 16; ++l) a += s_red[l][j >> 3][c * 8 + (j & 7)];
+    p[o] = a;
+  }
+  __syncthreads();
+  if (cg == 0) { s_red[pl][0][0] = bacc[0]; s_red[pl][0][1] = bacc[1]; s_red[pl][0][2] = bacc[2]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float a = 0.f;
+    for (int l = 0; l < kHeadsBwdThreads / 16; ++l) a += s_red[l][0][threadIdx.x];
+    p[384 + threadIdx.x] = a;
+  }
 }
+// one warp per output, lanes over the per-CTA partials, fixed shuffle tree
 __global__ void heads_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ gWrgb,
                                         float* __restrict__ gBrgb) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 387) return;
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (o >= 387) return;
   float acc = 0.f;
-  for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * 388 + i];
-  if (i < 384) gWrgb[i] = acc; else gBrgb[i - 384] = acc;
+  for (int b = lane; b < nblk; b += 32) acc += partial[(size_t)b * 388 + o];
+  acc = warp_sum(acc);
+  if (lane == 0) { if (o < 384) gWrgb[o] = acc; else gBrgb[o - 384] = acc; }
 }
 
 // model.py:181,194 activations for the NeRF.forward API
@@ -346,20 +339,14 @@ int launch_encode(const float* pts, const float* dirs, int64_t M, int group, voi
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
-int launch_heads_fwd(const void* H7, const void* HC, int64_t M, const float* f32sec, float* raw, cudaStream_t st) {
-  heads_fwd_kernel<<<grid_for(M * 8, 256), 256, 0, st>>>((const __nv_bfloat16*)H7, (const __nv_bfloat16*)HC, M, f32sec,
-                                                          (float4*)raw);
-  RN_LAUNCH_CHECK();
-  return RN_OK;
-}
-size_t heads_bwd_scratch_bytes(int64_t M) { return (size_t)ceil_div(M, kHeadsBwdPts) * 388 * sizeof(float); }
+size_t heads_bwd_scratch_bytes(int64_t M) { return (size_t)num_sms() * kHeadsBwdCtasPerSm * 388 * sizeof(float) + 256; }
 int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,
                      float* scratch, float* gWrgb, float* gBrgb, cudaStream_t st) {
-  const int nblk = (int)ceil_div(M, kHeadsBwdPts);
-  heads_bwd_kernel<<<nblk, 128, 0, st>>>((const float4*)g_raw, (const __nv_bfloat16*)HC, M, f32sec, (__nv_bfloat16*)dHC,
-                                         (__nv_bfloat16*)dFS, ldfs, scratch);
+  const int nblk = num_sms() * kHeadsBwdCtasPerSm;
+  heads_bwd_kernel<<<nblk, kHeadsBwdThreads, 0, st>>>((const float4*)g_raw, (const __nv_bfloat16*)HC, M, f32sec,
+                                                      (__nv_bfloat16*)dHC, (__nv_bfloat16*)dFS, ldfs, scratch);
   RN_LAUNCH_CHECK();
-  heads_bwd_reduce_kernel<<<4, 128, 0, st>>>(scratch, nblk, gWrgb, gBrgb);
+  heads_bwd_reduce_kernel<<<(387 * 32 + 255) / 256, 256, 0, st>>>(scratch, nblk, gWrgb, gBrgb);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

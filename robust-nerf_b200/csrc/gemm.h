@@ -8,7 +8,8 @@ namespace rn {
 struct TnInfo { int m_tiles, splits, N; float* scratch; };
 int check_arch();
 int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
-            const float* bias, int relu, cudaStream_t st);
+            const float* bias, int relu, cudaStream_t st, int n_heads = 0, const float* head_w = nullptr,
+            const float* head_b = nullptr, float* head_out = nullptr, int head_col = 0);
 int gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
             const void* mask, int64_t ldmask, cudaStream_t st);
 size_t gemm_tn_scratch_bytes();
@@ -18,7 +19,6 @@ int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int ncols, float* ds
                    cudaStream_t st);
 
 int launch_encode(const float* pts, const float* dirs, int64_t M, int group, void* XC, int ldx, void* FD, int ldf, cudaStream_t st);
-int launch_heads_fwd(const void* H7, const void* HC, int64_t M, const float* f32sec, float* raw, cudaStream_t st);
 size_t heads_bwd_scratch_bytes(int64_t M);
 int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,
                      float* scratch, float* gWrgb, float* gBrgb, cudaStream_t st);

@@ -45,6 +45,12 @@ struct GemmArgs {
   const float* bias;      // NT (may be null)
   int relu;               // NT
   int has_mask;           // NN
+  int64_t m_rows;         // NT: valid rows of D (head outputs are bounds-checked against it)
+  int n_heads;            // NT: 0, or number of fused fp32 head dot-products (1 = sigma, 3 = rgb)
+  const float* head_w;    // NT: [n_heads][BN] fp32
+  const float* head_b;    // NT: [n_heads] fp32
+  float* head_out;        // NT: raw[M][4]; head h is written to column head_col + h
+  int head_col;
   float* partial;         // TN: [m_tiles*splits][128*(BN+1)] fp32
   int splits;             // TN
   int chunks_per_split;   // TN
@@ -55,12 +61,13 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = (MODE == MODE_TN) ? kOnesBytes : (BN / 64) * 16384;
-  static constexpr int kBudget = 225 * 1024 - kStagingBytes - 2048 /*bias+barriers*/ - 1024 /*align slack*/;
+  static constexpr int kHeadBytes = (MODE == MODE_NT) ? 3 * BN * 4 : 0;    // fused head weights (fp32)
+  static constexpr int kBudget = 225 * 1024 - kStagingBytes - kHeadBytes - 2048 /*bias+barriers*/ - 1024 /*align slack*/;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccCols = (MODE == MODE_TN) ? (BN + 16) : 2 * BN;
   static constexpr int kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 2048 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kHeadBytes + 2048 + 1024;
   static_assert(kStages >= 2, "pipeline too shallow");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128, 192 or 256");
 };
@@ -75,7 +82,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_stage = smem;
   uint8_t* s_staging = smem + NS * Cfg::kStageBytes;
-  float* s_bias = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes);
+  float* s_head = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes);           // [3][BN] (NT only)
+  float* s_bias = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes + Cfg::kHeadBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint64_t* full_bar = bars;                 // [NS]
   uint64_t* empty_bar = bars + NS;           // [NS]
@@ -102,6 +110,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int t = threadIdx.x - 64;
     if (MODE == MODE_NT) {
       for (int i = t; i < BN; i += kEpiThreads) s_bias[i] = args.bias ? args.bias[i] : 0.f;
+      for (int i = t; i < args.n_heads * BN; i += kEpiThreads) s_head[i] = args.head_w[i];
     }
     if (MODE == MODE_TN) {
       uint32_t* ones = reinterpret_cast<uint32_t*>(s_staging);
@@ -186,6 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tmem_full[acc], acc_ph);
         tcgen05_fence_after();
         const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+        float hacc0 = 0.f, hacc1 = 0.f, hacc2 = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
@@ -215,8 +225,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
               __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
               packed[e] = *reinterpret_cast<uint32_t*>(&p);
+              if (MODE == MODE_NT && args.n_heads > 0) {
+                // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation that is stored
+                const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xFFFF0000u);
+                const int j = c * 32 + cc * 8 + 2 * e;
+                hacc0 = fmaf(r0, s_head[j], hacc0); hacc0 = fmaf(r1, s_head[j + 1], hacc0);
+                if (args.n_heads == 3) {
+                  hacc1 = fmaf(r0, s_head[BN + j], hacc1); hacc1 = fmaf(r1, s_head[BN + j + 1], hacc1);
+                  hacc2 = fmaf(r0, s_head[2 * BN + j], hacc2); hacc2 = fmaf(r1, s_head[2 * BN + j + 1], hacc2);
+                }
+              }
             }
             *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+        }
+        if (MODE == MODE_NT && args.n_heads > 0) {
+          const int64_t gr = (int64_t)tile * kBlockM + row;
+          if (gr < args.m_rows) {
+            float* o = args.head_out + gr * 4 + args.head_col;
+            o[0] = hacc0 + args.head_b[0];
+            if (args.n_heads == 3) { o[1] = hacc1 + args.head_b[1]; o[2] = hacc2 + args.head_b[2]; }
           }
         }
         // accumulator drained -> hand it back to the MMA warp
@@ -338,12 +366,14 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int m_ti
       if (!dst) continue;
       const int r = row0 + i / ncols, c = i % ncols;
       const int mt = r / kBlockM, rr = r % kBlockM;
+#pragma unroll 8
       for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * m_tiles + mt) * blk + (size_t)rr * BN + c];
       dst[(int64_t)(i / ncols) * dst_ld + c] = acc;
     } else {
       if (!colsum_dst) continue;
       const int r = row0 + (i - total);
       const int mt = r / kBlockM, rr = r % kBlockM;
+#pragma unroll 8
       for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * m_tiles + mt) * blk + (size_t)kBlockM * BN + rr];
       colsum_dst[i - total] = acc;
     }
@@ -438,7 +468,8 @@ int check_arch() {
 
 // D[M,N] = act(A[M,K] B[N,K]^T + bias)        (forward layer)
 int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
-            const float* bias, int relu, cudaStream_t st) {
+            const float* bias, int relu, cudaStream_t st, int n_heads, const float* head_w, const float* head_b,
+            float* head_out, int head_col) {
   int rc = check_arch();
   if (rc != RN_OK) return rc;
   RN_REQUIRE(M > 0 && K > 0 && K % 8 == 0 && (N == 256 || N == 128 || N == 64));
@@ -448,6 +479,8 @@ int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int
   if ((rc = make_tmap(&tD, D, N, M, ldd, kBlockM)) != RN_OK) return rc;
   GemmArgs a{};
   a.m_tiles = (int)ceil_div(M, kBlockM); a.k_chunks = (int)ceil_div(K, kBlockK); a.k_total = K; a.bias = bias; a.relu = relu;
+  RN_REQUIRE(n_heads == 0 || ((n_heads == 1 || n_heads == 3) && head_w && head_b && head_out));
+  a.m_rows = M; a.n_heads = n_heads; a.head_w = head_w; a.head_b = head_b; a.head_out = head_out; a.head_col = head_col;
   const int grid = a.m_tiles < num_sms() ? a.m_tiles : num_sms();
   g_prof_next_flops = 2.0 * (double)M * N * K;
   if (N == 256) return launch_gemm<256, MODE_NT>(tA, tB, tD, tD, a, grid, st);
@@ -552,7 +585,7 @@ int rn_gemm_bf16(int mode, const void* A, int64_t lda, const void* B, int64_t ld
                  size_t scratch_bytes, rn_stream_t stream) {
   RN_REQUIRE(A && B && D);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == MODE_NT) return gemm_nt(A, lda, B, ldb, D, ldd, M, N, (int)K, bias, relu, st);
+  if (mode == MODE_NT) return gemm_nt(A, lda, B, ldb, D, ldd, M, N, (int)K, bias, relu, st, 0, nullptr, nullptr, nullptr, 0);
   if (mode == MODE_NN) return gemm_nn(A, lda, B, ldb, D, ldd, M, N, (int)K, mask, ldmask, st);
   if (mode == MODE_TN) {
     TnInfo info;

@@ -11,7 +11,8 @@
 //   L6, L7      ...                   -> H7
 //   feature     H7 x WFS[0:256]^T     -> FD[:, 0:256]  (no activation)
 //   dir         FD[:, 0:320] x WD^T   -> HC            (N=128, K=320)
-//   heads       (H7 . w_sigma, HC . W_rgb) -> raw[M,4]  (fp32 CUDA cores)
+//   heads       sigma = H7 . w_sigma and rgb = HC . W_rgb^T are fp32 dot products fused into the
+//               epilogues of L7 and of the view-branch GEMM -> raw[M,4]
 // Backward mirrors it: heads_bwd, then per layer one TN GEMM (weight + bias gradient, split-K over
 // points) and one NN GEMM (data gradient with the ReLU mask of the layer input fused in).
 #include "common.cuh"
@@ -87,11 +88,14 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
     const bf16* in = (l == 5) ? XC : H[l - 1];
     const int K = (l == 5) ? 320 : 256;
     const int ldin = (l == 5) ? 320 : ld_of(l - 1);
-    RN_TRY(gemm_nt(in, ldin, W + trunk_w(l), K, H[l], ld_of(l), M, 256, K, F + kB0 + 256 * l, 1, st));
+    if (l == 7)   // sigma head fused into the epilogue: raw[:, 3] = H7 . w_sigma + b_sigma
+      RN_TRY(gemm_nt(in, ldin, W + trunk_w(l), K, H[l], ld_of(l), M, 256, K, F + kB0 + 256 * l, 1, st, 1, F + kWSig, F + kBSig, raw, 3));
+    else
+      RN_TRY(gemm_nt(in, ldin, W + trunk_w(l), K, H[l], ld_of(l), M, 256, K, F + kB0 + 256 * l, 1, st));
   }
   RN_TRY(gemm_nt(H[7], 256, W + kWFS, 256, FD, 320, M, 256, 256, F + kBF, 0, st));
-  RN_TRY(gemm_nt(FD, 320, W + kWD, 320, HC, 128, M, 128, 320, F + kBD, 1, st));
-  RN_TRY(launch_heads_fwd(H[7], HC, M, F, raw, st));
+  // rgb head fused into the view-branch epilogue: raw[:, 0:3] = HC . W_rgb^T + b_rgb
+  RN_TRY(gemm_nt(FD, 320, W + kWD, 320, HC, 128, M, 128, 320, F + kBD, 1, st, 3, F + kWRgb, F + kBRgb, raw, 0));
   return RN_OK;
 }
 

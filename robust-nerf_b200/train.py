@@ -206,7 +206,7 @@ class Trainer:
             off = _flatten_into(ps, self.flat, self.gflat, off)
             self.net_offsets.append(off)
         off = _flatten_into(self.pose_params, self.flat, self.gflat, off)
-        self.norms = torch.zeros(8, device=dev)
+        self.norms = torch.zeros(2 * (8 + 8 * 64), device=dev)    # two rn_clip_adam_step scratch areas
         self.iteration = 0
         self.pose_steps = 0
         self.nets = nets
@@ -243,7 +243,7 @@ class Trainer:
             self.pose_steps += 1
             plr = self.pose_lr * (0.1 ** ((self.pose_steps - 1) / self.lr_decay_steps))
             self._adam(self.n_net, self.n_net + self.n_pose, [self.n_net, self.n_net + self.n_pose], [0.1], plr,
-                       self.pose_steps, 4)
+                       self.pose_steps, 8 + 8 * 64)
         for m in self.nets:
             m._packed.key = None          # parameters changed under the bf16 cache
 
