@@ -161,11 +161,14 @@ int rn_posenc_bwd(const float* x, int64_t n, int C, int num_freqs, const float* 
 
 /* ---- building block exposed for unit tests / profiling: one bf16 tcgen05 GEMM ----
  * mode 0 (NT): D[M,N] = act(A[M,K] * B[N,K]^T + bias)            forward layer
- * mode 1 (NN): D[M,N] = (A[M,K] * B[K,N]) (.) (mask[M,N] > 0)     data gradient
+ * mode 1 (NN): D[M,N] = (A[M,K] * B[K,N]) (.) mask                data gradient
  * mode 2 (TN): D[Mo,N] (fp32) = A[K,Mo]^T * B[K,N]                weight gradient (split-K inside)
- * A, B, mask, D(mode 0/1) are bf16 with leading dimensions in ELEMENTS; ld % 8 == 0. */
+ * A, B, D(mode 0/1) are bf16 with leading dimensions in ELEMENTS; ld % 8 == 0.
+ * ReLU masks are packed: [M][N/32] uint32 words, bit j of word c <=> element (m, 32c+j) > 0.
+ * mode 0 optionally WRITES the mask of its (bf16-rounded) output to mask_out; mode 1 optionally
+ * APPLIES mask_bits to its output. */
 int rn_gemm_bf16(int mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
-                 int64_t M, int N, int64_t K, const float* bias, int relu, const void* mask, int64_t ldmask,
+                 int64_t M, int N, int64_t K, const float* bias, int relu, const uint32_t* mask_bits, uint32_t* mask_out,
                  float* colsum_out /*mode 2: sum_k A[k,:] (bias gradient) or NULL*/, void* scratch, size_t scratch_bytes,
                  rn_stream_t stream);
 size_t rn_gemm_scratch_bytes(void);

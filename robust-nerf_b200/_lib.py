@@ -61,7 +61,7 @@ _SIGS = {
     "rn_posenc_fwd": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "rn_posenc_bwd": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P]),
     "rn_gemm_bf16": (c_int, [c_int, _P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int, c_int64, _P, c_int, _P,
-                             c_int64, _P, _P, c_size_t, _P]),
+                             _P, _P, _P, c_size_t, _P]),
     "rn_gemm_scratch_bytes": (c_size_t, []),
     "rn_clip_adam_step": (c_int, [_P, _P, _P, _P, c_int64, POINTER(c_int64), POINTER(c_float), c_int, c_float, c_float,
                                   c_float, c_float, c_int, _P, _P]),

@@ -8,10 +8,10 @@ namespace rn {
 struct TnInfo { int m_tiles, splits, N; float* scratch; };
 int check_arch();
 int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
-            const float* bias, int relu, cudaStream_t st, int n_heads = 0, const float* head_w = nullptr,
-            const float* head_b = nullptr, float* head_out = nullptr, int head_col = 0);
+            const float* bias, int relu, cudaStream_t st, uint32_t* mask_out = nullptr, int n_heads = 0,
+            const float* head_w = nullptr, const float* head_b = nullptr, float* head_out = nullptr, int head_col = 0);
 int gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
-            const void* mask, int64_t ldmask, cudaStream_t st);
+            const uint32_t* mask_bits, cudaStream_t st);
 size_t gemm_tn_scratch_bytes();
 int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ldb, int N, int64_t K, float* scratch,
                    size_t scratch_bytes, TnInfo* info, cudaStream_t st);

@@ -33,10 +33,10 @@ enum { MODE_NT = 0, MODE_NN = 1, MODE_TN = 2 };
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;               // one 128-byte swizzle span of bf16
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 224;         // 7 warps: A producer, MMA, 4 epilogue, B producer
 constexpr int kEpiThreads = 128;
 constexpr int kOnesBytes = 2048;          // 16 k-rows x 128 B of bf16 1.0 (TN bias-gradient trick)
-
+constexpr int kMaxSmem = 231424;          // 226 KiB (1 KiB under the 227 KiB per-block limit)
 
 struct GemmArgs {
   int m_tiles;            // NT/NN: 128-row tiles of D;  TN: 128-row tiles of Mo
@@ -44,8 +44,9 @@ struct GemmArgs {
   int k_total;            // K
   const float* bias;      // NT (may be null)
   int relu;               // NT
-  int has_mask;           // NN
-  int64_t m_rows;         // NT: valid rows of D (head outputs are bounds-checked against it)
+  int64_t m_rows;         // NT/NN: valid rows of D (per-row global accesses are bounds-checked against it)
+  uint32_t* mask_out;     // NT: packed ReLU mask of D, [M][BN/32] words (bit j of word c <=> D[m, 32c+j] > 0), or null
+  const uint32_t* mask_bits;  // NN: packed mask applied to D (same layout), or null
   int n_heads;            // NT: 0, or number of fused fp32 head dot-products (1 = sigma, 3 = rgb)
   const float* head_w;    // NT: [n_heads][BN] fp32
   const float* head_b;    // NT: [n_heads] fp32
@@ -59,38 +60,52 @@ struct GemmArgs {
 template <int BN, int MODE>
 struct GemmCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = (MODE == MODE_TN) ? kOnesBytes : (BN / 64) * 16384;
   static constexpr int kHeadBytes = (MODE == MODE_NT) ? 3 * BN * 4 : 0;    // fused head weights (fp32)
-  static constexpr int kBudget = 225 * 1024 - kStagingBytes - kHeadBytes - 2048 /*bias+barriers*/ - 1024 /*align slack*/;
-  static constexpr int kStagesRaw = kBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kMisc = 2048 /*bias + barriers*/ + 1024 /*alignment slack*/;
+  // NT / NN: the activation operand A streams from HBM (needs ~100 KB in flight per SM to cover
+  // the latency), the weight operand B comes from L2: separate rings, deep for A, shallow for B.
+  static constexpr int kStagingBytes = (MODE == MODE_TN) ? kOnesBytes : (BN / 64) * 16384;
+  static constexpr int kNB = 2;
+  static constexpr int kNARaw = (kMaxSmem - kMisc - kHeadBytes - kStagingBytes - kNB * kBBytes) / kABytes;
+  static constexpr int kNA = kNARaw > 8 ? 8 : kNARaw;
+  // TN: A and B both stream from HBM, one combined ring
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kNSRaw = (kMaxSmem - kMisc - kStagingBytes) / kStageBytes;
+  static constexpr int kNS = kNSRaw > 8 ? 8 : kNSRaw;
+  static constexpr int kRingBytes = (MODE == MODE_TN) ? kNS * kStageBytes : kNA * kABytes + kNB * kBBytes;
   static constexpr int kAccCols = (MODE == MODE_TN) ? (BN + 16) : 2 * BN;
   static constexpr int kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kHeadBytes + 2048 + 1024;
-  static_assert(kStages >= 2, "pipeline too shallow");
+  static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kHeadBytes + kMisc;
+  static_assert(kNA >= 3 && kNS >= 2, "pipeline too shallow");
+  static_assert(kSmemBytes <= kMaxSmem, "shared memory budget exceeded");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128, 192 or 256");
 };
 
-template <int BN, int MODE>
+// HEADS (NT only): number of fp32 head dot-products fused into the epilogue (0, 1 = sigma, 3 = rgb).
+// WMASK (NT only): also emit the packed ReLU mask of the output tile (training forward).
+template <int BN, int MODE, int HEADS, bool WMASK>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmMask, GemmArgs args) {
+            const __grid_constant__ CUtensorMap tmD, GemmArgs args) {
   using Cfg = GemmCfg<BN, MODE>;
-  constexpr int NS = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_stage = smem;
-  uint8_t* s_staging = smem + NS * Cfg::kStageBytes;
+  constexpr int NA = Cfg::kNA, NB = Cfg::kNB, NS = Cfg::kNS;
+  constexpr int NW = BN / 32;                // mask words per row
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // keep the pointer in the shared address space (LDS/STS, not generic LD/ST): offset arithmetic only
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_a = smem;                                   // NT/NN: A ring;  TN: combined ring
+  uint8_t* s_b = smem + NA * kABytes;                    // NT/NN: B ring
+  uint8_t* s_staging = smem + Cfg::kRingBytes;
   float* s_head = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes);           // [3][BN] (NT only)
   float* s_bias = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes + Cfg::kHeadBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
-  uint64_t* full_bar = bars;                 // [NS]
-  uint64_t* empty_bar = bars + NS;           // [NS]
-  uint64_t* tmem_full = bars + 2 * NS;       // [2]
-  uint64_t* tmem_empty = bars + 2 * NS + 2;  // [2]
-  uint64_t* mask_bar = bars + 2 * NS + 4;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
+  uint64_t* full_a = bars;                   // [8]
+  uint64_t* empty_a = bars + 8;              // [8]
+  uint64_t* full_b = bars + 16;              // [2]
+  uint64_t* empty_b = bars + 18;             // [2]
+  uint64_t* tmem_full = bars + 20;           // [2]
+  uint64_t* tmem_empty = bars + 22;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,18 +114,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     if (MODE != MODE_TN) prefetch_tmap(&tmD);
-    if (MODE == MODE_NN) prefetch_tmap(&tmMask);
-    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
-    mbar_init(mask_bar, 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1);
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     const int t = threadIdx.x - 64;
     if (MODE == MODE_NT) {
       for (int i = t; i < BN; i += kEpiThreads) s_bias[i] = args.bias ? args.bias[i] : 0.f;
-      for (int i = t; i < args.n_heads * BN; i += kEpiThreads) s_head[i] = args.head_w[i];
+      for (int i = t; i < HEADS * BN; i += kEpiThreads) s_head[i] = args.head_w[i];
     }
     if (MODE == MODE_TN) {
       uint32_t* ones = reinterpret_cast<uint32_t*>(s_staging);
@@ -128,39 +144,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // NT / NN: persistent over 128-row tiles
     // =====================================================================================
     if (warp == 0) {
+      // ---------------- A producer: activations, HBM -> smem, deep ring ----------------
       if (lane == 0) {
         int s = 0; uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
           for (int kc = 0; kc < args.k_chunks; ++kc) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* a_s = s_stage + s * Cfg::kStageBytes;
-            uint8_t* b_s = a_s + kABytes;
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-            tma_load_2d(a_s, &tmA, &full_bar[s], kc * kBlockK, tile * kBlockM);
+            mbar_wait(&empty_a[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_a[s], kABytes);
+            tma_load_2d(s_a + s * kABytes, &tmA, &full_a[s], kc * kBlockK, tile * kBlockM);
+            if (++s == NA) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 6) {
+      // ---------------- B producer: weights, L2 -> smem, shallow ring ----------------
+      if (lane == 0) {
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
+          for (int kc = 0; kc < args.k_chunks; ++kc) {
+            mbar_wait(&empty_b[s], ph ^ 1);
+            uint8_t* b_s = s_b + s * Cfg::kBBytes;
+            mbar_arrive_expect_tx(&full_b[s], Cfg::kBBytes);
             if (MODE == MODE_NT) {
-              tma_load_2d(b_s, &tmB, &full_bar[s], kc * kBlockK, 0);                 // [BN rows][64 k]
+              tma_load_2d(b_s, &tmB, &full_b[s], kc * kBlockK, 0);                      // [BN rows][64 k]
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)                                        // [64 k rows][64 n] boxes
-                tma_load_2d(b_s + j * 8192, &tmB, &full_bar[s], j * 64, kc * kBlockK);
+                tma_load_2d(b_s + j * 8192, &tmB, &full_b[s], j * 64, kc * kBlockK);
             }
-            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++s == NB) { s = 0; ph ^= 1; }
           }
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
         constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, MODE == MODE_NN ? 1 : 0);
-        int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int acc = 0; uint32_t acc_ph = 0;
         for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
           mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kc = 0; kc < args.k_chunks; ++kc) {
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait(&full_b[sb], phb);
+            mbar_wait(&full_a[sa], pha);
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(s_stage + s * Cfg::kStageBytes);
-            const uint32_t b_addr = a_addr + kABytes;
+            const uint32_t a_addr = smem_u32(s_a + sa * kABytes);
+            const uint32_t b_addr = smem_u32(s_b + sb * Cfg::kBBytes);
             const int krem = args.k_total - kc * kBlockK;
             const int ksteps = krem >= kBlockK ? 4 : (krem + 15) / 16;
             for (int k = 0; k < ksteps; ++k) {
@@ -169,9 +198,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                                       : make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
               umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
             }
-            umma_commit(&empty_bar[s]);
+            umma_commit(&empty_a[sa]);
+            umma_commit(&empty_b[sb]);
             if (kc == args.k_chunks - 1) umma_commit(&tmem_full[acc]);
-            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++sa == NA) { sa = 0; pha ^= 1; }
+            if (++sb == NB) { sb = 0; phb ^= 1; }
           }
           acc ^= 1; if (acc == 0) acc_ph ^= 1;
         }
@@ -181,56 +212,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int q = warp & 3;                       // TMEM lane quarter this warp may access
       const int row = q * 32 + lane;                // row inside the 128-row tile
       const bool issuer = (threadIdx.x == 64);
-      int acc = 0; uint32_t acc_ph = 0, mask_ph = 0;
+      int acc = 0; uint32_t acc_ph = 0;
       for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
-        if (MODE == MODE_NN && args.has_mask) {
-          if (issuer) {
-            mbar_arrive_expect_tx(mask_bar, (BN / 64) * 16384);
+        const int64_t gr = (int64_t)tile * kBlockM + row;
+        const bool row_ok = gr < args.m_rows;
+        uint32_t mbits[NW];
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(s_staging + j * 16384, &tmMask, mask_bar, j * 64, tile * kBlockM);
-          }
-          mbar_wait(mask_bar, mask_ph);
-          mask_ph ^= 1;
+        for (int i = 0; i < NW; ++i) mbits[i] = (MODE == MODE_NN) ? 0xFFFFFFFFu : 0u;
+        if (MODE == MODE_NN && args.mask_bits && row_ok) {
+          // packed ReLU mask of this row (32 B for BN = 256): issued before the accumulator wait
+#pragma unroll
+          for (int i = 0; i < NW; ++i) mbits[i] = __ldg(args.mask_bits + gr * NW + i);   // 32 contiguous bytes
         }
         mbar_wait(&tmem_full[acc], acc_ph);
         tcgen05_fence_after();
         const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
         float hacc0 = 0.f, hacc1 = 0.f, hacc2 = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        const float relu_lo = (MODE == MODE_NT && args.relu) ? 0.f : -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < NW; ++c) {
           uint32_t v[32];
           tmem_ld_x32(t_base + c * 32, v);
           tmem_ld_wait();
           uint8_t* box = s_staging + (c >> 1) * 16384 + row * 128;
+          const uint32_t word = mbits[c];
+          uint32_t outbits = 0u;
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             const int lchunk = (c & 1) * 4 + cc;
             uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[cc * 8 + e]);
+            if (MODE == MODE_NT) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cc * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cc * 8 + 4);
+              x[0] = fmaxf(x[0] + b0.x, relu_lo); x[1] = fmaxf(x[1] + b0.y, relu_lo);
+              x[2] = fmaxf(x[2] + b0.z, relu_lo); x[3] = fmaxf(x[3] + b0.w, relu_lo);
+              x[4] = fmaxf(x[4] + b1.x, relu_lo); x[5] = fmaxf(x[5] + b1.y, relu_lo);
+              x[6] = fmaxf(x[6] + b1.z, relu_lo); x[7] = fmaxf(x[7] + b1.w, relu_lo);
+              if (WMASK) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << (cc * 8 + e)) : 0u;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = ((word >> (cc * 8 + e)) & 1u) ? x[e] : 0.f;
+            }
             uint32_t packed[4];
-            uint4 mk = make_uint4(0, 0, 0, 0);
-            if (MODE == MODE_NN && args.has_mask) mk = *dst;
-            const uint32_t mkw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float x0 = __uint_as_float(v[cc * 8 + 2 * e]);
-              float x1 = __uint_as_float(v[cc * 8 + 2 * e + 1]);
-              if (MODE == MODE_NT) {
-                x0 += s_bias[c * 32 + cc * 8 + 2 * e];
-                x1 += s_bias[c * 32 + cc * 8 + 2 * e + 1];
-                if (args.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              } else if (args.has_mask) {
-                // mask holds post-ReLU activations (>= 0): bf16 bit pattern != 0 (and not -0) <=> > 0
-                if ((mkw[e] & 0x7FFFu) == 0u) x0 = 0.f;
-                if ((mkw[e] & 0x7FFF0000u) == 0u) x1 = 0.f;
-              }
-              __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
+              __nv_bfloat162 p = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
               packed[e] = *reinterpret_cast<uint32_t*>(&p);
-              if (MODE == MODE_NT && args.n_heads > 0) {
-                // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation that is stored
+            }
+            if (MODE == MODE_NT && HEADS > 0) {
+              // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation that is stored
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
                 const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xFFFF0000u);
                 const int j = c * 32 + cc * 8 + 2 * e;
                 hacc0 = fmaf(r0, s_head[j], hacc0); hacc0 = fmaf(r1, s_head[j + 1], hacc0);
-                if (args.n_heads == 3) {
+                if (HEADS == 3) {
                   hacc1 = fmaf(r0, s_head[BN + j], hacc1); hacc1 = fmaf(r1, s_head[BN + j + 1], hacc1);
                   hacc2 = fmaf(r0, s_head[2 * BN + j], hacc2); hacc2 = fmaf(r1, s_head[2 * BN + j + 1], hacc2);
                 }
@@ -238,13 +280,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           }
+          if (MODE == MODE_NT && WMASK) mbits[c] = outbits;
         }
-        if (MODE == MODE_NT && args.n_heads > 0) {
-          const int64_t gr = (int64_t)tile * kBlockM + row;
-          if (gr < args.m_rows) {
+        if (MODE == MODE_NT && row_ok) {
+          if (WMASK) {
+            uint4* mo = reinterpret_cast<uint4*>(args.mask_out + gr * NW);
+            if (NW == 8) { mo[0] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]); mo[1] = make_uint4(mbits[4 % NW], mbits[5 % NW], mbits[6 % NW], mbits[7 % NW]); }
+            else {
+#pragma unroll
+              for (int i = 0; i < NW; ++i) args.mask_out[gr * NW + i] = mbits[i];
+            }
+          }
+          if (HEADS > 0) {
             float* o = args.head_out + gr * 4 + args.head_col;
             o[0] = hacc0 + args.head_b[0];
-            if (args.n_heads == 3) { o[1] = hacc1 + args.head_b[1]; o[2] = hacc2 + args.head_b[2]; }
+            if (HEADS == 3) { o[1] = hacc1 + args.head_b[1]; o[2] = hacc2 + args.head_b[2]; }
           }
         }
         // accumulator drained -> hand it back to the MMA warp
@@ -277,14 +327,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (lane == 0) {
         int s = 0; uint32_t ph = 0;
         for (int kc = c0; kc < c1; ++kc) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* a_s = s_stage + s * Cfg::kStageBytes;
+          mbar_wait(&empty_a[s], ph ^ 1);
+          uint8_t* a_s = s_a + s * Cfg::kStageBytes;
           uint8_t* b_s = a_s + kABytes;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_2d(a_s, &tmA, &full_bar[s], m_tile * kBlockM, kc * kBlockK);          // [64 pts][64 out]
-          tma_load_2d(a_s + 8192, &tmA, &full_bar[s], m_tile * kBlockM + 64, kc * kBlockK);
+          mbar_arrive_expect_tx(&full_a[s], Cfg::kStageBytes);
+          tma_load_2d(a_s, &tmA, &full_a[s], m_tile * kBlockM, kc * kBlockK);          // [64 pts][64 out]
+          tma_load_2d(a_s + 8192, &tmA, &full_a[s], m_tile * kBlockM + 64, kc * kBlockK);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_s + j * 8192, &tmB, &full_bar[s], j * 64, kc * kBlockK);
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_s + j * 8192, &tmB, &full_a[s], j * 64, kc * kBlockK);
           if (++s == NS) { s = 0; ph ^= 1; }
         }
       }
@@ -295,9 +345,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t ones_addr = smem_u32(s_staging);
         int s = 0; uint32_t ph = 0;
         for (int kc = c0; kc < c1; ++kc) {
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait(&full_a[s], ph);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(s_stage + s * Cfg::kStageBytes);
+          const uint32_t a_addr = smem_u32(s_a + s * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -308,12 +358,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
             umma_bf16(tmem_base + BN, adesc, odesc, idesc1, accum);      // column sums of A (bias gradient)
           }
-          umma_commit(&empty_bar[s]);
+          umma_commit(&empty_a[s]);
           if (++s == NS) { s = 0; ph ^= 1; }
         }
         umma_commit(&tmem_full[0]);
       }
-    } else {
+    } else if (warp < 6) {
       const int q = warp & 3;
       const int row = q * 32 + lane;
       float* out = args.partial + (size_t)blockIdx.x * (kBlockM * (BN + 1));
@@ -438,18 +488,19 @@ static void prof_end(int slot, cudaStream_t st) {
   if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
 }
 
-template <int BN, int MODE>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tM,
-                       const GemmArgs& args, int grid, cudaStream_t st) {
+template <int BN, int MODE, int HEADS = 0, bool WMASK = false>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const GemmArgs& args, int grid,
+                       cudaStream_t st) {
   using Cfg = GemmCfg<BN, MODE>;
   static bool configured = false;
   if (!configured) {
-    RN_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RN_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, MODE, HEADS, WMASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
     configured = true;
   }
   int slot;
   prof_begin(MODE, st, &slot);
-  gemm_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tA, tB, tD, tM, args);
+  gemm_kernel<BN, MODE, HEADS, WMASK><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tA, tB, tD, args);
   prof_end(slot, st);
   RN_LAUNCH_CHECK();
   return RN_OK;
@@ -468,8 +519,8 @@ int check_arch() {
 
 // D[M,N] = act(A[M,K] B[N,K]^T + bias)        (forward layer)
 int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
-            const float* bias, int relu, cudaStream_t st, int n_heads, const float* head_w, const float* head_b,
-            float* head_out, int head_col) {
+            const float* bias, int relu, cudaStream_t st, uint32_t* mask_out, int n_heads, const float* head_w,
+            const float* head_b, float* head_out, int head_col) {
   int rc = check_arch();
   if (rc != RN_OK) return rc;
   RN_REQUIRE(M > 0 && K > 0 && K % 8 == 0 && (N == 256 || N == 128 || N == 64));
@@ -480,32 +531,44 @@ int gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int
   GemmArgs a{};
   a.m_tiles = (int)ceil_div(M, kBlockM); a.k_chunks = (int)ceil_div(K, kBlockK); a.k_total = K; a.bias = bias; a.relu = relu;
   RN_REQUIRE(n_heads == 0 || ((n_heads == 1 || n_heads == 3) && head_w && head_b && head_out));
+  a.mask_out = mask_out;
   a.m_rows = M; a.n_heads = n_heads; a.head_w = head_w; a.head_b = head_b; a.head_out = head_out; a.head_col = head_col;
   const int grid = a.m_tiles < num_sms() ? a.m_tiles : num_sms();
   g_prof_next_flops = 2.0 * (double)M * N * K;
-  if (N == 256) return launch_gemm<256, MODE_NT>(tA, tB, tD, tD, a, grid, st);
-  if (N == 128) return launch_gemm<128, MODE_NT>(tA, tB, tD, tD, a, grid, st);
-  return launch_gemm<64, MODE_NT>(tA, tB, tD, tD, a, grid, st);
+  if (N == 256) {
+    RN_REQUIRE(n_heads <= 1);
+    if (n_heads == 1) return mask_out ? launch_gemm<256, MODE_NT, 1, true>(tA, tB, tD, a, grid, st)
+                                      : launch_gemm<256, MODE_NT, 1, false>(tA, tB, tD, a, grid, st);
+    return mask_out ? launch_gemm<256, MODE_NT, 0, true>(tA, tB, tD, a, grid, st)
+                    : launch_gemm<256, MODE_NT, 0, false>(tA, tB, tD, a, grid, st);
+  }
+  RN_REQUIRE(mask_out == nullptr);
+  if (N == 128) {
+    RN_REQUIRE(n_heads == 0 || n_heads == 3);
+    return n_heads == 3 ? launch_gemm<128, MODE_NT, 3, false>(tA, tB, tD, a, grid, st)
+                        : launch_gemm<128, MODE_NT, 0, false>(tA, tB, tD, a, grid, st);
+  }
+  RN_REQUIRE(n_heads == 0);
+  return launch_gemm<64, MODE_NT>(tA, tB, tD, a, grid, st);
 }
 
-// D[M,N] = (A[M,K] B[K,N]) .* (mask[M,N] > 0)   (data gradient; mask may be null)
+// D[M,N] = (A[M,K] B[K,N]) .* mask   (data gradient; mask_bits = packed ReLU mask [M][N/32] or null)
 int gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N, int K,
-            const void* mask, int64_t ldmask, cudaStream_t st) {
+            const uint32_t* mask_bits, cudaStream_t st) {
   int rc = check_arch();
   if (rc != RN_OK) return rc;
   RN_REQUIRE(M > 0 && K > 0 && K % 8 == 0 && (N == 256 || N == 64));
-  CUtensorMap tA, tB, tD, tM;
+  CUtensorMap tA, tB, tD;
   if ((rc = make_tmap(&tA, A, K, M, lda, kBlockM)) != RN_OK) return rc;
   if ((rc = make_tmap(&tB, B, N, K, ldb, 64)) != RN_OK) return rc;
   if ((rc = make_tmap(&tD, D, N, M, ldd, kBlockM)) != RN_OK) return rc;
-  tM = tD;
-  if (mask && (rc = make_tmap(&tM, mask, N, M, ldmask, kBlockM)) != RN_OK) return rc;
   GemmArgs a{};
-  a.m_tiles = (int)ceil_div(M, kBlockM); a.k_chunks = (int)ceil_div(K, kBlockK); a.k_total = K; a.has_mask = mask != nullptr;
+  a.m_tiles = (int)ceil_div(M, kBlockM); a.k_chunks = (int)ceil_div(K, kBlockK); a.k_total = K;
+  a.m_rows = M; a.mask_bits = mask_bits;
   const int grid = a.m_tiles < num_sms() ? a.m_tiles : num_sms();
   g_prof_next_flops = 2.0 * (double)M * N * K;
-  if (N == 256) return launch_gemm<256, MODE_NN>(tA, tB, tD, tM, a, grid, st);
-  return launch_gemm<64, MODE_NN>(tA, tB, tD, tM, a, grid, st);
+  if (N == 256) return launch_gemm<256, MODE_NN>(tA, tB, tD, a, grid, st);
+  return launch_gemm<64, MODE_NN>(tA, tB, tD, a, grid, st);
 }
 
 size_t gemm_tn_scratch_bytes() { return (size_t)(num_sms() + 8) * kBlockM * 257 * sizeof(float); }
@@ -534,8 +597,8 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
   RN_REQUIRE((size_t)a.splits * a.m_tiles * kBlockM * (N + 1) * sizeof(float) <= scratch_bytes);
   const int grid = a.m_tiles * a.splits;
   g_prof_next_flops = 2.0 * (double)K * N * Mo;
-  if (N == 256) rc = launch_gemm<256, MODE_TN>(tA, tB, tA, tA, a, grid, st);
-  else rc = launch_gemm<64, MODE_TN>(tA, tB, tA, tA, a, grid, st);
+  if (N == 256) rc = launch_gemm<256, MODE_TN>(tA, tB, tA, a, grid, st);
+  else rc = launch_gemm<64, MODE_TN>(tA, tB, tA, a, grid, st);
   info->m_tiles = a.m_tiles; info->splits = a.splits; info->N = N; info->scratch = scratch;
   return rc;
 }
@@ -581,12 +644,13 @@ int rn_prof_collect(double* ms3_host, double* flops3_host, int* launches3_host) 
 }
 
 int rn_gemm_bf16(int mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M, int N,
-                 int64_t K, const float* bias, int relu, const void* mask, int64_t ldmask, float* colsum_out, void* scratch,
-                 size_t scratch_bytes, rn_stream_t stream) {
+                 int64_t K, const float* bias, int relu, const uint32_t* mask_bits, uint32_t* mask_out, float* colsum_out,
+                 void* scratch, size_t scratch_bytes, rn_stream_t stream) {
   RN_REQUIRE(A && B && D);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == MODE_NT) return gemm_nt(A, lda, B, ldb, D, ldd, M, N, (int)K, bias, relu, st, 0, nullptr, nullptr, nullptr, 0);
-  if (mode == MODE_NN) return gemm_nn(A, lda, B, ldb, D, ldd, M, N, (int)K, mask, ldmask, st);
+  if (mode == MODE_NT)
+    return gemm_nt(A, lda, B, ldb, D, ldd, M, N, (int)K, bias, relu, st, mask_out, 0, nullptr, nullptr, nullptr, 0);
+  if (mode == MODE_NN) return gemm_nn(A, lda, B, ldb, D, ldd, M, N, (int)K, mask_bits, st);
   if (mode == MODE_TN) {
     TnInfo info;
     int rc = gemm_tn_launch(A, lda, (int)M, B, ldb, N, K, (float*)scratch, scratch_bytes, &info, st);

@@ -25,6 +25,7 @@ typedef __nv_bfloat16 bf16;
 
 struct TrainWs {
   bf16 *XC, *H[8], *FD, *HC, *dHC, *dFS, *dA, *dB, *dXE0, *dXE5, *dDE;
+  uint32_t* MB[8];          // packed ReLU masks of H0..H7, [M][8] words each (written by the forward epilogues)
   float* scratch;
   size_t scratch_bytes;
   float* heads_scratch;
@@ -47,6 +48,7 @@ static void carve_train(void* ws, int64_t M, TrainWs* w) {
   w->H[4] = w->XC + 64;                           // H4 lives in XC[:, 64:320] (ld 320)
   w->H[5] = take(256); w->H[6] = take(256); w->H[7] = take(256);
   w->FD = take(320); w->HC = take(128);
+  for (int i = 0; i < 8; ++i) w->MB[i] = reinterpret_cast<uint32_t*>(take(16));
   w->dHC = take(128); w->dFS = take(272); w->dA = take(256); w->dB = take(256);
   w->dXE0 = take(64); w->dXE5 = take(64); w->dDE = take(64);
   uint8_t* q = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(p), 256));
@@ -68,11 +70,12 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
   const bf16* W = reinterpret_cast<const bf16*>(packed);
   const float* F = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kBf16Bytes);
   bf16 *XC, *H[8], *FD, *HC;
+  uint32_t* MB[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (training) {
     TrainWs w;
     carve_train(ws, M, &w);
     XC = w.XC; FD = w.FD; HC = w.HC;
-    for (int i = 0; i < 8; ++i) H[i] = w.H[i];
+    for (int i = 0; i < 8; ++i) { H[i] = w.H[i]; MB[i] = w.MB[i]; }
   } else {
     bf16* p = reinterpret_cast<bf16*>(align_up(reinterpret_cast<uintptr_t>(ws), 256));
     XC = p; p += (size_t)M * 320;
@@ -83,19 +86,20 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
     H[0] = HA; H[1] = HB; H[2] = HA; H[3] = HB; H[4] = XC + 64; H[5] = HA; H[6] = HB; H[7] = HA;
   }
   RN_TRY(launch_encode(pts, dirs, M, group, XC, 320, FD, 320, st));
-  RN_TRY(gemm_nt(XC, 320, W + kW0, 64, H[0], 256, M, 256, 64, F + kB0, 1, st));
+  RN_TRY(gemm_nt(XC, 320, W + kW0, 64, H[0], 256, M, 256, 64, F + kB0, 1, st, MB[0]));
   for (int l = 1; l < 8; ++l) {
     const bf16* in = (l == 5) ? XC : H[l - 1];
     const int K = (l == 5) ? 320 : 256;
     const int ldin = (l == 5) ? 320 : ld_of(l - 1);
     if (l == 7)   // sigma head fused into the epilogue: raw[:, 3] = H7 . w_sigma + b_sigma
-      RN_TRY(gemm_nt(in, ldin, W + trunk_w(l), K, H[l], ld_of(l), M, 256, K, F + kB0 + 256 * l, 1, st, 1, F + kWSig, F + kBSig, raw, 3));
+      RN_TRY(gemm_nt(in, ldin, W + trunk_w(l), K, H[l], ld_of(l), M, 256, K, F + kB0 + 256 * l, 1, st, MB[l], 1, F + kWSig,
+                     F + kBSig, raw, 3));
     else
-      RN_TRY(gemm_nt(in, ldin, W + trunk_w(l), K, H[l], ld_of(l), M, 256, K, F + kB0 + 256 * l, 1, st));
+      RN_TRY(gemm_nt(in, ldin, W + trunk_w(l), K, H[l], ld_of(l), M, 256, K, F + kB0 + 256 * l, 1, st, MB[l]));
   }
   RN_TRY(gemm_nt(H[7], 256, W + kWFS, 256, FD, 320, M, 256, 256, F + kBF, 0, st));
   // rgb head fused into the view-branch epilogue: raw[:, 0:3] = HC . W_rgb^T + b_rgb
-  RN_TRY(gemm_nt(FD, 320, W + kWD, 320, HC, 128, M, 128, 320, F + kBD, 1, st, 3, F + kWRgb, F + kBRgb, raw, 0));
+  RN_TRY(gemm_nt(FD, 320, W + kWD, 320, HC, 128, M, 128, 320, F + kBD, 1, st, nullptr, 3, F + kWRgb, F + kBRgb, raw, 0));
   return RN_OK;
 }
 
@@ -115,14 +119,14 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD + 256, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
   RN_TRY(gemm_tn_reduce(ti, 0, 128, 27, G + kG_WD + 256, 283, nullptr, st));
   // d feat = dHC x WD[:, 0:256]  -> dFS[:, 0:256]   (feature_linear has no activation: no mask)
-  RN_TRY(gemm_nn(w.dHC, 128, W + kWD, 320, w.dFS, 272, M, 256, 128, nullptr, 0, st));
-  if (g_dirs) RN_TRY(gemm_nn(w.dHC, 128, W + kWD + 256, 320, w.dDE, 64, M, 64, 128, nullptr, 0, st));
+  RN_TRY(gemm_nn(w.dHC, 128, W + kWD, 320, w.dFS, 272, M, 256, 128, nullptr, st));
+  if (g_dirs) RN_TRY(gemm_nn(w.dHC, 128, W + kWD + 256, 320, w.dDE, 64, M, 64, 128, nullptr, st));
   // feature_linear + sigma_linear (row 256 of dFS^T): weights, biases
   RN_TRY(gemm_tn_launch(w.dFS, 272, 272, w.H[7], 256, 256, M, w.scratch, w.scratch_bytes, &ti, st));
   RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + kG_WF, 256, G + kG_BF, st));
   RN_TRY(gemm_tn_reduce(ti, 256, 1, 256, G + kG_WSig, 256, G + kG_BSig, st));
   // dH7 = [dF | dsigma] x WFS, masked by H7 > 0
-  RN_TRY(gemm_nn(w.dFS, 272, W + kWFS, 256, w.dA, 256, M, 256, 272, w.H[7], 256, st));
+  RN_TRY(gemm_nn(w.dFS, 272, W + kWFS, 256, w.dA, 256, M, 256, 272, w.MB[7], st));
   bf16* dY = w.dA;
   bf16* dN = w.dB;
   for (int l = 7; l >= 1; --l) {
@@ -132,14 +136,14 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
       RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5), st));
       RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
       RN_TRY(gemm_tn_reduce(ti, 0, 256, 63, G + trunk_gw(5), 319, nullptr, st));
-      RN_TRY(gemm_nn(dY, 256, W + kW5 + 64, 320, dN, 256, M, 256, 256, w.XC + 64, 320, st));
-      if (need_in) RN_TRY(gemm_nn(dY, 256, W + kW5, 320, w.dXE5, 64, M, 64, 256, nullptr, 0, st));
+      RN_TRY(gemm_nn(dY, 256, W + kW5 + 64, 320, dN, 256, M, 256, 256, w.MB[4], st));
+      if (need_in) RN_TRY(gemm_nn(dY, 256, W + kW5, 320, w.dXE5, 64, M, 64, 256, nullptr, st));
     } else {
       const bf16* in = w.H[l - 1];
       const int ldin = ld_of(l - 1);
       RN_TRY(gemm_tn_launch(dY, 256, 256, in, ldin, 256, M, w.scratch, w.scratch_bytes, &ti, st));
       RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + trunk_gw(l), 256, G + trunk_gb(l), st));
-      RN_TRY(gemm_nn(dY, 256, W + trunk_w(l), 256, dN, 256, M, 256, 256, in, ldin, st));
+      RN_TRY(gemm_nn(dY, 256, W + trunk_w(l), 256, dN, 256, M, 256, 256, w.MB[l - 1], st));
     }
     bf16* t = dY; dY = dN; dN = t;
   }
@@ -147,7 +151,7 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
   RN_TRY(gemm_tn_reduce(ti, 0, 256, 63, G + trunk_gw(0), 63, G + trunk_gb(0), st));
   if (need_in) {
-    RN_TRY(gemm_nn(dY, 256, W + kW0, 64, w.dXE0, 64, M, 64, 256, nullptr, 0, st));
+    RN_TRY(gemm_nn(dY, 256, W + kW0, 64, w.dXE0, 64, M, 64, 256, nullptr, st));
     if (!g_pts) { /* dirs only */ }
     RN_TRY(launch_encode_bwd(pts, dirs, M, group, w.dXE0, w.dXE5, w.dDE, g_pts, g_dirs, st));
   }

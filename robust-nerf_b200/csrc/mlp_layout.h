@@ -65,9 +65,9 @@ constexpr size_t kG_Total = kG_BRgb + 3;
 static_assert(kG_Total == 595844, "parameter count must match the reference (summary.json:46)");
 
 // ---- activation workspace (bf16 elements per point) ----
-// training: XC[320] H0 H1 H2 H3 H5 H6 H7 (7 x 256) FD[320] HC[128] | backward: dHC[128] dFS[272] dA[256] dB[256]
+// training: XC[320] H0 H1 H2 H3 H5 H6 H7 (7 x 256) FD[320] HC[128] MB0..MB7 (packed masks) | backward: dHC[128] dFS[272] dA[256] dB[256]
 //           dXE0[64] dXE5[64] dDE[64]
-constexpr int kTrainFwdElems = 320 + 7 * 256 + 320 + 128;           // 2560
+constexpr int kTrainFwdElems = 320 + 7 * 256 + 320 + 128 + 8 * 16;  // 2688 (last term: 8 packed ReLU masks, 32 B/point each)
 constexpr int kTrainBwdElems = 128 + 272 + 256 + 256 + 64 + 64 + 64; // 1104
 constexpr int kInferElems = 320 + 256 + 256 + 320 + 128;            // 1280
 

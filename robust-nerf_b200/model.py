@@ -81,7 +81,7 @@ class NeRF(nn.Module):
 
     def forward_raw(self, x: torch.Tensor, d: torch.Tensor, group: int = 1) -> torch.Tensor:
         """(rgb pre-sigmoid, sigma pre-ReLU) [M,4]; d has one row per `group` consecutive points."""
-        return ops.NeRFMLP.apply(x, d, group, self._packed, *self.kernel_params())
+        return ops.NeRFMLP.apply(x, d, group, self._packed, torch.is_grad_enabled(), *self.kernel_params())
 
     def forward(self, x: torch.Tensor, d: torch.Tensor | None = None) -> Tuple[torch.Tensor, torch.Tensor]:
         if d is None:

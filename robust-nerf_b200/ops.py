@@ -282,6 +282,10 @@ class PackedWeights:
     def __init__(self):
         self.buf: Optional[torch.Tensor] = None
         self.key = None
+        # Optional flat fp32 gradient sink (RN_NUM_PARAMS floats).  When set (Trainer), the backward
+        # kernels write this network's parameter gradients straight into it (overwrite, one MLP call per
+        # net and step) and autograd receives None for the parameters -- no 48 accumulate launches.
+        self.grad_sink: Optional[torch.Tensor] = None
 
     def get(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
         key = tuple((p.data_ptr(), p._version) for p in params)
@@ -316,7 +320,7 @@ class NeRFMLP(torch.autograd.Function):
     """raw[M,4] = (rgb pre-sigmoid, sigma pre-ReLU).  dirs has one row per `group` consecutive points."""
 
     @staticmethod
-    def forward(ctx, pts, dirs, group, cache: PackedWeights, *params):
+    def forward(ctx, pts, dirs, group, cache: PackedWeights, grad_mode: bool, *params):
         pts, dirs = _f32(pts, "x"), _f32(dirs, "d")
         for i, p in enumerate(params):
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
@@ -325,7 +329,9 @@ class NeRFMLP(torch.autograd.Function):
         if M % group != 0 or dirs.shape[0] * group != M:
             raise ValueError("dirs must have M/group rows")
         packed = cache.get(params)
-        training = any(ctx.needs_input_grad)
+        # grad_mode = torch.is_grad_enabled() sampled by the caller: inside Function.forward it is always
+        # False, and ctx.needs_input_grad ignores no_grad()
+        training = bool(grad_mode) and any(ctx.needs_input_grad)
         raw = _empty((M, 4), pts)
         if M == 0:
             ctx.meta = None
@@ -334,27 +340,30 @@ class NeRFMLP(torch.autograd.Function):
         call("rn_mlp_fwd", ptr(packed), ptr(pts), ptr(dirs), M, int(group), ptr(ws), int(training), ptr(raw), stream_ptr())
         if training:
             ctx.save_for_backward(pts, dirs)
-            ctx.ws, ctx.packed = ws, packed
+            ctx.ws, ctx.packed, ctx.cache = ws, packed, cache
         ctx.meta = (M, int(group), training)
         return raw
 
     @staticmethod
     def backward(ctx, g_raw):
-        n_in = 4
+        n_in = 5
         if ctx.meta is None:
             return (None,) * (n_in + L.NUM_PARAM_TENSORS)
         M, group, training = ctx.meta
         pts, dirs = ctx.saved_tensors
         g_raw = _f32(g_raw, "g_raw")
-        flat = _empty((L.NUM_PARAMS,), pts)
+        sink = ctx.cache.grad_sink
+        flat = sink if sink is not None else _empty((L.NUM_PARAMS,), pts)
         g_pts = _empty((M, 3), pts) if ctx.needs_input_grad[0] else None
         g_dirs = _empty((M // group, 3), pts) if ctx.needs_input_grad[1] else None
         call("rn_mlp_bwd", ptr(ctx.packed), ptr(pts), ptr(dirs), M, group, ptr(ctx.ws), ptr(g_raw), ptr(flat), ptr(g_pts),
              ptr(g_dirs), stream_ptr())
         ctx.ws = None
+        if sink is not None:
+            return (g_pts, g_dirs, None, None, None) + (None,) * L.NUM_PARAM_TENSORS
         grads = split_flat_grads(flat)
         grads = [g if ctx.needs_input_grad[n_in + i] else None for i, g in enumerate(grads)]
-        return (g_pts, g_dirs, None, None, *grads)
+        return (g_pts, g_dirs, None, None, None, *grads)
 
 
 class HeadAct(torch.autograd.Function):
@@ -408,10 +417,19 @@ class PosEnc(torch.autograd.Function):
 _gemm_scratch = {}
 
 
-def gemm_bf16(mode, A, B, bias=None, relu=False, mask=None, out=None):
-    """mode 0: A[M,K] @ B[N,K]^T (+bias, relu) -> bf16 [M,N]; mode 1: (A[M,K] @ B[K,N]) * (mask>0) -> bf16;
-    mode 2: A[K,Mo]^T @ B[K,N] -> (fp32 [Mo,N], colsum fp32 [Mo])."""
-    for name, t in (("A", A), ("B", B), ("mask", mask), ("out", out)):
+def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+    """bool/real [M,N] (N % 32 == 0) -> packed uint32-as-int32 [M, N/32], bit j of word c <=> mask[m, 32c+j] > 0
+    (test helper; the kernels produce / consume this layout)."""
+    M, N = mask.shape
+    b = (mask > 0).reshape(M, N // 32, 32).to(torch.int64)
+    w = (b << torch.arange(32, device=mask.device, dtype=torch.int64)).sum(-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
+
+
+def gemm_bf16(mode, A, B, bias=None, relu=False, mask_bits=None, out=None, want_mask=False):
+    """mode 0: A[M,K] @ B[N,K]^T (+bias, relu) -> bf16 [M,N] (and, with want_mask, the packed ReLU mask of the output);
+    mode 1: (A[M,K] @ B[K,N]) with packed mask_bits applied -> bf16; mode 2: A[K,Mo]^T @ B[K,N] -> (fp32 [Mo,N], colsum [Mo])."""
+    for name, t in (("A", A), ("B", B), ("out", out)):
         if t is not None and (not t.is_cuda or t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1):
             raise RuntimeError(f"{name} must be a 2-D bf16 CUDA tensor with unit inner stride")
     dev = A.device
@@ -422,20 +440,23 @@ def gemm_bf16(mode, A, B, bias=None, relu=False, mask=None, out=None):
         M, K = A.shape
         N = B.shape[0]
         D = torch.empty((M, N), device=dev, dtype=torch.bfloat16) if out is None else out
+        mo = torch.empty((M, N // 32), device=dev, dtype=torch.int32) if want_mask else None
         call("rn_gemm_bf16", 0, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(D), D.stride(0), M, N, K, ptr(bias), int(relu),
-             None, 0, None, ptr(sc), sc.numel(), stream_ptr())
-        return D
+             None, ptr(mo), None, ptr(sc), sc.numel(), stream_ptr())
+        return (D, mo) if want_mask else D
     if mode == 1:
         M, K = A.shape
         N = B.shape[1]
         D = torch.empty((M, N), device=dev, dtype=torch.bfloat16) if out is None else out
-        call("rn_gemm_bf16", 1, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(D), D.stride(0), M, N, K, None, 0, ptr(mask),
-             0 if mask is None else mask.stride(0), None, ptr(sc), sc.numel(), stream_ptr())
+        if mask_bits is not None:
+            mask_bits = require_cuda(mask_bits, "mask_bits", torch.int32)
+        call("rn_gemm_bf16", 1, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(D), D.stride(0), M, N, K, None, 0,
+             ptr(mask_bits), None, None, ptr(sc), sc.numel(), stream_ptr())
         return D
     K, Mo = A.shape
     N = B.shape[1]
     D = torch.empty((Mo, N), device=dev, dtype=torch.float32)
     colsum = torch.empty((Mo,), device=dev, dtype=torch.float32)
-    call("rn_gemm_bf16", 2, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(D), D.stride(0), Mo, N, K, None, 0, None, 0,
+    call("rn_gemm_bf16", 2, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(D), D.stride(0), Mo, N, K, None, 0, None, None,
          ptr(colsum), ptr(sc), sc.numel(), stream_ptr())
     return D, colsum

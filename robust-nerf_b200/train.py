@@ -202,9 +202,11 @@ class Trainer:
         self.exp_avg_sq = torch.zeros(total, device=dev)
         off = 0
         self.net_offsets = [0]
-        for ps in self.net_params:
+        for m, ps in zip(nets, self.net_params):
+            start = off
             off = _flatten_into(ps, self.flat, self.gflat, off)
             self.net_offsets.append(off)
+            m._packed.grad_sink = self.gflat[start:off]      # backward kernels write gradients here directly
         off = _flatten_into(self.pose_params, self.flat, self.gflat, off)
         self.norms = torch.zeros(2 * (8 + 8 * 64), device=dev)    # two rn_clip_adam_step scratch areas
         self.iteration = 0
@@ -213,7 +215,8 @@ class Trainer:
 
     # -- pieces --------------------------------------------------------------------------------
     def _zero_grad(self):
-        self.gflat.zero_()
+        if self.n_pose:
+            self.gflat[self.n_net:].zero_()                  # net gradients are overwritten by the kernels
         off = 0
         for p in [q for ps in self.net_params for q in ps] + self.pose_params:
             n = p.numel()

@@ -77,13 +77,18 @@ def test_gemm_nt(rn, dev, M, N, K):
     B = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).bfloat16()
     bias = torch.randn(N, generator=g).to(dev)
     for relu in (False, True):
-        D = ops.gemm_bf16(0, A, B, bias=bias, relu=relu)
+        want_mask = N == 256                                        # the packed-mask epilogue exists for 256-wide layers
+        D = ops.gemm_bf16(0, A, B, bias=bias, relu=relu, want_mask=want_mask)
+        if want_mask:
+            D, mbits = D
         ref = A.float() @ B.float().T + bias
         if relu:
             ref = ref.relu()
         torch.cuda.synchronize()
         err = (D.float() - ref).abs().max().item()
         assert err < 0.03 * max(1.0, ref.abs().max().item() / 4), (relu, err)
+        if want_mask:
+            assert torch.equal(mbits, ops.pack_mask_bits(D.float()))    # packed mask of the stored output, bit-exact
 
 
 def test_gemm_nt_strided_views(rn, dev):
@@ -109,7 +114,7 @@ def test_gemm_nn_with_mask(rn, dev, M, N, K):
     mask = torch.randn(M, N, generator=g).relu().to(dev).bfloat16()
     ref = A.float() @ B.float()
     D0 = ops.gemm_bf16(1, A, B)
-    D1 = ops.gemm_bf16(1, A, B, mask=mask)
+    D1 = ops.gemm_bf16(1, A, B, mask_bits=ops.pack_mask_bits(mask.float()))
     torch.cuda.synchronize()
     assert (D0.float() - ref).abs().max().item() < 0.05
     assert (D1.float() - ref * (mask.float() > 0)).abs().max().item() < 0.05
