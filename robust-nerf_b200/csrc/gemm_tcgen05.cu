@@ -64,7 +64,11 @@ struct GemmCfg {
   static constexpr int kMisc = 2048 /*bias + barriers*/ + 1024 /*alignment slack*/;
   // NT / NN: the activation operand A streams from HBM (needs ~100 KB in flight per SM to cover
   // the latency), the weight operand B comes from L2: separate rings, deep for A, shallow for B.
-  static constexpr int kStagingBytes = (MODE == MODE_TN) ? kOnesBytes : (BN / 64) * 16384;
+  // output staging: two buffers of up to 128 columns each, so the TMA store of one half drains while the
+  // epilogue converts the next half (or the next tile)
+  static constexpr int kHalfCols = BN >= 128 ? 128 : BN;
+  static constexpr int kHalfBytes = (kHalfCols / 64) * 16384;
+  static constexpr int kStagingBytes = (MODE == MODE_TN) ? kOnesBytes : 2 * kHalfBytes;
   static constexpr int kNB = 2;
   static constexpr int kNARaw = (kMaxSmem - kMisc - kHeadBytes - kStagingBytes - kNB * kBBytes) / kABytes;
   static constexpr int kNA = kNARaw > 8 ? 8 : kNARaw;
@@ -213,6 +217,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row = q * 32 + lane;                // row inside the 128-row tile
       const bool issuer = (threadIdx.x == 64);
       int acc = 0; uint32_t acc_ph = 0;
+      int sbuf = 0;                                  // staging half buffer written next
       for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
         const int64_t gr = (int64_t)tile * kBlockM + row;
         const bool row_ok = gr < args.m_rows;
@@ -229,59 +234,86 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
         float hacc0 = 0.f, hacc1 = 0.f, hacc2 = 0.f;
         const float relu_lo = (MODE == MODE_NT && args.relu) ? 0.f : -3.0e38f;
+        constexpr int kHalves = BN / Cfg::kHalfCols;          // 2 for BN = 256, else 1
+        constexpr int kGroupsPerHalf = Cfg::kHalfCols / 32;
 #pragma unroll
-        for (int c = 0; c < NW; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(t_base + c * 32, v);
-          tmem_ld_wait();
-          uint8_t* box = s_staging + (c >> 1) * 16384 + row * 128;
-          const uint32_t word = mbits[c];
-          uint32_t outbits = 0u;
+        for (int h = 0; h < kHalves; ++h) {
+          uint8_t* s_half = s_staging + sbuf * Cfg::kHalfBytes;
+          // the previous store out of this buffer (two commits ago) must have finished READING it
+          if (issuer) tma_store_wait_read1();
+          named_bar_sync(1, kEpiThreads);
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int lchunk = (c & 1) * 4 + cc;
-            uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
-            float x[8];
+          for (int cg = 0; cg < kGroupsPerHalf; ++cg) {
+            const int c = h * kGroupsPerHalf + cg;
+            uint32_t v[32];
+            tmem_ld_x32(t_base + c * 32, v);
+            tmem_ld_wait();
+            uint8_t* box = s_half + (cg >> 1) * 16384 + row * 128;
+            const uint32_t word = mbits[c];
+            uint32_t outbits = 0u;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[cc * 8 + e]);
-            if (MODE == MODE_NT) {
-              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cc * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cc * 8 + 4);
-              x[0] = fmaxf(x[0] + b0.x, relu_lo); x[1] = fmaxf(x[1] + b0.y, relu_lo);
-              x[2] = fmaxf(x[2] + b0.z, relu_lo); x[3] = fmaxf(x[3] + b0.w, relu_lo);
-              x[4] = fmaxf(x[4] + b1.x, relu_lo); x[5] = fmaxf(x[5] + b1.y, relu_lo);
-              x[6] = fmaxf(x[6] + b1.z, relu_lo); x[7] = fmaxf(x[7] + b1.w, relu_lo);
-              if (WMASK) {
+            for (int cc = 0; cc < 4; ++cc) {
+              const int lchunk = (cg & 1) * 4 + cc;
+              uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
+              float x[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << (cc * 8 + e)) : 0u;
+              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[cc * 8 + e]);
+              if (MODE == MODE_NT) {
+                const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cc * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cc * 8 + 4);
+                x[0] = fmaxf(x[0] + b0.x, relu_lo); x[1] = fmaxf(x[1] + b0.y, relu_lo);
+                x[2] = fmaxf(x[2] + b0.z, relu_lo); x[3] = fmaxf(x[3] + b0.w, relu_lo);
+                x[4] = fmaxf(x[4] + b1.x, relu_lo); x[5] = fmaxf(x[5] + b1.y, relu_lo);
+                x[6] = fmaxf(x[6] + b1.z, relu_lo); x[7] = fmaxf(x[7] + b1.w, relu_lo);
+                if (WMASK) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << (cc * 8 + e)) : 0u;
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = ((word >> (cc * 8 + e)) & 1u) ? x[e] : 0.f;
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = ((word >> (cc * 8 + e)) & 1u) ? x[e] : 0.f;
-            }
-            uint32_t packed[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 p = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-              packed[e] = *reinterpret_cast<uint32_t*>(&p);
-            }
-            if (MODE == MODE_NT && HEADS > 0) {
-              // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation that is stored
+              uint32_t packed[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xFFFF0000u);
-                const int j = c * 32 + cc * 8 + 2 * e;
-                hacc0 = fmaf(r0, s_head[j], hacc0); hacc0 = fmaf(r1, s_head[j + 1], hacc0);
-                if (HEADS == 3) {
-                  hacc1 = fmaf(r0, s_head[BN + j], hacc1); hacc1 = fmaf(r1, s_head[BN + j + 1], hacc1);
-                  hacc2 = fmaf(r0, s_head[2 * BN + j], hacc2); hacc2 = fmaf(r1, s_head[2 * BN + j + 1], hacc2);
+                __nv_bfloat162 p = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+                packed[e] = *reinterpret_cast<uint32_t*>(&p);
+              }
+              if (MODE == MODE_NT && HEADS > 0) {
+                // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation that is stored
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xFFFF0000u);
+                  const int j = c * 32 + cc * 8 + 2 * e;
+                  hacc0 = fmaf(r0, s_head[j], hacc0); hacc0 = fmaf(r1, s_head[j + 1], hacc0);
+                  if (HEADS == 3) {
+                    hacc1 = fmaf(r0, s_head[BN + j], hacc1); hacc1 = fmaf(r1, s_head[BN + j + 1], hacc1);
+                    hacc2 = fmaf(r0, s_head[2 * BN + j], hacc2); hacc2 = fmaf(r1, s_head[2 * BN + j + 1], hacc2);
+                  }
                 }
               }
+              *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
-            *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (MODE == MODE_NT && WMASK) mbits[c] = outbits;
           }
-          if (MODE == MODE_NT && WMASK) mbits[c] = outbits;
+          if (h == kHalves - 1) {
+            // accumulator fully drained -> hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          // staged half tile -> global (TMA store clips rows beyond M); do not wait for it here
+          fence_proxy_async_smem();
+          named_bar_sync(2, kEpiThreads);
+          if (issuer) {
+#pragma unroll
+            for (int j = 0; j < Cfg::kHalfCols / 64; ++j)
+              tma_store_2d(&tmD, s_half + j * 16384, h * Cfg::kHalfCols + j * 64, tile * kBlockM);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
         }
+        acc ^= 1; if (acc == 0) acc_ph ^= 1;
         if (MODE == MODE_NT && row_ok) {
           if (WMASK) {
             uint4* mo = reinterpret_cast<uint4*>(args.mask_out + gr * NW);
@@ -297,21 +329,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (HEADS == 3) { o[1] = hacc1 + args.head_b[1]; o[2] = hacc2 + args.head_b[2]; }
           }
         }
-        // accumulator drained -> hand it back to the MMA warp
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        acc ^= 1; if (acc == 0) acc_ph ^= 1;
-        // staged tile -> global (TMA store clips rows beyond M)
-        fence_proxy_async_smem();
-        named_bar_sync(1, kEpiThreads);
-        if (issuer) {
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_store_2d(&tmD, s_staging + j * 16384, j * 64, tile * kBlockM);
-          tma_store_commit();
-          tma_store_wait_read0();
-        }
-        named_bar_sync(1, kEpiThreads);
       }
       if (issuer) tma_store_wait_all0();
     }
