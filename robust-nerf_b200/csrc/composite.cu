@@ -41,23 +41,38 @@ __device__ __forceinline__ float warp_suffix_sum(float v, int lane) {
 }
 
 struct SampleIn { float c0, c1, c2, sig, z, dist; };
+struct Fetched { float a, b, c, sig, z, zn, nz; };     // raw global values of one sample, no dependent math
 
-// load one sample (s < S guaranteed) in either input convention
+// issue the global loads of one sample (s < S guaranteed) in either input convention
 template <bool RAW>
-__device__ __forceinline__ SampleIn load_sample(const float* __restrict__ rgb, const float* __restrict__ sigma,
+__device__ __forceinline__ Fetched fetch_sample(const float* __restrict__ rgb, const float* __restrict__ sigma,
                                                 const float4* __restrict__ raw4, const float* __restrict__ z,
-                                                const float* __restrict__ noise, int64_t base, int s, int S, float nrm) {
-  SampleIn o;
+                                                const float* __restrict__ noise, int64_t base, int s, int S) {
+  Fetched f;
   const int64_t i = base + s;
   if (RAW) {
     const float4 r = __ldcs(raw4 + i);
-    o.c0 = sigmoidf_acc(r.x); o.c1 = sigmoidf_acc(r.y); o.c2 = sigmoidf_acc(r.z); o.sig = r.w;   // model.py:181,194
+    f.a = r.x; f.b = r.y; f.c = r.z; f.sig = r.w;
   } else {
-    o.c0 = __ldcs(rgb + i * 3); o.c1 = __ldcs(rgb + i * 3 + 1); o.c2 = __ldcs(rgb + i * 3 + 2); o.sig = __ldcs(sigma + i);
+    f.a = __ldcs(rgb + i * 3); f.b = __ldcs(rgb + i * 3 + 1); f.c = __ldcs(rgb + i * 3 + 2); f.sig = __ldcs(sigma + i);
   }
-  if (noise) o.sig = __fadd_rn(o.sig, __ldcs(noise + i));                                          // rendering.py:78-80
-  o.z = __ldg(z + i);
-  const float dz = (s == S - 1) ? 1e10f : __fsub_rn(__ldg(z + i + 1), o.z);                        // rendering.py:67-72
+  f.nz = noise ? __ldcs(noise + i) : 0.f;
+  f.z = __ldg(z + i);
+  f.zn = (s == S - 1) ? 0.f : __ldg(z + i + 1);
+  return f;
+}
+
+template <bool RAW>
+__device__ __forceinline__ SampleIn activate_sample(const Fetched& f, bool has_noise, int s, int S, float nrm) {
+  SampleIn o;
+  if (RAW) {
+    o.c0 = sigmoidf_acc(f.a); o.c1 = sigmoidf_acc(f.b); o.c2 = sigmoidf_acc(f.c);                  // model.py:181,194
+  } else {
+    o.c0 = f.a; o.c1 = f.b; o.c2 = f.c;
+  }
+  o.sig = has_noise ? __fadd_rn(f.sig, f.nz) : f.sig;                                              // rendering.py:78-80
+  o.z = f.z;
+  const float dz = (s == S - 1) ? 1e10f : __fsub_rn(f.zn, f.z);                                    // rendering.py:67-72
   o.dist = __fmul_rn(dz, nrm);                                                                     // rendering.py:75
   return o;
 }
@@ -82,17 +97,23 @@ composite_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
     const int64_t base = b * S;
     float carry = 1.0f, a0 = 0.f, a1 = 0.f, a2 = 0.f, ad = 0.f, aw = 0.f;
     int r = 0;
+    Fetched cur{};
+    if (lane < S) cur = fetch_sample<RAW>(rgb, sigma, raw4, z, noise, base, lane, S);
     for (; r < rounds; ++r) {
       if (t_min > 0.f && carry < t_min) break;                       // early termination (warp-uniform)
       const int s = r * 32 + lane;
       const bool valid = s < S;
+      // software pipelining: the next round's loads are in flight while this round is scanned
+      Fetched nxt{};
+      if (s + 32 < S) nxt = fetch_sample<RAW>(rgb, sigma, raw4, z, noise, base, s + 32, S);
       float alpha = 0.f, t = 1.f;
       SampleIn in{};
       if (valid) {
-        in = load_sample<RAW>(rgb, sigma, raw4, z, noise, base, s, S, nrm);
+        in = activate_sample<RAW>(cur, noise != nullptr, s, S, nrm);
         alpha = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(in.sig, 0.f), in.dist)));                    // rendering.py:83
         t = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);                                             // rendering.py:90
       }
+      cur = nxt;
       const float incl = warp_scan_mul(t, lane);
       float excl = __shfl_up_sync(0xffffffffu, incl, 1);
       if (lane == 0) excl = 1.0f;
@@ -135,22 +156,35 @@ composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
     const float gm0 = g_map[b * 3], gm1 = g_map[b * 3 + 1], gm2 = g_map[b * 3 + 2];
     const float gD = g_depth ? g_depth[b] : 0.f;
     const float gconst = (g_acc ? g_acc[b] : 0.f) - (white ? (gm0 + gm1 + gm2) : 0.f);
-    float al[MAXR], Tn[MAXR], c0[MAXR], c1[MAXR], c2[MAXR], sg[MAXR], ds[MAXR], G[MAXR];
+    float al[MAXR], Tn[MAXR], c0[MAXR], c1[MAXR], c2[MAXR], sg[MAXR], ds[MAXR], G[MAXR], zz[MAXR], nzv[MAXR];
+    // ---- phase 0: issue every global load of the ray before any dependent math ----
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      c0[r] = c1[r] = c2[r] = 0.f; sg[r] = 0.f; ds[r] = 0.f; G[r] = 0.f; zz[r] = 0.f; nzv[r] = 0.f;
+      const int s = r * 32 + lane;
+      if (r < rounds && s < S) {
+        const Fetched f = fetch_sample<RAW>(rgb, sigma, raw4, z, noise, base, s, S);
+        c0[r] = f.a; c1[r] = f.b; c2[r] = f.c; sg[r] = f.sig; zz[r] = f.z; ds[r] = f.zn; nzv[r] = f.nz;
+        G[r] = g_w ? __ldcs(g_w + base + s) : 0.f;
+      }
+    }
     float carry = 1.0f;
     // ---- forward sweep: alpha, incoming transmittance, dL/dw per sample ----
 #pragma unroll
     for (int r = 0; r < MAXR; ++r) {
-      al[r] = 0.f; Tn[r] = 0.f; c0[r] = c1[r] = c2[r] = 0.f; sg[r] = 0.f; ds[r] = 0.f; G[r] = 0.f;
+      al[r] = 0.f; Tn[r] = 0.f;
       if (r < rounds) {
         const int s = r * 32 + lane;
         const bool valid = s < S;
         float t = 1.f;
         if (valid) {
-          const SampleIn in = load_sample<RAW>(rgb, sigma, raw4, z, noise, base, s, S, nrm);
+          Fetched f;
+          f.a = c0[r]; f.b = c1[r]; f.c = c2[r]; f.sig = sg[r]; f.z = zz[r]; f.zn = ds[r]; f.nz = nzv[r];
+          const SampleIn in = activate_sample<RAW>(f, noise != nullptr, s, S, nrm);
           al[r] = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(in.sig, 0.f), in.dist)));
           t = __fadd_rn(__fsub_rn(1.0f, al[r]), 1e-10f);
           c0[r] = in.c0; c1[r] = in.c1; c2[r] = in.c2; sg[r] = in.sig; ds[r] = in.dist;
-          G[r] = gm0 * in.c0 + gm1 * in.c1 + gm2 * in.c2 + gD * in.z + gconst + (g_w ? __ldcs(g_w + base + s) : 0.f);
+          G[r] = gm0 * in.c0 + gm1 * in.c1 + gm2 * in.c2 + gD * in.z + gconst + G[r];
         }
         const float incl = warp_scan_mul(t, lane);
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);

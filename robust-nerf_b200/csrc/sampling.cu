@@ -162,11 +162,120 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
   }
 }
 
+// ---- register-resident bitonic sort: 32*E values, element index i = lane*E + e ----
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[E], int lane) {
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= E) {
+        const int lj = j / E;                       // partner lane distance
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const float other = __shfl_xor_sync(0xffffffffu, v[e], lj);
+          const int i = lane * E + e;
+          const bool up = (i & k) == 0;
+          const bool lower = (i & j) == 0;
+          v[e] = (lower == up) ? fminf(v[e], other) : fmaxf(v[e], other);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & j) == 0) {
+            const int i = lane * E + e;
+            const bool up = (i & k) == 0;
+            const float a = v[e], b = v[e | j];
+            const float mn = fminf(a, b), mx = fmaxf(a, b);
+            v[e] = up ? mn : mx;
+            v[e | j] = up ? mx : mn;
+          }
+        }
+      }
+    }
+  }
+}
+
+// sample_hierarchical, fast path (Nf <= 32*E <= 256): samples are inverted and sorted in registers
+// (shuffle bitonic network), then merged with the already sorted coarse depths by rank: a coarse
+// depth lands at i + #{samples < z_i}, a sample at j + #{coarse <= s_j} (binary searches in smem).
+template <int E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict__ rd,
                            const float* __restrict__ zc, const float* __restrict__ weights, int64_t B, int Nc,
-                           const float* __restrict__ u, int64_t u_stride, int Nf, int P,
+                           const float* __restrict__ u, int64_t u_stride, int Nf,
                            float* __restrict__ z_all, float* __restrict__ pts, int64_t* __restrict__ inds_out) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nb = Nc - 1, Nt = Nc + Nf;
+  constexpr int NS = 32 * E;
+  float* s_z = smem + (size_t)w * (5 * Nc + NS + Nf);
+  float* s_bins = s_z + Nc;
+  float* s_w = s_bins + Nc;
+  float* s_cdf = s_w + Nc;
+  float* s_smp = s_cdf + Nc;                 // [NS] sorted samples
+  float* s_out = s_smp + NS;                 // [Nc + Nf] merged depths
+  for (int64_t b = blockIdx.x * (int64_t)kWarpsPerCta + w; b < B; b += (int64_t)gridDim.x * kWarpsPerCta) {
+    for (int k = lane; k < Nc; k += 32) s_z[k] = __ldcs(zc + b * Nc + k);
+    for (int k = lane; k < Nc - 2; k += 32) s_w[k] = __ldcs(weights + b * Nc + k + 1);   // interior weights, rays.py:321
+    __syncwarp();
+    for (int k = lane; k < nb; k += 32) s_bins[k] = __fmul_rn(0.5f, __fadd_rn(s_z[k + 1], s_z[k]));   // rays.py:316
+    __syncwarp();
+    warp_build_cdf(s_w, s_cdf, nb, lane);
+    float v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int j = e * 32 + lane;            // coalesced over u / inds
+      v[e] = CUDART_INF_F;
+      if (j < Nf) {
+        int ind;
+        v[e] = invert_cdf(s_cdf, s_bins, nb, __ldg(u + b * u_stride + j), ind);
+        if (inds_out) inds_out[b * Nf + j] = ind;
+      }
+    }
+    warp_bitonic_sort_regs<E>(v, lane);
+#pragma unroll
+    for (int e = 0; e < E; ++e) s_smp[lane * E + e] = v[e];
+    __syncwarp();
+    // rank merge (rays.py:328: sort of the concatenation, values only)
+    for (int i = lane; i < Nc; i += 32) {
+      const float zi = s_z[i];
+      int lo = 0, hi = Nf;                    // #{samples < zi}
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_smp[mid] < zi) lo = mid + 1; else hi = mid; }
+      s_out[i + lo] = zi;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int j = lane * E + e;
+      if (j < Nf) {
+        const float sj = v[e];
+        int lo = 0, hi = Nc;                  // #{coarse <= sj}
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_z[mid] <= sj) lo = mid + 1; else hi = mid; }
+        s_out[j + lo] = sj;
+      }
+    }
+    __syncwarp();
+    for (int k = lane; k < Nt; k += 32) z_all[b * Nt + k] = s_out[k];
+    if (pts) {
+      const float o0 = ro[b * 3], o1 = ro[b * 3 + 1], o2 = ro[b * 3 + 2];
+      const float d0 = rd[b * 3], d1 = rd[b * 3 + 1], d2 = rd[b * 3 + 2];
+      for (int e = lane; e < 3 * Nt; e += 32) {     // 3*Nt contiguous floats per ray: coalesced stores
+        const int s = e / 3, k = e - 3 * s;
+        const float o = k == 0 ? o0 : (k == 1 ? o1 : o2), d = k == 0 ? d0 : (k == 1 ? d1 : d2);
+        pts[(b * Nt) * 3 + e] = __fadd_rn(o, __fmul_rn(d, s_out[s]));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// generic path (any Nf): shared-memory bitonic sort of the concatenation
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+sample_hierarchical_generic_kernel(const float* __restrict__ ro, const float* __restrict__ rd,
+                                   const float* __restrict__ zc, const float* __restrict__ weights, int64_t B, int Nc,
+                                   const float* __restrict__ u, int64_t u_stride, int Nf, int P,
+                                   float* __restrict__ z_all, float* __restrict__ pts, int64_t* __restrict__ inds_out) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nb = Nc - 1, Nt = Nc + Nf;
@@ -175,7 +284,6 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
   float* s_cdf = s_w + Nc;
   float* s_sort = s_cdf + Nc;
   for (int64_t b = blockIdx.x * (int64_t)kWarpsPerCta + w; b < B; b += (int64_t)gridDim.x * kWarpsPerCta) {
-    // coarse depths -> sort buffer; mid-point bins; interior weights (rays.py:316-321)
     for (int k = lane; k < Nc; k += 32) s_sort[k] = __ldcs(zc + b * Nc + k);
     for (int k = Nt + lane; k < P; k += 32) s_sort[k] = CUDART_INF_F;
     for (int k = lane; k < Nc - 2; k += 32) s_w[k] = __ldcs(weights + b * Nc + k + 1);
@@ -189,12 +297,11 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
       if (inds_out) inds_out[b * Nf + j] = ind;
     }
     __syncwarp();
-    warp_bitonic_sort(s_sort, P, lane);                                       // rays.py:328 (values only)
+    warp_bitonic_sort(s_sort, P, lane);
     for (int k = lane; k < Nt; k += 32) z_all[b * Nt + k] = s_sort[k];
     if (pts) {
       const float o0 = ro[b * 3], o1 = ro[b * 3 + 1], o2 = ro[b * 3 + 2];
       const float d0 = rd[b * 3], d1 = rd[b * 3 + 1], d2 = rd[b * 3 + 2];
-      // 3*Nt contiguous floats per ray: lane-strided so the stores coalesce
       for (int e = lane; e < 3 * Nt; e += 32) {
         const int s = e / 3, k = e - 3 * s;
         const float o = k == 0 ? o0 : (k == 1 ? o1 : o2), d = k == 0 ? d0 : (k == 1 ? d1 : d2);
@@ -203,6 +310,21 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
     }
     __syncwarp();
   }
+}
+
+template <int E>
+static int launch_hier(const float* ro, const float* rd, const float* zc, const float* weights, int64_t B, int Nc,
+                       const float* u, int64_t u_stride, int Nf, float* z_all, float* pts, int64_t* inds_out, cudaStream_t st) {
+  const size_t smem = (size_t)kWarpsPerCta * (5 * Nc + 32 * E + Nf) * sizeof(float);
+  if (smem > 200 * 1024) return RN_ERR_INVALID_ARG;
+  if (smem > 48 * 1024)
+    RN_CUDA_CHECK(cudaFuncSetAttribute(sample_hierarchical_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t want = ceil_div(B, kWarpsPerCta);
+  const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  sample_hierarchical_kernel<E><<<grid, kWarpsPerCta * 32, smem, st>>>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts,
+                                                                      inds_out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
 }
 
 }  // namespace rn
@@ -255,15 +377,20 @@ int rn_sample_hierarchical_fwd(const float* ro, const float* rd, const float* zc
                                rn_stream_t stream) {
   RN_REQUIRE(zc && weights && u && z_all && B >= 0 && Nc >= 3 && Nf >= 1 && (!pts || (ro && rd)));
   if (B == 0) return RN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Nf <= 32) return launch_hier<1>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts, inds_out, st);
+  if (Nf <= 64) return launch_hier<2>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts, inds_out, st);
+  if (Nf <= 128) return launch_hier<4>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts, inds_out, st);
+  if (Nf <= 256) return launch_hier<8>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts, inds_out, st);
   int P = 2;
   while (P < Nc + Nf) P <<= 1;
   const size_t smem = (size_t)kWarpsPerCta * (3 * Nc + P) * sizeof(float);
   RN_REQUIRE(smem <= 200 * 1024);
   if (smem > 48 * 1024)
-    RN_CUDA_CHECK(cudaFuncSetAttribute(sample_hierarchical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RN_CUDA_CHECK(cudaFuncSetAttribute(sample_hierarchical_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(ceil_div(B, kWarpsPerCta) < (int64_t)num_sms() * 8 ? ceil_div(B, kWarpsPerCta) : (int64_t)num_sms() * 8);
-  sample_hierarchical_kernel<<<grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(ro, rd, zc, weights, B, Nc, u, u_stride,
-                                                                                     Nf, P, z_all, pts, inds_out);
+  sample_hierarchical_generic_kernel<<<grid, kWarpsPerCta * 32, smem, st>>>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, P, z_all,
+                                                                           pts, inds_out);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
