@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

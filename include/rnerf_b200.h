@@ -43,6 +43,13 @@ unsigned long long rn_launch_count(void);
 /* measurement hooks: when enabled, every tcgen05 GEMM launch is bracketed by CUDA events on its
  * stream; rn_prof_collect synchronises and returns, per mode (0 NT fwd, 1 NN dgrad, 2 TN wgrad),
  * the summed kernel milliseconds, executed FLOPs (2*M*N*K incl. padding) and launch counts. */
+/* tuning flags: flag 0 = run the MLP forward as ONE layer-chained persistent launch (default 1)
+ * instead of ten per-layer GEMM launches (0). Results are identical.
+ * flag 2 = operand ring depths of the chained kernel: 0 -> (A,B) = (5,2) stages, 1 -> (3,3).
+ * flag 1 exists only in builds made with RN_EXPERIMENTS=1 (bottleneck experiments of
+ * scripts/chain_experiments.py: switches parts of the pipeline off, results are then wrong);
+ * the shipped library rejects it. */
+int rn_set_flag(int flag, int value);
 int rn_prof_enable(int on);
 int rn_prof_collect(double* ms3_host, double* flops3_host, int* launches3_host);
 

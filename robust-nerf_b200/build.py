@@ -19,6 +19,8 @@ SOURCES = ["api.cu", "raygen.cu", "sampling.cu", "composite.cu", "encode.cu", "g
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("RN_EXPERIMENTS") == "1":      # measurement-only knobs (scripts/chain_experiments.py); never shipped
+    FLAGS.append("-DRN_EXPERIMENTS")
 
 
 def _digest():

@@ -18,6 +18,15 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
 int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int ncols, float* dst, int64_t dst_ld, float* colsum_dst,
                    cudaStream_t st);
 
+// one layer of the chained forward (mlp_chain_forward): D[M,n] = act(A[M,k] B[n,k]^T + bias), bf16 views
+struct ChainLayerHost {
+  const void* A; int64_t lda; const void* B; int64_t ldb; void* D; int64_t ldd;
+  int k, n, relu, heads, head_col, bias_off, head_w_off, head_b_off, dep;
+  uint32_t* mask_out;
+};
+int mlp_chain_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const float* consts, float* raw, bool wmask,
+                      cudaStream_t st);
+
 int launch_encode(const float* pts, const float* dirs, int64_t M, int group, void* XC, int ldx, void* FD, int ldf, cudaStream_t st);
 size_t heads_bwd_scratch_bytes(int64_t M);
 int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,

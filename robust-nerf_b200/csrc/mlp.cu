@@ -65,6 +65,12 @@ static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimen
     if (_rc != RN_OK) return _rc; \
   } while (0)
 
+#ifdef RN_EXPERIMENTS
+extern int g_chain_dbg;
+#endif
+extern int g_chain_ring;
+int g_chain_fwd = 1;      // rn_set_flag(0, v): run the forward as one layer-chained persistent launch
+
 static int mlp_forward(const void* packed, const float* pts, const float* dirs, int64_t M, int group, void* ws,
                        int training, float* raw, cudaStream_t st) {
   const bf16* W = reinterpret_cast<const bf16*>(packed);
@@ -86,6 +92,19 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
     H[0] = HA; H[1] = HB; H[2] = HA; H[3] = HB; H[4] = XC + 64; H[5] = HA; H[6] = HB; H[7] = HA;
   }
   RN_TRY(launch_encode(pts, dirs, M, group, XC, 320, FD, 320, st));
+  if (g_chain_fwd) {
+    ChainLayerHost L[10];
+    for (int l = 0; l < 8; ++l) {
+      const bool skip_in = (l == 5);
+      L[l] = ChainLayerHost{l == 0 ? (const void*)XC : (skip_in ? (const void*)XC : (const void*)H[l - 1]),
+                            (l == 0 || skip_in) ? 320 : ld_of(l - 1), W + trunk_w(l), l == 0 ? 64 : (skip_in ? 320 : 256),
+                            H[l], ld_of(l), l == 0 ? 64 : (skip_in ? 320 : 256), 256, 1, l == 7 ? 1 : 0, 3,
+                            (int)(kB0 + 256 * l), (int)kWSig, (int)kBSig, l == 0 ? 0 : 1, MB[l]};
+    }
+    L[8] = ChainLayerHost{H[7], 256, W + kWFS, 256, FD, 320, 256, 256, 0, 0, 0, (int)kBF, 0, 0, 1, nullptr};
+    L[9] = ChainLayerHost{FD, 320, W + kWD, 320, HC, 128, 320, 128, 1, 3, 0, (int)kBD, (int)kWRgb, (int)kBRgb, 1, nullptr};
+    return mlp_chain_forward(L, 10, M, F, raw, training != 0, st);
+  }
   RN_TRY(gemm_nt(XC, 320, W + kW0, 64, H[0], 256, M, 256, 64, F + kB0, 1, st, MB[0]));
   for (int l = 1; l < 8; ++l) {
     const bf16* in = (l == 5) ? XC : H[l - 1];
@@ -163,6 +182,15 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
 using namespace rn;
 
 extern "C" {
+
+int rn_set_flag(int flag, int value) {
+  if (flag == 0) { g_chain_fwd = value != 0; return RN_OK; }
+#ifdef RN_EXPERIMENTS
+  if (flag == 1) { g_chain_dbg = value; return RN_OK; }
+#endif
+  if (flag == 2) { g_chain_ring = value; return RN_OK; }
+  return RN_ERR_INVALID_ARG;
+}
 
 size_t rn_mlp_workspace_bytes(int64_t M, int training) { return M > 0 ? workspace_bytes(M, training) : 0; }
 

@@ -660,3 +660,35 @@ def test_pose_gradients_through_full_render(rn, dev):
             rel = np.linalg.norm(got[touched] - want[touched]) / np.linalg.norm(want[touched])
             cos = (got * want).sum() / (np.linalg.norm(got) * np.linalg.norm(want))
             assert rel < tol and cos > cos_min, (emulate, nm, rel, cos)
+
+
+def test_chained_forward_equals_per_layer_forward(rn, dev):
+    """The layer-chained persistent forward (one launch) must reproduce the per-layer GEMM chain bit for bit
+    (same MMAs, same epilogue arithmetic), in inference and in training mode, including ragged tile counts."""
+    from robust_nerf_b200 import _lib
+    lib = _lib.lib()
+    w = O.make_weights(13, sharpen=True)
+    net = load_net(rn, w, dev)
+    rng = np.random.default_rng(4)
+    try:
+        for M in (1, 128, 129, 700, 5000, 70000):
+            pts = T(rng.uniform(-3, 3, (M, 3)).astype(np.float32), dev)
+            dirs = T(rng.standard_normal((M, 3)).astype(np.float32), dev)
+            outs = {}
+            for chain in (0, 1):
+                lib.rn_set_flag(0, chain)
+                with torch.no_grad():
+                    outs[("eval", chain)] = net.forward_raw(pts, dirs, 1).clone()
+                net.zero_grad()
+                x = pts.clone().requires_grad_(True)
+                raw = net.forward_raw(x, dirs, 1)
+                outs[("train", chain)] = raw.detach().clone()
+                raw.square().sum().backward()
+                outs[("grad", chain)] = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+                outs[("dx", chain)] = x.grad.clone()
+            torch.cuda.synchronize()
+            for k in ("eval", "train", "grad", "dx"):
+                assert torch.equal(outs[(k, 0)], outs[(k, 1)]), (M, k, (outs[(k, 0)] - outs[(k, 1)]).abs().max().item())
+            assert torch.equal(outs[("eval", 1)], outs[("train", 1)])
+    finally:
+        lib.rn_set_flag(0, 1)
