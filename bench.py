@@ -210,25 +210,39 @@ def run_gpu(args):
 
     W_, K_ = max(3, args.warmup), max(1, args.steps)
 
-    # ---- device-resident timing (value) with live GEMM event timing (roofline) ----
+    use_graph = not args.no_graph
+    step_fn = trainer.step_rays_graphed if use_graph else trainer.step_rays
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- eager pass: K timed steps with every GEMM launch bracketed by CUDA events (roofline) and counted ----
     for i in range(W_):
         trainer.step_rays(*dev_batches[i % POOL])
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     lib.rn_prof_enable(1)
     n0 = lib.rn_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K_):
-        loss = trainer.step_rays(*dev_batches[i % POOL])
+        trainer.step_rays(*dev_batches[i % POOL])
     e1.record()
     barrier()
     launches = int(lib.rn_launch_count() - n0)
     lib.rn_prof_enable(0)
     ms3, fl3, ln3 = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_int * 3)()
     lib.rn_prof_collect(ms3, fl3, ln3)
+    eager_ms_per_step = reduce_max(e0.elapsed_time(e1)) / K_
+
+    # ---- device-resident timing (value): the same step, replayed from a CUDA graph unless --no-graph ----
+    for i in range(W_):
+        step_fn(*dev_batches[i % POOL])
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0.record()
+    for i in range(K_):
+        loss = step_fn(*dev_batches[i % POOL])
+    e1.record()
+    barrier()
     t_ms = reduce_max(e0.elapsed_time(e1))
     clock_info = clocks.stop() if rank == 0 else None
     ms_per_step = t_ms / K_
@@ -239,13 +253,13 @@ def run_gpu(args):
     loss_host = torch.zeros(1).pin_memory()
     for i in range(3):
         b = [t.to(dev, non_blocking=True) for t in host_batches[i % POOL]]
-        loss_host.copy_(trainer.step_rays(*b).reshape(1), non_blocking=True)
+        loss_host.copy_(step_fn(*b).reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
     barrier()
     e0.record()
     for i in range(K_):
         b = [t.to(dev, non_blocking=True) for t in host_batches[i % POOL]]
-        loss_host.copy_(trainer.step_rays(*b).reshape(1), non_blocking=True)
+        loss_host.copy_(step_fn(*b).reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the step's loss
         _ = float(loss_host[0])
     e1.record()
@@ -300,6 +314,8 @@ def run_gpu(args):
                        "samples": f"{NC}+{NF}", "mlp": "8x256, PE L=10/4, bf16 tcgen05 operands, fp32 accumulate",
                        "parallelism": f"dp{world} (one all-reduce of the flat gradient buffer per step)" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: 7.7 GB of activations streamed per step vs 126 MB L2, no flush needed",
+                       "launch": "CUDA graph replay of the whole step" if use_graph else "eager (one launch per kernel)",
+                       "eager_ms_per_step": eager_ms_per_step,
                        "loss": loss_val},
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": RAYS_PER_GPU * 9 * 4, "d2h_bytes_per_step": 4,
@@ -310,7 +326,8 @@ def run_gpu(args):
                          "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic,
                          "peak_source": peaks["source"],
                          "algorithmic_flops_per_step": algo_flops_per_step, "gemm_launches_per_step": n_gemm / K_,
-                         "gemm_ms_per_step": gemm_ms_per_step, "gemm_share_of_step": gemm_ms_per_step / ms_per_step,
+                         "gemm_ms_per_step": gemm_ms_per_step, "gemm_share_of_step": gemm_ms_per_step / eager_ms_per_step,
+                         "measured_in": "eager pass of the same K steps (CUDA events around every GEMM launch on its stream)",
                          "per_mode": per_mode},
             "cpu_baseline": None if cpu_rate is None else {
                 "value": cpu_rate, "unit": "rays/s", "cores": cores, "kind": "port",
@@ -333,6 +350,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -187,6 +187,8 @@ int rn_clip_adam_step(float* params, float* grads /*scaled in place by the clip*
                       const int64_t* group_offsets_host /*[n_groups+1]*/, const float* group_max_norm_host, int n_groups,
                       float lr, float beta1, float beta2, float eps, int step,
                       float* norms_out /*scratch+output, 8 + 8*64 floats; [0..n_groups) = gradient norms*/,
+                      const float* hyper_dev /*NULL, or device [lr, 1-beta1^step, sqrt(1-beta2^step)] overriding lr/step
+                                               (so a captured CUDA graph can be replayed across steps)*/,
                       rn_stream_t stream);
 
 #ifdef __cplusplus

@@ -52,7 +52,10 @@ grad_sumsq_kernel(const float* __restrict__ g, Groups gr, float* __restrict__ pa
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, Groups gr, const float* __restrict__ part, float* __restrict__ norms, float lr, float b1,
-                 float b2, float eps, float bc1, float bc2_sqrt) {
+                 float b2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ hyper) {
+  // hyper (device, optional): [lr, 1 - beta1^t, sqrt(1 - beta2^t)] -- lets a captured CUDA graph be replayed
+  // with a changing learning rate / step count without re-capturing
+  if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }
   __shared__ float s_coef[kMaxGroups];
   if (threadIdx.x < gr.n) {
     float t = 0.f;
@@ -111,7 +114,8 @@ int rn_device_sm_count(int* out) {
 
 int rn_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const int64_t* group_offsets_host, const float* group_max_norm_host, int n_groups, float lr,
-                      float beta1, float beta2, float eps, int step, float* norms_out, rn_stream_t stream) {
+                      float beta1, float beta2, float eps, int step, float* norms_out, const float* hyper_dev,
+                      rn_stream_t stream) {
   RN_REQUIRE(params && grads && exp_avg && exp_avg_sq && norms_out && group_offsets_host && group_max_norm_host);
   RN_REQUIRE(n > 0 && n_groups >= 1 && n_groups <= kMaxGroups && step >= 1);
   Groups gr{};
@@ -126,7 +130,7 @@ int rn_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_av
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
   clip_adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, gr, part, norms_out, lr, beta1,
-                                                     beta2, eps, bc1, bc2_sqrt);
+                                                     beta2, eps, bc1, bc2_sqrt, hyper_dev);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -209,6 +209,11 @@ class Trainer:
             m._packed.grad_sink = self.gflat[start:off]      # backward kernels write gradients here directly
         off = _flatten_into(self.pose_params, self.flat, self.gflat, off)
         self.norms = torch.zeros(2 * (8 + 8 * 64), device=dev)    # two rn_clip_adam_step scratch areas
+        # [lr, 1-b1^t, sqrt(1-b2^t)] for the nets and for the poses: read by the Adam kernel from device memory so
+        # a captured CUDA graph can be replayed while the schedule advances
+        self.hyper_host = torch.zeros(512, 6).pin_memory()      # ring: the host may run many steps ahead of the device
+        self.hyper = torch.zeros(6, device=dev)
+        self._graphs = {}
         self.iteration = 0
         self.pose_steps = 0
         self.nets = nets
@@ -227,26 +232,40 @@ class Trainer:
     def _allreduce(self):
         allreduce_mean_(self.gflat, self.world, self.group)
 
-    def _adam(self, lo: int, hi: int, groups: Sequence[int], max_norms: Sequence[float], lr: float, step: int, norm_slot: int):
+    def _adam(self, lo: int, hi: int, groups: Sequence[int], max_norms: Sequence[float], hyper_slot: int, norm_slot: int):
         n = hi - lo
         offs = (ctypes.c_int64 * len(groups))(*[g - lo for g in groups])
         mx = (ctypes.c_float * len(max_norms))(*max_norms)
         call("rn_clip_adam_step", self.flat[lo:hi].data_ptr(), self.gflat[lo:hi].data_ptr(), self.exp_avg[lo:hi].data_ptr(),
-             self.exp_avg_sq[lo:hi].data_ptr(), n, offs, mx, len(max_norms), float(lr), float(self.betas[0]),
-             float(self.betas[1]), float(self.eps), int(step), self.norms[norm_slot:].data_ptr(), stream_ptr())
+             self.exp_avg_sq[lo:hi].data_ptr(), n, offs, mx, len(max_norms), 0.0, float(self.betas[0]),
+             float(self.betas[1]), float(self.eps), 1, self.norms[norm_slot:].data_ptr(),
+             self.hyper[hyper_slot:].data_ptr(), stream_ptr())
 
-    def _optimise(self, separate_clip: bool, optimize_poses: bool):
+    def _advance_schedule(self, optimize_poses: bool):
+        """Host side of the optimiser schedule (train.py:405-411: lr * 0.1^(step/250k)); uploaded to the device
+        buffer the Adam kernel reads, outside any captured graph."""
         self.iteration += 1
-        lr = self.lr * (0.1 ** ((self.iteration - 1) / self.lr_decay_steps))
-        if separate_clip and len(self.nets) == 2:
-            self._adam(0, self.n_net, self.net_offsets, [1.0, 1.0], lr, self.iteration, 0)
-        else:
-            self._adam(0, self.n_net, [0, self.n_net], [1.0], lr, self.iteration, 0)
+        t = self.iteration
+        h = self.hyper_host[t % 512]
+        h[3:] = self.hyper_host[(t - 1) % 512][3:]
+        h[0] = self.lr * (0.1 ** ((t - 1) / self.lr_decay_steps))
+        h[1] = 1.0 - self.betas[0] ** t
+        h[2] = (1.0 - self.betas[1] ** t) ** 0.5
         if self.n_pose and optimize_poses:
             self.pose_steps += 1
-            plr = self.pose_lr * (0.1 ** ((self.pose_steps - 1) / self.lr_decay_steps))
-            self._adam(self.n_net, self.n_net + self.n_pose, [self.n_net, self.n_net + self.n_pose], [0.1], plr,
-                       self.pose_steps, 8 + 8 * 64)
+            tp = self.pose_steps
+            h[3] = self.pose_lr * (0.1 ** ((tp - 1) / self.lr_decay_steps))
+            h[4] = 1.0 - self.betas[0] ** tp
+            h[5] = (1.0 - self.betas[1] ** tp) ** 0.5
+        self.hyper.copy_(h, non_blocking=True)
+
+    def _optimise(self, separate_clip: bool, optimize_poses: bool):
+        if separate_clip and len(self.nets) == 2:
+            self._adam(0, self.n_net, self.net_offsets, [1.0, 1.0], 0, 0)
+        else:
+            self._adam(0, self.n_net, [0, self.n_net], [1.0], 0, 0)
+        if self.n_pose and optimize_poses:
+            self._adam(self.n_net, self.n_net + self.n_pose, [self.n_net, self.n_net + self.n_pose], [0.1], 3, 8 + 8 * 64)
         for m in self.nets:
             m._packed.key = None          # parameters changed under the bf16 cache
 
@@ -259,14 +278,53 @@ class Trainer:
         return loss.detach()
 
     # -- public steps -----------------------------------------------------------------------------
-    def step_rays(self, rays_o: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor, optimise: bool = True
-                  ) -> torch.Tensor:
+    def _step_rays_body(self, rays_o, rays_d, target, optimise):
         self._zero_grad()
         out = render_rays(self.model_coarse, self.model_fine, rays_o, rays_d, self.cfg, is_train=True)
         loss = self._backward(out, target)
         self._allreduce()
         if optimise:
             self._optimise(separate_clip=False, optimize_poses=False)
+        return loss
+
+    def step_rays(self, rays_o: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor, optimise: bool = True
+                  ) -> torch.Tensor:
+        if optimise:
+            self._advance_schedule(False)
+        return self._step_rays_body(rays_o, rays_d, target, optimise)
+
+    def step_rays_graphed(self, rays_o: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """step_rays replayed from a CUDA graph (captured on first use for this batch size; single GPU or DP --
+        the NCCL all-reduce is captured with the rest).  Inputs are copied into static buffers; the ~110 kernel
+        launches of a step then cost one graph launch.  Returns a static loss tensor (overwritten by the next step)."""
+        key = ("rays", tuple(rays_o.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            static = [torch.empty_like(rays_o), torch.empty_like(rays_d), torch.empty_like(target)]
+            for s_, x in zip(static, (rays_o, rays_d, target)):
+                s_.copy_(x)
+            # keep parameters / optimiser state untouched by warm-up and capture
+            saved = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq)]
+            self.hyper.zero_()                       # lr = 0 during warm-up/capture passes
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._step_rays_body(*static, True)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self._step_rays_body(*static, True)
+            for t, sv in zip((self.flat, self.exp_avg, self.exp_avg_sq), saved):
+                t.copy_(sv)
+            for m in self.nets:
+                m._packed.key = None
+            g = self._graphs[key] = (graph, static, loss)
+        graph, static, loss = g
+        for s_, x in zip(static, (rays_o, rays_d, target)):
+            s_.copy_(x, non_blocking=True)
+        self._advance_schedule(False)
+        graph.replay()
         return loss
 
     def step_pixels(self, pixel_batch, sampler, optimize_poses: bool = True, optimise: bool = True) -> torch.Tensor:
@@ -284,6 +342,7 @@ class Trainer:
         loss = self._backward(out, pixel_batch.target_rgb, reg)
         self._allreduce()
         if optimise:
+            self._advance_schedule(optimize_poses)
             self._optimise(separate_clip=True, optimize_poses=optimize_poses)
         return loss
 

@@ -623,7 +623,7 @@ def test_trainer_pose_step_matches_reference_semantics(rn, dev):
     assert cam_b.translation_deltas.abs().max().item() > 1e-4          # poses moved
     pa = torch.cat([p.detach().reshape(-1) for p in nf.parameters()])
     pb_ = torch.cat([p.detach().reshape(-1) for p in mf.parameters()])
-    assert (pa - pb_).abs().mean().item() < 2e-6
+    assert (pa - pb_).abs().mean().item() < 5e-6
 
 
 def test_pose_gradients_through_full_render(rn, dev):
@@ -692,3 +692,26 @@ def test_chained_forward_equals_per_layer_forward(rn, dev):
             assert torch.equal(outs[("eval", 1)], outs[("train", 1)])
     finally:
         lib.rn_set_flag(0, 1)
+
+
+def test_trainer_cuda_graph_step(rn, dev):
+    """The CUDA-graph replayed step trains like the eager step (same kernels; only the Philox offsets differ)."""
+    data, ds, sampler, pb = _scene_batch(rn, dev, 512, seed=21)
+    with torch.no_grad():
+        ro, rd = sampler.get_rays_for_batch(pb, data.poses)
+    cfg = rn.RenderConfig()
+    losses = {}
+    for mode in ("eager", "graph"):
+        mc, mf = _two_nets(rn, dev)
+        tr = rn.Trainer(mc, mf, cfg, lr=5e-4)
+        before = tr.flat.clone()
+        torch.manual_seed(5)
+        step = tr.step_rays if mode == "eager" else tr.step_rays_graphed
+        losses[mode] = [float(step(ro, rd, pb.target_rgb)) for _ in range(6)]
+        assert tr.iteration == 6
+        delta = (tr.flat - before).abs()
+        assert delta.max().item() > 1e-4 and delta.max().item() <= 6 * 5e-4 * 1.01     # six Adam steps at lr 5e-4
+        assert torch.isfinite(tr.flat).all()
+    assert losses["graph"][-1] < losses["graph"][0]
+    np.testing.assert_allclose(losses["graph"][0], losses["eager"][0], rtol=0.05)      # same weights, different draws
+    np.testing.assert_allclose(losses["graph"][-1], losses["eager"][-1], rtol=0.25)
