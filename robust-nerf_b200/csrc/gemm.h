@@ -15,8 +15,8 @@ int gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int
 size_t gemm_tn_scratch_bytes();
 int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ldb, int N, int64_t K, float* scratch,
                    size_t scratch_bytes, TnInfo* info, cudaStream_t st);
-int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int ncols, float* dst, int64_t dst_ld, float* colsum_dst,
-                   cudaStream_t st);
+int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int col0, int ncols, float* dst, int64_t dst_ld,
+                   float* colsum_dst, cudaStream_t st);
 
 // one layer of the chained forward (mlp_chain_forward): D[M,n] = act(A[M,k] B[n,k]^T + bias), bf16 views
 struct ChainLayerHost {

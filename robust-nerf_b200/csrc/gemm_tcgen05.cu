@@ -83,7 +83,7 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kHeadBytes + kMisc;
   static_assert(kNA >= 3 && kNS >= 2, "pipeline too shallow");
   static_assert(kSmemBytes <= kMaxSmem, "shared memory budget exceeded");
-  static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128, 192 or 256");
+  static_assert(BN % 64 == 0 && (BN <= 256 || (MODE == MODE_TN && BN == 320)), "BN: 64..256, or 320 for the TN mode");
 };
 
 // HEADS (NT only): number of fp32 head dot-products fused into the epilogue (0, 1 = sigma, 3 = rgb).
@@ -358,7 +358,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 1, 1);
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN > 256 ? 256 : BN, 1, 1);
+        constexpr uint32_t idesc2 = make_idesc_bf16(kBlockM, BN > 256 ? BN - 256 : 16, 1, 1);
         constexpr uint32_t idesc1 = make_idesc_bf16(kBlockM, 16, 1, 1);
         const uint32_t ones_addr = smem_u32(s_staging);
         int s = 0; uint32_t ph = 0;
@@ -374,6 +375,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint64_t odesc = make_smem_desc_sw128(ones_addr, 8192, 1024);
             const uint32_t accum = (kc != c0 || k != 0);
             umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
+            if (BN > 256)                                                 // columns 256.. : a second, narrower MMA
+              umma_bf16(tmem_base + 256, adesc, make_smem_desc_sw128(b_addr + 4 * 8192 + k * 2048, 8192, 1024), idesc2, accum);
             umma_bf16(tmem_base + BN, adesc, odesc, idesc1, accum);      // column sums of A (bias gradient)
           }
           umma_commit(&empty_a[s]);
@@ -427,8 +430,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // of a thread-per-element loop (the partial tiles total up to 19 MB per layer).
 constexpr int kRedParts = 8;
 __global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float* __restrict__ partial, int m_tiles, int splits, int BN, int row0, int nrows, int ncols,
-                     float* __restrict__ dst, int64_t dst_ld, float* __restrict__ colsum_dst) {
+splitk_reduce_kernel(const float* __restrict__ partial, int m_tiles, int splits, int BN, int row0, int nrows, int col0,
+                     int ncols, float* __restrict__ dst, int64_t dst_ld, float* __restrict__ colsum_dst) {
   __shared__ float s_part[kRedParts][32];
   const int e = threadIdx.x & 31;            // element within the CTA's 32-element block
   const int part = threadIdx.x >> 5;         // which splits this thread sums
@@ -441,7 +444,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int m_tiles, int splits,
   int mt = 0;
   if (o < total) {
     live = dst != nullptr;
-    const int r = row0 + o / ncols, c = o % ncols;
+    const int r = row0 + o / ncols, c = col0 + o % ncols;
     mt = r / kBlockM;
     off = (size_t)(r % kBlockM) * BN + c;
   } else if (o < total + nrows) {
@@ -606,7 +609,7 @@ int gemm_nn(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int
   return launch_gemm<64, MODE_NN>(tA, tB, tD, a, grid, st);
 }
 
-size_t gemm_tn_scratch_bytes() { return (size_t)(num_sms() + 8) * kBlockM * 257 * sizeof(float); }
+size_t gemm_tn_scratch_bytes() { return (size_t)(num_sms() + 8) * kBlockM * 321 * sizeof(float); }
 
 // Weight / bias gradient: partial[split][m_tile] = A[Kslice, Mo]^T B[Kslice, N] (+ column sums of A),
 // then gemm_tn_reduce sums the splits in a fixed order and scatters rows [row0,row0+nrows) x first
@@ -615,7 +618,7 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
                    size_t scratch_bytes, TnInfo* info, cudaStream_t st) {
   int rc = check_arch();
   if (rc != RN_OK) return rc;
-  RN_REQUIRE(K > 0 && Mo > 0 && (N == 256 || N == 64) && scratch && info);
+  RN_REQUIRE(K > 0 && Mo > 0 && (N == 320 || N == 256 || N == 64) && scratch && info);
   CUtensorMap tA, tB;
   if ((rc = make_tmap(&tA, A, Mo, K, lda, 64)) != RN_OK) return rc;
   if ((rc = make_tmap(&tB, B, N, K, ldb, 64)) != RN_OK) return rc;
@@ -632,18 +635,20 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
   RN_REQUIRE((size_t)a.splits * a.m_tiles * kBlockM * (N + 1) * sizeof(float) <= scratch_bytes);
   const int grid = a.m_tiles * a.splits;
   g_prof_next_flops = 2.0 * (double)K * N * Mo;
-  if (N == 256) rc = launch_gemm<256, MODE_TN>(tA, tB, tA, a, grid, st);
+  if (N == 320) rc = launch_gemm<320, MODE_TN>(tA, tB, tA, a, grid, st);
+  else if (N == 256) rc = launch_gemm<256, MODE_TN>(tA, tB, tA, a, grid, st);
   else rc = launch_gemm<64, MODE_TN>(tA, tB, tA, a, grid, st);
   info->m_tiles = a.m_tiles; info->splits = a.splits; info->N = N; info->scratch = scratch;
   return rc;
 }
 
-int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int ncols, float* dst, int64_t dst_ld, float* colsum_dst,
-                   cudaStream_t st) {
-  RN_REQUIRE(row0 >= 0 && nrows > 0 && ncols > 0 && ncols <= info.N && row0 + nrows <= info.m_tiles * kBlockM);
+int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int col0, int ncols, float* dst, int64_t dst_ld,
+                   float* colsum_dst, cudaStream_t st) {
+  RN_REQUIRE(row0 >= 0 && nrows > 0 && col0 >= 0 && ncols > 0 && col0 + ncols <= info.N &&
+             row0 + nrows <= info.m_tiles * kBlockM);
   const int total = nrows * ncols + nrows;
   splitk_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(info.scratch, info.m_tiles, info.splits, info.N, row0, nrows,
-                                                            ncols, dst, dst_ld, colsum_dst);
+                                                           col0, ncols, dst, dst_ld, colsum_dst);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
@@ -1097,7 +1102,7 @@ int rn_gemm_bf16(int mode, const void* A, int64_t lda, const void* B, int64_t ld
     TnInfo info;
     int rc = gemm_tn_launch(A, lda, (int)M, B, ldb, N, K, (float*)scratch, scratch_bytes, &info, st);
     if (rc != RN_OK) return rc;
-    return gemm_tn_reduce(info, 0, (int)M, N, (float*)D, ldd, colsum_out, st);
+    return gemm_tn_reduce(info, 0, (int)M, 0, N, (float*)D, ldd, colsum_out, st);
   }
   return RN_ERR_INVALID_ARG;
 }

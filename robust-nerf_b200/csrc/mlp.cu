@@ -133,17 +133,16 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   // heads: dHC, dFS[:, 256:272], rgb_linear grads
   RN_TRY(launch_heads_bwd(g_raw, w.HC, M, F, w.dHC, w.dFS, 272, w.heads_scratch, G + kG_WRgb, G + kG_BRgb, st));
   // dir_linear: weight grads over [feat(256) | d_enc(27)] and bias
-  RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 256, M, w.scratch, w.scratch_bytes, &ti, st));
-  RN_TRY(gemm_tn_reduce(ti, 0, 128, 256, G + kG_WD, 283, G + kG_BD, st));
-  RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD + 256, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
-  RN_TRY(gemm_tn_reduce(ti, 0, 128, 27, G + kG_WD + 256, 283, nullptr, st));
+  // one launch over the whole 320-wide input [feat(256) | d_enc(27) | 0]
+  RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 320, M, w.scratch, w.scratch_bytes, &ti, st));
+  RN_TRY(gemm_tn_reduce(ti, 0, 128, 0, 283, G + kG_WD, 283, G + kG_BD, st));
   // d feat = dHC x WD[:, 0:256]  -> dFS[:, 0:256]   (feature_linear has no activation: no mask)
   RN_TRY(gemm_nn(w.dHC, 128, W + kWD, 320, w.dFS, 272, M, 256, 128, nullptr, st));
   if (g_dirs) RN_TRY(gemm_nn(w.dHC, 128, W + kWD + 256, 320, w.dDE, 64, M, 64, 128, nullptr, st));
   // feature_linear + sigma_linear (row 256 of dFS^T): weights, biases
   RN_TRY(gemm_tn_launch(w.dFS, 272, 272, w.H[7], 256, 256, M, w.scratch, w.scratch_bytes, &ti, st));
-  RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + kG_WF, 256, G + kG_BF, st));
-  RN_TRY(gemm_tn_reduce(ti, 256, 1, 256, G + kG_WSig, 256, G + kG_BSig, st));
+  RN_TRY(gemm_tn_reduce(ti, 0, 256, 0, 256, G + kG_WF, 256, G + kG_BF, st));
+  RN_TRY(gemm_tn_reduce(ti, 256, 1, 0, 256, G + kG_WSig, 256, G + kG_BSig, st));
   // dH7 = [dF | dsigma] x WFS, masked by H7 > 0
   RN_TRY(gemm_nn(w.dFS, 272, W + kWFS, 256, w.dA, 256, M, 256, 272, w.MB[7], st));
   bf16* dY = w.dA;
@@ -151,24 +150,24 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   for (int l = 7; l >= 1; --l) {
     if (l == 5) {
       // input = XC = [x_enc(64) | H4(256)]
-      RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC + 64, 320, 256, M, w.scratch, w.scratch_bytes, &ti, st));
-      RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5), st));
-      RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
-      RN_TRY(gemm_tn_reduce(ti, 0, 256, 63, G + trunk_gw(5), 319, nullptr, st));
+      // one launch over the whole 320-wide input; the zero pad column 63 is dropped by the two scatters
+      RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 320, M, w.scratch, w.scratch_bytes, &ti, st));
+      RN_TRY(gemm_tn_reduce(ti, 0, 256, 0, 63, G + trunk_gw(5), 319, nullptr, st));
+      RN_TRY(gemm_tn_reduce(ti, 0, 256, 64, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5), st));
       RN_TRY(gemm_nn(dY, 256, W + kW5 + 64, 320, dN, 256, M, 256, 256, w.MB[4], st));
       if (need_in) RN_TRY(gemm_nn(dY, 256, W + kW5, 320, w.dXE5, 64, M, 64, 256, nullptr, st));
     } else {
       const bf16* in = w.H[l - 1];
       const int ldin = ld_of(l - 1);
       RN_TRY(gemm_tn_launch(dY, 256, 256, in, ldin, 256, M, w.scratch, w.scratch_bytes, &ti, st));
-      RN_TRY(gemm_tn_reduce(ti, 0, 256, 256, G + trunk_gw(l), 256, G + trunk_gb(l), st));
+      RN_TRY(gemm_tn_reduce(ti, 0, 256, 0, 256, G + trunk_gw(l), 256, G + trunk_gb(l), st));
       RN_TRY(gemm_nn(dY, 256, W + trunk_w(l), 256, dN, 256, M, 256, 256, w.MB[l - 1], st));
     }
     bf16* t = dY; dY = dN; dN = t;
   }
   // layer 0: input = x_enc
   RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
-  RN_TRY(gemm_tn_reduce(ti, 0, 256, 63, G + trunk_gw(0), 63, G + trunk_gb(0), st));
+  RN_TRY(gemm_tn_reduce(ti, 0, 256, 0, 63, G + trunk_gw(0), 63, G + trunk_gb(0), st));
   if (need_in) {
     RN_TRY(gemm_nn(dY, 256, W + kW0, 64, w.dXE0, 64, M, 64, 256, nullptr, st));
     if (!g_pts) { /* dirs only */ }
