@@ -339,7 +339,14 @@ def run_gpu(args):
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down with captured NCCL kernels alive can block in destroy_process_group: release the graphs,
+        # drain the device, meet once more, then leave without running NCCL's destructors.
+        trainer._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
