@@ -130,7 +130,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 512
+    # bounded sample: keep the whole --steps/--warmup run to a few minutes of CPU time (~5.5 s per 512 rays on 8 cores)
+    n_steps = max(1, args.steps) + max(0, args.warmup)
+    sample = int(min(512, max(64, (512 * 20 // n_steps) // 64 * 64)))
     rate, cores, t = cpu_train_step_rate(sample, max(1, args.steps), max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,

@@ -283,9 +283,9 @@ extern "C" {
 int rn_composite_fwd(const float* rgb, const float* sigma, const float* raw4, const float* z, const float* rd,
                      const float* noise, int64_t B, int S, int white, float t_min, float* rgb_map, float* depth_map,
                      float* acc_map, float* weights, rn_stream_t stream) {
+  if (B == 0) return RN_OK;
   RN_REQUIRE(z && rd && rgb_map && depth_map && acc_map && weights && B >= 0 && S >= 1);
   RN_REQUIRE((raw4 != nullptr) != (rgb != nullptr && sigma != nullptr));
-  if (B == 0) return RN_OK;
   const int grid = (int)(ceil_div(B, kCompWarps) < (int64_t)num_sms() * 8 ? ceil_div(B, kCompWarps) : (int64_t)num_sms() * 8);
   if (raw4)
     composite_fwd_kernel<true><<<grid, kCompWarps * 32, 0, (cudaStream_t)stream>>>(
@@ -301,10 +301,10 @@ int rn_composite_bwd(const float* rgb, const float* sigma, const float* raw4, co
                      const float* noise, int64_t B, int S, int white, const float* g_map, const float* g_depth,
                      const float* g_acc, const float* g_w, float* d_rgb, float* d_sigma, float* d_raw4, float* d_rd,
                      rn_stream_t stream) {
+  if (B == 0) return RN_OK;
   RN_REQUIRE(z && rd && g_map && B >= 0 && S >= 1);
   RN_REQUIRE((raw4 != nullptr) != (rgb != nullptr && sigma != nullptr));
   RN_REQUIRE(raw4 ? (d_raw4 != nullptr) : (d_rgb != nullptr && d_sigma != nullptr));
-  if (B == 0) return RN_OK;
   const int rounds = (S + 31) / 32;
   const int grid = (int)(ceil_div(B, kCompWarps) < (int64_t)num_sms() * 4 ? ceil_div(B, kCompWarps) : (int64_t)num_sms() * 4);
   int rc;

@@ -383,32 +383,32 @@ int rn_mlp_pack_weights(const float* const* params_host, void* packed, rn_stream
 }
 
 int rn_head_act_fwd(const float* raw4, int64_t M, float* rgb, float* sigma, rn_stream_t stream) {
-  RN_REQUIRE(raw4 && rgb && sigma && M >= 0);
   if (M == 0) return RN_OK;
+  RN_REQUIRE(raw4 && rgb && sigma && M >= 0);
   head_act_fwd_kernel<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)raw4, M, rgb, sigma);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
 
 int rn_head_act_bwd(const float* raw4, int64_t M, const float* g_rgb, const float* g_sigma, float* g_raw4, rn_stream_t stream) {
-  RN_REQUIRE(raw4 && g_raw4 && M >= 0);
   if (M == 0) return RN_OK;
+  RN_REQUIRE(raw4 && g_raw4 && M >= 0);
   head_act_bwd_kernel<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)raw4, M, g_rgb, g_sigma, (float4*)g_raw4);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
 
 int rn_posenc_fwd(const float* x, int64_t n, int C, int L, float* out, rn_stream_t stream) {
-  RN_REQUIRE(x && out && n >= 0 && C >= 1 && L >= 0 && L <= 30);
   if (n == 0) return RN_OK;
+  RN_REQUIRE(x && out && n >= 0 && C >= 1 && L >= 0 && L <= 30);
   posenc_fwd_kernel<<<grid_for(n * C, 256), 256, 0, (cudaStream_t)stream>>>(x, n, C, L, out);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
 
 int rn_posenc_bwd(const float* x, int64_t n, int C, int L, const float* g_out, float* g_x, rn_stream_t stream) {
-  RN_REQUIRE(x && g_out && g_x && n >= 0 && C >= 1 && L >= 0 && L <= 30);
   if (n == 0) return RN_OK;
+  RN_REQUIRE(x && g_out && g_x && n >= 0 && C >= 1 && L >= 0 && L <= 30);
   posenc_bwd_kernel<<<grid_for(n * C, 256), 256, 0, (cudaStream_t)stream>>>(x, n, C, L, g_out, g_x);
   RN_LAUNCH_CHECK();
   return RN_OK;

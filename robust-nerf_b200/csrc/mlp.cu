@@ -195,8 +195,8 @@ size_t rn_mlp_workspace_bytes(int64_t M, int training) { return M > 0 ? workspac
 
 int rn_mlp_fwd(const void* packed, const float* pts, const float* dirs, int64_t M, int dir_group, void* workspace,
                int training, float* raw_out, rn_stream_t stream) {
-  RN_REQUIRE(packed && pts && dirs && workspace && raw_out && M >= 0 && dir_group >= 1 && M % dir_group == 0);
   if (M == 0) return RN_OK;
+  RN_REQUIRE(packed && pts && dirs && workspace && raw_out && M >= 0 && dir_group >= 1 && M % dir_group == 0);
   RN_TRY(check_arch());
   return mlp_forward(packed, pts, dirs, M, dir_group, workspace, training, raw_out, (cudaStream_t)stream);
 }

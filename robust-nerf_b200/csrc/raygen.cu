@@ -348,8 +348,8 @@ extern "C" {
 
 int rn_se3_poses_fwd(const float* P0, const float* rot, const float* trans, const int64_t* idx, int n, int n_total,
                      int learn_r, int learn_t, float* out, rn_stream_t stream) {
-  RN_REQUIRE(P0 && rot && trans && out && n >= 0 && n_total > 0);
   if (n == 0) return RN_OK;
+  RN_REQUIRE(P0 && rot && trans && out && n >= 0 && n_total > 0);
   se3_poses_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P0, rot, trans, idx, n, learn_r, learn_t, out);
   RN_LAUNCH_CHECK();
   return RN_OK;
@@ -357,8 +357,8 @@ int rn_se3_poses_fwd(const float* P0, const float* rot, const float* trans, cons
 
 int rn_se3_poses_bwd(const float* P0, const float* rot, const int64_t* idx, int n, int n_total, const float* gP,
                      float* d_rot, float* d_trans, rn_stream_t stream) {
-  RN_REQUIRE(P0 && rot && gP && n >= 0 && n_total > 0);
   if (n == 0) return RN_OK;
+  RN_REQUIRE(P0 && rot && gP && n >= 0 && n_total > 0);
   se3_poses_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P0, rot, idx, n, gP, d_rot, d_trans);
   RN_LAUNCH_CHECK();
   return RN_OK;
@@ -372,8 +372,8 @@ int rn_ray_directions(int H, int W, float focal, float cx, float cy, float* dirs
 }
 
 int rn_get_rays(const float* dirs, const float* c2w, int64_t n, float* ro, float* rd, rn_stream_t stream) {
-  RN_REQUIRE(dirs && c2w && ro && rd && n >= 0);
   if (n == 0) return RN_OK;
+  RN_REQUIRE(dirs && c2w && ro && rd && n >= 0);
   get_rays_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dirs, c2w, n, ro, rd);
   RN_LAUNCH_CHECK();
   return RN_OK;
@@ -389,8 +389,8 @@ int rn_get_rays_bwd(const float* dirs, const float* c2w, int64_t n, const float*
 
 int rn_raygen_fwd(const int64_t* img, const float* uv, int64_t B, const float* poses, int n_poses, int H, int W,
                   float focal, float cx, float cy, float* ro, float* rd, rn_stream_t stream) {
-  RN_REQUIRE(img && uv && poses && ro && rd && B >= 0 && n_poses > 0 && H > 0 && W > 0);
   if (B == 0) return RN_OK;
+  RN_REQUIRE(img && uv && poses && ro && rd && B >= 0 && n_poses > 0 && H > 0 && W > 0);
   raygen_fwd_kernel<false><<<grid_for(B, 128), 128, 0, (cudaStream_t)stream>>>(img, uv, B, poses, nullptr, nullptr, 0, 0,
                                                                                 focal, cx, cy, ro, rd);
   RN_LAUNCH_CHECK();
@@ -410,8 +410,8 @@ int rn_raygen_bwd(const int64_t* img, const float* uv, int64_t B, const float* p
 int rn_raygen_se3_fwd(const int64_t* img, const float* uv, int64_t B, const float* P0, const float* rot,
                       const float* trans, int n_poses, int learn_r, int learn_t, int H, int W, float focal, float cx,
                       float cy, float* ro, float* rd, rn_stream_t stream) {
-  RN_REQUIRE(img && uv && P0 && rot && trans && ro && rd && B >= 0 && n_poses > 0 && H > 0 && W > 0);
   if (B == 0) return RN_OK;
+  RN_REQUIRE(img && uv && P0 && rot && trans && ro && rd && B >= 0 && n_poses > 0 && H > 0 && W > 0);
   raygen_fwd_kernel<true><<<grid_for(B, 128), 128, 0, (cudaStream_t)stream>>>(img, uv, B, P0, rot, trans, learn_r, learn_t,
                                                                                focal, cx, cy, ro, rd);
   RN_LAUNCH_CHECK();
@@ -430,8 +430,8 @@ int rn_raygen_se3_bwd(const int64_t* img, const float* uv, int64_t B, const floa
 
 int rn_pixel_gather(const int64_t* flat, int64_t B, int H, int W, const float* images, int64_t* img_out, float* uv_out,
                     float* rgb_out, rn_stream_t stream) {
-  RN_REQUIRE(flat && img_out && uv_out && B >= 0 && H > 0 && W > 0);
   if (B == 0) return RN_OK;
+  RN_REQUIRE(flat && img_out && uv_out && B >= 0 && H > 0 && W > 0);
   pixel_gather_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(flat, B, H, W, images, img_out, uv_out, rgb_out);
   RN_LAUNCH_CHECK();
   return RN_OK;

@@ -335,24 +335,24 @@ extern "C" {
 
 int rn_stratified_fwd(const float* ro, const float* rd, int64_t B, const float* zb, int Nc, const float* t_rand,
                       float* z_out, float* pts, rn_stream_t stream) {
-  RN_REQUIRE(zb && z_out && B >= 0 && Nc >= 1 && (!pts || (ro && rd)));
   if (B == 0) return RN_OK;
+  RN_REQUIRE(zb && z_out && B >= 0 && Nc >= 1 && (!pts || (ro && rd)));
   stratified_kernel<<<grid_for(B * Nc, 256), 256, 0, (cudaStream_t)stream>>>(ro, rd, B, zb, Nc, t_rand, z_out, pts);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
 
 int rn_points_fwd(const float* ro, const float* rd, const float* z, int64_t B, int S, float* pts, rn_stream_t stream) {
-  RN_REQUIRE(ro && rd && z && pts && B >= 0 && S >= 1);
   if (B == 0) return RN_OK;
+  RN_REQUIRE(ro && rd && z && pts && B >= 0 && S >= 1);
   points_fwd_kernel<<<grid_for(B * S, 256), 256, 0, (cudaStream_t)stream>>>(ro, rd, z, B, S, pts);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
 
 int rn_points_bwd(const float* g_pts, const float* z, int64_t B, int S, float* g_o, float* g_d, rn_stream_t stream) {
-  RN_REQUIRE(g_pts && z && g_o && g_d && B >= 0 && S >= 1);
   if (B == 0) return RN_OK;
+  RN_REQUIRE(g_pts && z && g_o && g_d && B >= 0 && S >= 1);
   points_bwd_kernel<<<grid_for(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(g_pts, z, B, S, g_o, g_d);
   RN_LAUNCH_CHECK();
   return RN_OK;
@@ -360,8 +360,8 @@ int rn_points_bwd(const float* g_pts, const float* z, int64_t B, int S, float* g
 
 int rn_sample_pdf_fwd(const float* bins, const float* weights, int64_t B, int nb, const float* u, int64_t u_stride,
                       int Nf, float* samples, int64_t* inds_out, rn_stream_t stream) {
-  RN_REQUIRE(bins && weights && u && samples && B >= 0 && nb >= 2 && Nf >= 1 && nb <= 4096);
   if (B == 0) return RN_OK;
+  RN_REQUIRE(bins && weights && u && samples && B >= 0 && nb >= 2 && Nf >= 1 && nb <= 4096);
   const size_t smem = (size_t)kWarpsPerCta * 3 * nb * sizeof(float);
   if (smem > 48 * 1024)
     RN_CUDA_CHECK(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -375,8 +375,8 @@ int rn_sample_pdf_fwd(const float* bins, const float* weights, int64_t B, int nb
 int rn_sample_hierarchical_fwd(const float* ro, const float* rd, const float* zc, const float* weights, int64_t B, int Nc,
                                const float* u, int64_t u_stride, int Nf, float* z_all, float* pts, int64_t* inds_out,
                                rn_stream_t stream) {
-  RN_REQUIRE(zc && weights && u && z_all && B >= 0 && Nc >= 3 && Nf >= 1 && (!pts || (ro && rd)));
   if (B == 0) return RN_OK;
+  RN_REQUIRE(zc && weights && u && z_all && B >= 0 && Nc >= 3 && Nf >= 1 && (!pts || (ro && rd)));
   cudaStream_t st = (cudaStream_t)stream;
   if (Nf <= 32) return launch_hier<1>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts, inds_out, st);
   if (Nf <= 64) return launch_hier<2>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts, inds_out, st);

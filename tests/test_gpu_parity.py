@@ -715,3 +715,47 @@ def test_trainer_cuda_graph_step(rn, dev):
     assert losses["graph"][-1] < losses["graph"][0]
     np.testing.assert_allclose(losses["graph"][0], losses["eager"][0], rtol=0.05)      # same weights, different draws
     np.testing.assert_allclose(losses["graph"][-1], losses["eager"][-1], rtol=0.25)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: empty and ragged inputs, tile-sharded rendering
+# ------------------------------------------------------------------------------------------------
+def test_empty_and_ragged_inputs(rn, dev):
+    nc, nf = _two_nets(rn, dev, sharpen=False)
+    cfg = rn.RenderConfig(num_samples=7, num_samples_fine=5)          # odd, tiny sample counts
+    with torch.no_grad():
+        e = rn.render_rays(nc, nf, torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev), cfg, is_train=False)
+        assert e["rgb_fine"].shape == (0, 3) and e["depth_fine"].shape == (0,)
+        rgb, sigma = nc(torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev))
+        assert rgb.shape == (0, 3) and sigma.shape == (0, 1)
+        ro = torch.tensor([[0.0, 0.0, 4.0]], device=dev)
+        rd = torch.tensor([[0.0, 0.0, -1.0]], device=dev)
+        one = rn.render_rays(nc, nf, ro, rd, cfg, is_train=False)       # a single ray
+        wc, wf = O.make_weights(41), O.make_weights(42)
+        ref = O.render_rays(wc, wf, N(ro), N(rd), O.RenderConfig(num_samples=7, num_samples_fine=5), is_train=False)
+        assert np.abs(N(one["rgb_fine"]) - ref["rgb_fine"]).max() < 1e-2
+        assert one["acc_fine"].shape == (1,)
+    out = rn.raw2outputs(torch.rand(0, 5, 3, device=dev), torch.rand(0, 5, 1, device=dev), torch.rand(0, 5, device=dev),
+                         torch.rand(0, 3, device=dev))
+    assert out["rgb_map"].shape == (0, 3) and out["weights"].shape == (0, 5)
+    pts, z = rn.sample_along_rays(torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev), 2.0, 6.0, 8)
+    assert pts.shape == (0, 8, 3) and z.shape == (0, 8)
+
+
+def test_render_views_tile_sharded(rn, dev):
+    """Tile-sharded test-view rendering (config 4): the union of the ranks' tiles equals the single-rank
+    render, every ray is rendered exactly once, no collective involved."""
+    nc, nf = _two_nets(rn, dev)
+    poses = rn.hemisphere_poses(2, seed=1, device=dev)
+    H = W = 48
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    cfg = rn.RenderConfig()
+    full = rn.render_views_sharded(nc, nf, poses, H, W, focal, cfg, tile_rays=500, rank=0, world=1)
+    assert full["rays_rendered"] == 2 * H * W
+    parts = [rn.render_views_sharded(nc, nf, poses, H, W, focal, cfg, tile_rays=500, rank=r, world=3) for r in range(3)]
+    assert sum(p["rays_rendered"] for p in parts) == 2 * H * W
+    union = sum(p["rgb"] for p in parts)                                  # disjoint tiles, zeros elsewhere
+    assert (union - full["rgb"]).abs().max().item() < 1e-5
+    img = rn.render_image_with_pose(nc, nf, poses[0], H, W, focal, cfg, chunk_size=700)
+    assert img["rgb"].shape == (H, W, 3) and img["depth"].shape == (H, W)
+    assert (img["rgb"].reshape(-1, 3) - full["rgb"][0]).abs().max().item() < 1e-5
