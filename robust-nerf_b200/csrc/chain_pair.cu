@@ -1,0 +1,422 @@
+// chain_pair.cu -- the NeRF MLP forward (noisy_src/model.py:145-196) as ONE persistent launch per network in which the
+// activations never leave the SM between layers.
+//
+// A pair of CTAs (cluster of 2 on one TPC) pushes two "pair tiles" of 256 points (128 rows per CTA) through all ten GEMM
+// layers.  Per CTA and tile slot a 64 KiB shared-memory buffer holds the current 128 x 256 bf16 activation in the
+// SWIZZLE_128B K-major layout the tensor core reads: layer l's epilogue converts the fp32 accumulator (TMEM) to bf16
+// and writes it IN PLACE over layer l-1's activation (whose MMAs have completed), and layer l+1's MMAs read it straight
+// from there -- no TMA load, no L2 round trip, no staging copy.  In training the same buffer is also the source of the
+// TMA store that keeps the activation for the backward pass; in inference nothing but raw[M,4] is written at all.
+// The skip concat [x_enc | h] and the view concat [features | d_enc] are extra 64-wide K chunks in a 16 KiB side buffer
+// (TMA-loaded).  MMAs are tcgen05.mma.cta_group::2 (M = 256 per pair): each CTA streams only HALF of every weight chunk
+// (16 KiB instead of 32), which halves the weight traffic through shared memory and makes a 4-deep ring fit.
+// The two tile slots ping-pong: slot X's MMAs run while slot Y's epilogue drains, so the tensor pipe is busy as long as
+// an epilogue (8 warps) is not slower than a layer's MMAs.
+//
+// Shared-memory traffic per 128 x 256 x 256 tile-layer and SM: 64 KiB weight writes + 64 KiB weight reads + 64 KiB
+// activation reads + 64 KiB activation writes (+ 64 KiB store reads in training) = 2048-2560 cycles at 128 B/clk, i.e.
+// at the 2048-cycle MMA floor -- the per-layer kernel moves 512 KiB (gemm_tcgen05.cu, profiles/r01_chain_experiments.md).
+//
+// Warp roles (352 threads): 0 = TMA producer (weights + side chunks), 1 = MMA issuer (pair leader only) + TMEM owner,
+// 2..9 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4), 10 = TMA store warp (training).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "gemm.h"
+#include "mlp_layout.h"
+#include <cuda_bf16.h>
+
+namespace rn {
+
+using namespace ptx;
+
+int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer);
+void prof_begin(int mode, cudaStream_t st, int* slot);
+void prof_end(int slot, cudaStream_t st);
+extern double g_prof_next_flops;
+
+constexpr int kPairThreads = 352;         // 11 warps: 65536 / 352 = 186 registers per thread, no spills
+constexpr int kPairMaxLayers = 12;
+constexpr int kPairMaxChunks = 8;
+constexpr int kChunkBytes = 16384;              // [128 rows][64 bf16], SWIZZLE_128B
+constexpr int kActBytes = 4 * kChunkBytes;      // one 128 x 256 activation
+constexpr int kAuxBytes = kChunkBytes;
+constexpr int kBStageBytes = 16384;             // half of a [256][64] weight chunk
+constexpr int kNBStages = 4;
+constexpr int kPairMisc = 2048;                 // head exchange [3][128] fp32 + barriers
+constexpr int kPairSmem = 2 * kActBytes + 2 * kAuxBytes + kNBStages * kBStageBytes + kPairMisc + 1024 /*alignment*/;
+static_assert(kPairSmem <= 232448, "pair chain kernel exceeds the 227 KiB shared-memory limit");
+
+struct PairLayer {
+  int n;                       // output columns: 256 or 128
+  int k_chunks;                // 64-wide K chunks of the A operand
+  int8_t a_src[kPairMaxChunks];   // per chunk: 0..3 = activation chunk, 4 = side buffer
+  int aux_load;                // 0, or 1 + index of the side tensor map loaded before this layer
+  int aux_release;             // the side buffer is free again once this layer's MMAs completed
+  int relu, heads, head_col;
+  int bias_off, head_w_off, head_b_off;   // float offsets into the fp32 constants
+  int store;                   // training: TMA-store the output tile through tmD
+  uint32_t* mask_out;          // packed ReLU mask [M][8] words, or null
+};
+// measurement knobs, compiled in only with -DRN_EXPERIMENTS (results are WRONG when any bit is set):
+// bit 0: no weight loads   bit 1: no TMA stores   bit 2: no side-chunk loads   bit 3: epilogue reads TMEM but skips the math
+// bit 4: epilogue does not even read TMEM
+#ifdef RN_EXPERIMENTS
+extern int g_chain_dbg;
+#define RN_PDBG(p, bit) ((p).dbg & (bit))
+#else
+#define RN_PDBG(p, bit) (0)
+#endif
+struct PairParams {
+  int dbg;
+  CUtensorMap tmB[kPairMaxLayers], tmD[kPairMaxLayers], tmAux[2];
+  PairLayer L[kPairMaxLayers];
+  int n_layers, n_ptiles;      // pair tiles of 256 rows
+  int64_t m_rows;
+  const float* consts;
+  float* raw;
+};
+
+// Biases and fp32 head weights of the network being evaluated (layout::kF32Elems floats), copied device-to-device on the
+// launching stream before each launch.  Every lane of an epilogue warp needs the SAME bias values: read through the
+// constant cache they cost no LSU/L1 cycles (a uniform LDG.128 per 4 columns made the load/store unit -- shared with the
+// tensor core's operand reads -- the bottleneck of the epilogue, profiles/r01_pair_experiments.md).
+__constant__ float c_pair_consts[3328];
+static_assert(layout::kF32Elems <= 3328, "constant staging buffer too small");
+
+// NG groups of 32 accumulator columns of one row: TMEM -> bias/ReLU -> bf16 -> in-place activation tile (+ mask, heads)
+template <int NG, int HEADS, bool WMASK>
+__device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int g0, int bias_off, int head_w_off,
+                                              int n, float relu_lo, uint32_t (&mb)[4], float& h0, float& h1, float& h2) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const int G = g0 + g;                      // 32-column group index within the layer output
+    uint32_t v[32];
+    tmem_ld_x32(t_addr + g * 32, v);
+    tmem_ld_wait();
+    uint8_t* box = s_tile + (G >> 1) * kChunkBytes + row * 128;
+    uint32_t outbits = 0u;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int lchunk = (G & 1) * 4 + cc;
+      uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
+      const int j0 = G * 32 + cc * 8;
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[cc * 8 + e]) + c_pair_consts[bias_off + j0 + e], relu_lo);
+      if (WMASK) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << (cc * 8 + e)) : 0u;
+      }
+      uint32_t packed[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 pk = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+        packed[e] = *reinterpret_cast<uint32_t*>(&pk);
+      }
+      if (HEADS > 0) {
+        // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation, as the per-layer kernel does
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xFFFF0000u);
+          const int j = j0 + 2 * e;
+          h0 = fmaf(r0, c_pair_consts[head_w_off + j], h0); h0 = fmaf(r1, c_pair_consts[head_w_off + j + 1], h0);
+          if (HEADS == 3) {
+            h1 = fmaf(r0, c_pair_consts[head_w_off + n + j], h1); h1 = fmaf(r1, c_pair_consts[head_w_off + n + j + 1], h1);
+            h2 = fmaf(r0, c_pair_consts[head_w_off + 2 * n + j], h2); h2 = fmaf(r1, c_pair_consts[head_w_off + 2 * n + j + 1], h2);
+          }
+        }
+      }
+      *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    mb[g] = outbits;
+  }
+}
+
+template <bool TRAIN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_act = smem;                                   // [2 slots][4 chunks][16 KiB]
+  uint8_t* s_aux = smem + 2 * kActBytes;                   // [2 slots][16 KiB]
+  uint8_t* s_b = s_aux + 2 * kAuxBytes;                    // [4 stages][16 KiB]
+  float* s_hx = reinterpret_cast<float*>(s_b + kNBStages * kBStageBytes);   // [3][128] head partials of column half 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_hx + 3 * 128);
+  uint64_t* full_b = bars;               // [4]  leader: weight chunk landed in BOTH CTAs
+  uint64_t* empty_b = bars + 4;          // [4]  each CTA: stage consumed (multicast commit)
+  uint64_t* aux_full = bars + 8;         // [2]  leader
+  uint64_t* aux_empty = bars + 10;       // [2]  each CTA (multicast commit)
+  uint64_t* act_ready = bars + 12;       // [2]  leader: 16 epilogue warps (both CTAs) wrote the tile and drained TMEM
+  uint64_t* tmem_full = bars + 14;       // [2]  each CTA (multicast commit)
+  uint64_t* staged = bars + 16;          // [2]  epilogue -> store warp (training)
+  uint64_t* store_done = bars + 18;      // [2]  store warp -> epilogue: the tile has been read out, overwrite allowed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int l = 0; l < p.n_layers; ++l) { prefetch_tmap(&p.tmB[l]); if (TRAIN) prefetch_tmap(&p.tmD[l]); }
+    prefetch_tmap(&p.tmAux[0]); prefetch_tmap(&p.tmAux[1]);
+    for (int i = 0; i < kNBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&aux_full[i], 1); mbar_init(&aux_empty[i], 1);
+      mbar_init(&act_ready[i], 16); mbar_init(&tmem_full[i], 1);
+      mbar_init(&staged[i], 8); mbar_init(&store_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // both CTAs' barriers exist before any remote arrive / multicast commit
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_groups = (p.n_ptiles + 1) >> 1;
+
+  if (warp == 0) {
+    // ---------------- TMA producer: this CTA's half of every weight chunk, and its rows of the side chunks ----------------
+    const uint32_t full_b_leader = mapa_u32(smem_u32(full_b), 0);
+    const uint32_t aux_full_leader = mapa_u32(smem_u32(aux_full), 0);
+    int s = 0; uint32_t ph = 0;
+    uint32_t aux_n0 = 0, aux_n1 = 0;
+    for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+      const int tiles_here = min(2, p.n_ptiles - grp * 2);
+      for (int l = 0; l < p.n_layers; ++l) {
+        const int n = p.L[l].n, k_chunks = p.L[l].k_chunks, aux_load = p.L[l].aux_load;
+        for (int slot = 0; slot < tiles_here; ++slot) {
+          if (aux_load) {
+            const uint32_t j = slot ? aux_n1++ : aux_n0++;
+            if (j > 0) mbar_wait(&aux_empty[slot], (j - 1) & 1u);
+            if (elect_one()) {
+              const int row0 = ((grp * 2 + slot) * 2 + (int)rank) * 128;
+              if RN_PDBG(p, 4) { if (rank == 0) mbar_arrive(&aux_full[slot]); }
+              else {
+                if (rank == 0) mbar_arrive_expect_tx(&aux_full[slot], 2 * kAuxBytes);
+                tma_load_2d_pair(s_aux + slot * kAuxBytes, &p.tmAux[aux_load - 1], aux_full_leader + slot * 8, 0, row0);
+              }
+            }
+            __syncwarp();
+          }
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(&empty_b[s], ph ^ 1);
+            if (elect_one()) {
+              if RN_PDBG(p, 1) { if (rank == 0) mbar_arrive(&full_b[s]); }
+              else {
+                if (rank == 0) mbar_arrive_expect_tx(&full_b[s], (uint32_t)n * 128u);
+                tma_load_2d_pair(s_b + s * kBStageBytes, &p.tmB[l], full_b_leader + s * 8, kc * 64, (int)rank * (n >> 1));
+              }
+            }
+            __syncwarp();
+            if (++s == kNBStages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (leader CTA; whole warp converged, one elected lane issues) ----------------
+    if (rank == 0) {
+      constexpr uint32_t kHi = desc_hi_sw128(1024);
+      const uint32_t act_lo0 = desc_lo_sw128(smem_u32(s_act), 16);
+      const uint32_t aux_lo0 = desc_lo_sw128(smem_u32(s_aux), 16);
+      const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_b), 16);
+      int s = 0; uint32_t ph = 0;
+      uint32_t it0 = 0, it1 = 0, aux_n0 = 0, aux_n1 = 0;
+      for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+        const int tiles_here = min(2, p.n_ptiles - grp * 2);
+        for (int l = 0; l < p.n_layers; ++l) {
+          const PairLayer& L = p.L[l];
+          const uint32_t idesc = make_idesc_bf16(256, L.n, 0, 0);
+          const int k_chunks = L.k_chunks;
+          for (int slot = 0; slot < tiles_here; ++slot) {
+            const uint32_t i = slot ? it1++ : it0++;
+            if (i > 0) mbar_wait_cluster(&act_ready[slot], (i - 1) & 1u);     // input tile written, accumulator drained
+            if (L.aux_load) {
+              const uint32_t j = slot ? aux_n1++ : aux_n0++;
+              mbar_wait(&aux_full[slot], j & 1u);
+            }
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            for (int kc = 0; kc < k_chunks; ++kc) {
+              mbar_wait(&full_b[s], ph);
+              tcgen05_fence_after();
+              if (elect_one()) {
+                const int src = L.a_src[kc];
+                const uint32_t al = (src == 4) ? aux_lo0 + slot * (kAuxBytes >> 4)
+                                               : act_lo0 + slot * (kActBytes >> 4) + src * (kChunkBytes >> 4);
+                const uint32_t bl = b_lo0 + s * (kBStageBytes >> 4);
+                umma_bf16_pair(d_tmem, pack64(al, kHi), pack64(bl, kHi), idesc, kc != 0);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16_pair(d_tmem, pack64(al + 2 * k, kHi), pack64(bl + 2 * k, kHi), idesc, 1u);
+                umma_commit_pair(&empty_b[s]);
+                if (kc == k_chunks - 1) {
+                  umma_commit_pair(&tmem_full[slot]);
+                  if (L.aux_release) umma_commit_pair(&aux_empty[slot]);
+                }
+              }
+              __syncwarp();
+              if (++s == kNBStages) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // ---------------- epilogue warps ----------------
+    const int q = warp & 3;                       // TMEM lane quarter
+    const int ch = (warp - 2) >> 2;               // column half of the layer output
+    const int row = q * 32 + lane;
+    const uint32_t act_ready_leader = mapa_u32(smem_u32(act_ready), 0);
+    uint32_t it0 = 0, it1 = 0;
+    for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+      const int tiles_here = min(2, p.n_ptiles - grp * 2);
+      for (int l = 0; l < p.n_layers; ++l) {
+        const PairLayer L = p.L[l];
+        const float relu_lo = L.relu ? 0.f : -3.0e38f;
+        for (int slot = 0; slot < tiles_here; ++slot) {
+          const uint32_t i = slot ? it1++ : it0++;
+          const int64_t gr = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128 + row;
+          const bool row_ok = gr < p.m_rows;
+          mbar_wait(&tmem_full[slot], i & 1u);
+          if (TRAIN && i > 0) mbar_wait(&store_done[slot], (i - 1) & 1u);   // the previous activation has been stored
+          tcgen05_fence_after();
+          uint8_t* s_tile = s_act + slot * kActBytes;
+          const uint32_t t_addr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + ch * (L.n >> 1);
+          float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+          uint32_t mb[4] = {0u, 0u, 0u, 0u};
+          if RN_PDBG(p, 16) { }
+          else if RN_PDBG(p, 8) {
+#pragma unroll 1
+            for (int g = 0; g < (L.n >> 6); ++g) { uint32_t v[32]; tmem_ld_x32(t_addr + g * 32, v); tmem_ld_wait(); if (v[0] == 0x7fc12345u) mb[0] ^= v[1]; }
+          }
+          else if (L.n == 256) {
+            if (L.heads == 1) pair_epilogue<4, 1, TRAIN>(t_addr, s_tile, row, ch * 4, L.bias_off, L.head_w_off, 256, relu_lo, mb, h0, h1, h2);
+            else pair_epilogue<4, 0, TRAIN>(t_addr, s_tile, row, ch * 4, L.bias_off, L.head_w_off, 256, relu_lo, mb, h0, h1, h2);
+          } else {
+            pair_epilogue<2, 3, false>(t_addr, s_tile, row, ch * 2, L.bias_off, L.head_w_off, 128, relu_lo, mb, h0, h1, h2);
+          }
+          tcgen05_fence_before();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(act_ready_leader + slot * 8);
+            if (TRAIN) mbar_arrive(&staged[slot]);
+          }
+          if (TRAIN && L.mask_out && row_ok)
+            *reinterpret_cast<uint4*>(L.mask_out + gr * 8 + ch * 4) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
+          if (L.heads > 0) {
+            // the two warps of a row quarter each hold half of the head dot products: combine through shared memory
+            if (ch == 1) {
+              s_hx[row] = h0;
+              if (L.heads == 3) { s_hx[128 + row] = h1; s_hx[256 + row] = h2; }
+            }
+            named_bar_sync(1 + q, 64);
+            if (ch == 0 && row_ok) {
+              const float* hb = c_pair_consts + L.head_b_off;
+              float* o = p.raw + gr * 4 + L.head_col;
+              o[0] = h0 + s_hx[row] + hb[0];
+              if (L.heads == 3) { o[1] = h1 + s_hx[128 + row] + hb[1]; o[2] = h2 + s_hx[256 + row] + hb[2]; }
+            }
+            named_bar_sync(1 + q, 64);
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ---------------- store warp (training): activation tiles -> global for the backward pass ----------------
+    if (TRAIN && lane == 0) {
+      uint32_t it0 = 0, it1 = 0;
+      for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+        const int tiles_here = min(2, p.n_ptiles - grp * 2);
+        for (int l = 0; l < p.n_layers; ++l) {
+          const int chunks = (p.L[l].store && !RN_PDBG(p, 2)) ? (p.L[l].n >> 6) : 0;
+          for (int slot = 0; slot < tiles_here; ++slot) {
+            const uint32_t i = slot ? it1++ : it0++;
+            const int row0 = ((grp * 2 + slot) * 2 + (int)rank) * 128;
+            mbar_wait(&staged[slot], i & 1u);
+            for (int c = 0; c < chunks; ++c)
+              tma_store_2d(&p.tmD[l], s_act + slot * kActBytes + c * kChunkBytes, c * 64, row0);
+            tma_store_commit();
+            tma_store_wait_read0();
+            mbar_arrive(&store_done[slot]);
+          }
+        }
+      }
+      tma_store_wait_all0();
+    }
+  }
+
+  // ---------------- teardown: neither CTA may leave (or free TMEM) while its peer still works ----------------
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+// Host launcher.  layers[l] uses the ChainLayerHost description of the per-layer chain (gemm.h); the pair kernel derives
+// where each K chunk of A lives: activation chunks for the part produced by the previous layer, the side buffer for
+// x_enc (first chunk of layers 0 and 5) and d_enc (last chunk of the view layer).
+int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const void* x_enc, int64_t ld_x,
+                           const void* d_enc, int64_t ld_d, const float* consts, float* raw, bool training, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != RN_OK) return rc;
+  RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kPairMaxLayers && M > 0 && consts && raw && x_enc && d_enc);
+  static PairParams p;
+  double flops = 0.0;
+  if ((rc = make_tmap(&p.tmAux[0], x_enc, 64, M, ld_x, 128)) != RN_OK) return rc;
+  if ((rc = make_tmap(&p.tmAux[1], d_enc, 64, M, ld_d, 128)) != RN_OK) return rc;
+  for (int l = 0; l < n_layers; ++l) {
+    const ChainLayerHost& h = layers[l];
+    RN_REQUIRE((h.n == 256 || h.n == 128) && (h.k == 64 || h.k == 256 || h.k == 320));
+    RN_REQUIRE(!(h.mask_out && h.n != 256) && !(h.n == 128 && h.heads != 3) && !(h.n == 256 && h.heads == 3));
+    if ((rc = make_tmap(&p.tmB[l], h.B, h.k, h.n, h.ldb, h.n / 2)) != RN_OK) return rc;
+    if (training && (rc = make_tmap(&p.tmD[l], h.D, h.n, M, h.ldd, 128)) != RN_OK) return rc;
+    PairLayer& L = p.L[l];
+    L = PairLayer{};
+    L.n = h.n; L.k_chunks = h.k / 64;
+    // aux_kind: 0 none, 1 = x_enc is the FIRST chunk (layers 0 and 5), 2 = d_enc is the LAST chunk (view layer)
+    int c = 0;
+    if (h.aux_kind == 1) L.a_src[c++] = 4;
+    for (int a = 0; c < L.k_chunks - (h.aux_kind == 2 ? 1 : 0); ++a) L.a_src[c++] = (int8_t)a;
+    if (h.aux_kind == 2) L.a_src[c++] = 4;
+    L.aux_load = h.aux_load; L.aux_release = h.aux_release;
+    L.relu = h.relu; L.heads = h.heads; L.head_col = h.head_col;
+    L.bias_off = h.bias_off; L.head_w_off = h.head_w_off; L.head_b_off = h.head_b_off;
+    L.store = training ? 1 : 0;
+    L.mask_out = training ? h.mask_out : nullptr;
+    flops += 2.0 * (double)M * h.n * h.k;
+  }
+#ifdef RN_EXPERIMENTS
+  p.dbg = g_chain_dbg;
+#else
+  p.dbg = 0;
+#endif
+  p.n_layers = n_layers;
+  p.n_ptiles = (int)ceil_div(M, 256);
+  p.m_rows = M; p.consts = consts; p.raw = raw;
+  static bool configured = false;
+  if (!configured) {
+    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+    configured = true;
+  }
+  RN_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pair_consts, consts, layout::kF32Elems * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
+  const int n_groups = (p.n_ptiles + 1) / 2;
+  const int max_clusters = num_sms() / 2;
+  const int grid = 2 * (n_groups < max_clusters ? n_groups : max_clusters);
+  g_prof_next_flops = flops;
+  int slot;
+  prof_begin(0 /*MODE_NT*/, st, &slot);
+  if (training) mlp_chain_pair_kernel<true><<<grid, kPairThreads, kPairSmem, st>>>(p);
+  else mlp_chain_pair_kernel<false><<<grid, kPairThreads, kPairSmem, st>>>(p);
+  prof_end(slot, st);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+}  // namespace rn

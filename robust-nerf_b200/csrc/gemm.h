@@ -23,7 +23,12 @@ struct ChainLayerHost {
   const void* A; int64_t lda; const void* B; int64_t ldb; void* D; int64_t ldd;
   int k, n, relu, heads, head_col, bias_off, head_w_off, head_b_off, dep;
   uint32_t* mask_out;
+  // pair kernel only (chain_pair.cu): which K chunk of A is a side chunk (0 none, 1 = first chunk is x_enc, 2 = last chunk
+  // is d_enc), whether that side chunk is (re)loaded before this layer (1 = x_enc, 2 = d_enc) and released after it
+  int aux_kind, aux_load, aux_release;
 };
+int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const void* x_enc, int64_t ld_x,
+                           const void* d_enc, int64_t ld_d, const float* consts, float* raw, bool training, cudaStream_t st);
 int mlp_chain_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const float* consts, float* raw, bool wmask,
                       cudaStream_t st);
 

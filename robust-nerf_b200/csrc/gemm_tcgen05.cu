@@ -182,35 +182,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, MODE == MODE_NN ? 1 : 0);
-        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int acc = 0; uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
-          mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+      // ---------------- MMA issuer: the whole warp runs the loop converged, one elected lane issues ----------------
+      // (a divergent `if (lane == 0)` region makes the compiler wrap every uniform-datapath instruction in a lane loop and
+      // rebuild descriptors with 64-bit arithmetic: ~230-320 cycles per MMA instead of the 128-cycle floor)
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, 0, MODE == MODE_NN ? 1 : 0);
+      constexpr uint32_t kHiA = desc_hi_sw128(1024), kHiB = desc_hi_sw128(1024);
+      constexpr uint32_t kBStep = (MODE == MODE_NT) ? 2u : 128u;                  // 32 B (K-major) or 2048 B (MN-major) per k step
+      const uint32_t a_lo0 = desc_lo_sw128(smem_u32(s_a), 16);
+      const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_b), MODE == MODE_NT ? 16 : 8192);
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int acc = 0; uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < args.m_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < args.k_chunks; ++kc) {
+          mbar_wait(&full_b[sb], phb);
+          mbar_wait(&full_a[sa], pha);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int kc = 0; kc < args.k_chunks; ++kc) {
-            mbar_wait(&full_b[sb], phb);
-            mbar_wait(&full_a[sa], pha);
-            tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(s_a + sa * kABytes);
-            const uint32_t b_addr = smem_u32(s_b + sb * Cfg::kBBytes);
+          if (elect_one()) {
+            const uint32_t al = a_lo0 + sa * (kABytes >> 4), bl = b_lo0 + sb * (Cfg::kBBytes >> 4);
             const int krem = args.k_total - kc * kBlockK;
-            const int ksteps = krem >= kBlockK ? 4 : (krem + 15) / 16;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-              const uint64_t bdesc = (MODE == MODE_NT) ? make_smem_desc_sw128(b_addr + k * 32, 16, 1024)
-                                                      : make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
-            }
+            umma_bf16(d_tmem, pack64(al, kHiA), pack64(bl, kHiB), idesc, kc != 0);
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+              if (krem > k * 16) umma_bf16(d_tmem, pack64(al + 2 * k, kHiA), pack64(bl + kBStep * k, kHiB), idesc, 1u);
             umma_commit(&empty_a[sa]);
             umma_commit(&empty_b[sb]);
             if (kc == args.k_chunks - 1) umma_commit(&tmem_full[acc]);
-            if (++sa == NA) { sa = 0; pha ^= 1; }
-            if (++sb == NB) { sb = 0; phb ^= 1; }
           }
-          acc ^= 1; if (acc == 0) acc_ph ^= 1;
+          __syncwarp();
+          if (++sa == NA) { sa = 0; pha ^= 1; }
+          if (++sb == NB) { sb = 0; phb ^= 1; }
         }
+        acc ^= 1; if (acc == 0) acc_ph ^= 1;
       }
     } else {
       // ---------------- epilogue warps ----------------
@@ -357,32 +360,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN > 256 ? 256 : BN, 1, 1);
-        constexpr uint32_t idesc2 = make_idesc_bf16(kBlockM, BN > 256 ? BN - 256 : 16, 1, 1);
-        constexpr uint32_t idesc1 = make_idesc_bf16(kBlockM, 16, 1, 1);
-        const uint32_t ones_addr = smem_u32(s_staging);
-        int s = 0; uint32_t ph = 0;
-        for (int kc = c0; kc < c1; ++kc) {
-          mbar_wait(&full_a[s], ph);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(s_a + s * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN > 256 ? 256 : BN, 1, 1);
+      constexpr uint32_t idesc2 = make_idesc_bf16(kBlockM, BN > 256 ? BN - 256 : 16, 1, 1);
+      constexpr uint32_t idesc1 = make_idesc_bf16(kBlockM, 16, 1, 1);
+      constexpr uint32_t kHi = desc_hi_sw128(1024);
+      const uint32_t a_lo0 = desc_lo_sw128(smem_u32(s_a), 8192);
+      const uint32_t o_lo = desc_lo_sw128(smem_u32(s_staging), 8192);
+      int s = 0; uint32_t ph = 0;
+      for (int kc = c0; kc < c1; ++kc) {
+        mbar_wait(&full_a[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t al = a_lo0 + s * (Cfg::kStageBytes >> 4), bl = al + (kABytes >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
-            const uint64_t odesc = make_smem_desc_sw128(ones_addr, 8192, 1024);
-            const uint32_t accum = (kc != c0 || k != 0);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
+            const uint32_t accum = (k != 0) ? 1u : (uint32_t)(kc != c0);
+            const uint64_t adesc = pack64(al + k * 128, kHi);
+            umma_bf16(tmem_base, adesc, pack64(bl + k * 128, kHi), idesc, accum);
             if (BN > 256)                                                 // columns 256.. : a second, narrower MMA
-              umma_bf16(tmem_base + 256, adesc, make_smem_desc_sw128(b_addr + 4 * 8192 + k * 2048, 8192, 1024), idesc2, accum);
-            umma_bf16(tmem_base + BN, adesc, odesc, idesc1, accum);      // column sums of A (bias gradient)
+              umma_bf16(tmem_base + 256, adesc, pack64(bl + 4 * 512 + k * 128, kHi), idesc2, accum);
+            umma_bf16(tmem_base + BN, adesc, pack64(o_lo, kHi), idesc1, accum);      // column sums of A (bias gradient)
           }
           umma_commit(&empty_a[s]);
-          if (++s == NS) { s = 0; ph ^= 1; }
+          if (kc == c1 - 1) umma_commit(&tmem_full[0]);
         }
-        umma_commit(&tmem_full[0]);
+        __syncwarp();
+        if (++s == NS) { s = 0; ph ^= 1; }
       }
     } else if (warp < 6) {
       const int q = warp & 3;
@@ -490,7 +493,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor [outer][inner] with leading dimension ld (elements), box [box_outer][64], SWIZZLE_128B
-static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return RN_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) != 0 || inner == 0 || outer == 0) return RN_ERR_INVALID_ARG;
@@ -510,9 +513,9 @@ struct ProfRec { cudaEvent_t a, b; int mode; double flops; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
-static double g_prof_next_flops = 0.0;
+double g_prof_next_flops = 0.0;
 
-static void prof_begin(int mode, cudaStream_t st, int* slot) {
+void prof_begin(int mode, cudaStream_t st, int* slot) {
   *slot = -1;
   if (!g_prof_on || g_prof.size() >= 16384) return;
   std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -522,7 +525,7 @@ static void prof_begin(int mode, cudaStream_t st, int* slot) {
   g_prof.push_back({ev.first, ev.second, mode, g_prof_next_flops});
   *slot = (int)g_prof.size() - 1;
 }
-static void prof_end(int slot, cudaStream_t st) {
+void prof_end(int slot, cudaStream_t st) {
   if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
 }
 
@@ -851,38 +854,41 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainParams p) {
           }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int acc = 0; uint32_t acc_ph = 0;
-      for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
-        for (int l = 0; l < p.n_layers; ++l) {
-          const uint32_t idesc = make_idesc_bf16(kBlockM, p.L[l].n, 0, 0);
-          for (int g = 0; g < G; ++g) {
-            if (grp * G + g >= p.m_tiles) break;
-            mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+    // ---------------- MMA issuer (whole warp converged, one elected lane issues; see gemm_kernel) ----------------
+    constexpr uint32_t kHi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo_sw128(smem_u32(s_a), 16);
+    const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_b), 16);
+    int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int acc = 0; uint32_t acc_ph = 0;
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+      for (int l = 0; l < p.n_layers; ++l) {
+        const uint32_t idesc = make_idesc_bf16(kBlockM, p.L[l].n, 0, 0);
+        const int k_chunks = p.L[l].k_chunks, k_total = p.L[l].k_total;
+        for (int g = 0; g < G; ++g) {
+          if (grp * G + g >= p.m_tiles) break;
+          mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(&full_b[sb], phb);
+            mbar_wait(&full_a[sa], pha);
             tcgen05_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 256;
-            for (int kc = 0; kc < p.L[l].k_chunks; ++kc) {
-              mbar_wait(&full_b[sb], phb);
-              mbar_wait(&full_a[sa], pha);
-              tcgen05_fence_after();
-              const uint32_t a_addr = smem_u32(s_a + sa * kABytes);
-              const uint32_t b_addr = smem_u32(s_b + sb * 32768);
-              const int krem = p.L[l].k_total - kc * kBlockK;
-              const int ksteps = krem >= kBlockK ? 4 : (krem + 15) / 16;
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
-                          make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (kc | k) != 0);
+            if (elect_one()) {
+              const uint32_t al = a_lo0 + sa * (kABytes >> 4), bl = b_lo0 + sb * (32768 >> 4);
+              const int krem = k_total - kc * kBlockK;
+              umma_bf16(d_tmem, pack64(al, kHi), pack64(bl, kHi), idesc, kc != 0);
+#pragma unroll
+              for (int k = 1; k < 4; ++k)
+                if (krem > k * 16) umma_bf16(d_tmem, pack64(al + 2 * k, kHi), pack64(bl + 2 * k, kHi), idesc, 1u);
               umma_commit(&empty_a[sa]);
               umma_commit(&empty_b[sb]);
-              if (kc == p.L[l].k_chunks - 1) umma_commit(&tmem_full[acc]);
-              if (++sa == kChainNA) { sa = 0; pha ^= 1; }
-              if (++sb == kChainNB) { sb = 0; phb ^= 1; }
+              if (kc == k_chunks - 1) umma_commit(&tmem_full[acc]);
             }
-            acc ^= 1; if (acc == 0) acc_ph ^= 1;
+            __syncwarp();
+            if (++sa == kChainNA) { sa = 0; pha ^= 1; }
+            if (++sb == kChainNB) { sb = 0; phb ^= 1; }
           }
+          acc ^= 1; if (acc == 0) acc_ph ^= 1;
         }
-    }
+      }
   } else if (warp == 7) {
     // ---------------- store warp: staged half tiles -> global, completion signalling ----------------
     // Completion is tracked lazily: after item i's stores are issued, wait until at most those bulk groups

@@ -69,7 +69,9 @@ static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimen
 extern int g_chain_dbg;
 #endif
 extern int g_chain_ring;
-int g_chain_fwd = 1;      // rn_set_flag(0, v): run the forward as one layer-chained persistent launch
+// rn_set_flag(0, v): 0 = one launch per layer, 1 = layer-chained persistent launch (activations round-trip through L2),
+// 2 = CTA-pair chain with shared-memory-resident activations (chain_pair.cu; default)
+int g_chain_fwd = 2;
 
 static int mlp_forward(const void* packed, const float* pts, const float* dirs, int64_t M, int group, void* ws,
                        int training, float* raw, cudaStream_t st) {
@@ -103,6 +105,12 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
     }
     L[8] = ChainLayerHost{H[7], 256, W + kWFS, 256, FD, 320, 256, 256, 0, 0, 0, (int)kBF, 0, 0, 1, nullptr};
     L[9] = ChainLayerHost{FD, 320, W + kWD, 320, HC, 128, 320, 128, 1, 3, 0, (int)kBD, (int)kWRgb, (int)kBRgb, 1, nullptr};
+    if (g_chain_fwd == 2) {
+      L[0].aux_kind = 1; L[0].aux_load = 1;
+      L[5].aux_kind = 1; L[5].aux_release = 1;
+      L[9].aux_kind = 2; L[9].aux_load = 2; L[9].aux_release = 1;
+      return mlp_chain_pair_forward(L, 10, M, XC, 320, FD + 256, 320, F, raw, training != 0, st);
+    }
     return mlp_chain_forward(L, 10, M, F, raw, training != 0, st);
   }
   RN_TRY(gemm_nt(XC, 320, W + kW0, 64, H[0], 256, M, 256, 64, F + kB0, 1, st, MB[0]));
@@ -183,7 +191,7 @@ using namespace rn;
 extern "C" {
 
 int rn_set_flag(int flag, int value) {
-  if (flag == 0) { g_chain_fwd = value != 0; return RN_OK; }
+  if (flag == 0) { g_chain_fwd = value; return RN_OK; }
 #ifdef RN_EXPERIMENTS
   if (flag == 1) { g_chain_dbg = value; return RN_OK; }
 #endif
