@@ -17,8 +17,11 @@
 // activation reads + 64 KiB activation writes (+ 64 KiB store reads in training) = 2048-2560 cycles at 128 B/clk, i.e.
 // at the 2048-cycle MMA floor -- the per-layer kernel moves 512 KiB (gemm_tcgen05.cu, profiles/r01_chain_experiments.md).
 //
-// Warp roles (352 threads): 0 = TMA producer (weights + side chunks), 1 = MMA issuer (pair leader only) + TMEM owner,
-// 2..9 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4), 10 = TMA store warp (training).
+// Warp roles (608 threads): 0 = TMA producer (weights + side chunks), 1 = MMA issuer (pair leader only) + TMEM owner,
+// 2..17 = epilogue (TMEM lane quarter = warp % 4, column quarter = (warp - 2) / 4), 18 = TMA store warp (training).
+// The epilogue is the pacing stage (profiles/r01_pair_experiments.md): sixteen warps (four per scheduler) hide the
+// TMEM-load and shared-store latencies, and the arithmetic is packed two columns per instruction (FADD2 for the bias,
+// F2FP to bf16x2, HMNMX2 for the ReLU; the mask bits come from the packed word with an add, a shift and a LOP3).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "gemm.h"
@@ -34,7 +37,7 @@ void prof_begin(int mode, cudaStream_t st, int* slot);
 void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
 
-constexpr int kPairThreads = 352;         // 11 warps: 65536 / 352 = 186 registers per thread, no spills
+constexpr int kPairThreads = 608;         // 19 warps
 constexpr int kPairMaxLayers = 12;
 constexpr int kPairMaxChunks = 8;
 constexpr int kChunkBytes = 16384;              // [128 rows][64 bf16], SWIZZLE_128B
@@ -42,7 +45,7 @@ constexpr int kActBytes = 4 * kChunkBytes;      // one 128 x 256 activation
 constexpr int kAuxBytes = kChunkBytes;
 constexpr int kBStageBytes = 16384;             // half of a [256][64] weight chunk
 constexpr int kNBStages = 4;
-constexpr int kPairMisc = 2048;                 // head exchange [3][128] fp32 + barriers
+constexpr int kPairMisc = 2048;                 // head partial sums [3][128] fp32 + barriers
 constexpr int kPairSmem = 2 * kActBytes + 2 * kAuxBytes + kNBStages * kBStageBytes + kPairMisc + 1024 /*alignment*/;
 static_assert(kPairSmem <= 232448, "pair chain kernel exceeds the 227 KiB shared-memory limit");
 
@@ -80,41 +83,52 @@ struct PairParams {
 // launching stream before each launch.  Every lane of an epilogue warp needs the SAME bias values: read through the
 // constant cache they cost no LSU/L1 cycles (a uniform LDG.128 per 4 columns made the load/store unit -- shared with the
 // tensor core's operand reads -- the bottleneck of the epilogue, profiles/r01_pair_experiments.md).
-__constant__ float c_pair_consts[3328];
+__constant__ float2 c_pair_consts2[1664];
+#define c_pair_consts (reinterpret_cast<const float*>(c_pair_consts2))
 static_assert(layout::kF32Elems <= 3328, "constant staging buffer too small");
 
-// NG groups of 32 accumulator columns of one row: TMEM -> bias/ReLU -> bf16 -> in-place activation tile (+ mask, heads)
-template <int NG, int HEADS, bool WMASK>
+__device__ __forceinline__ uint64_t fadd2(uint32_t a_lo, uint32_t a_hi, float2 b) {
+  uint64_t a, bb, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a_lo), "r"(a_hi));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(bb));
+  return r;
+}
+
+// NG groups of 32 accumulator columns of one row: TMEM -> bias (+ReLU) -> bf16 -> in-place activation tile (+ mask, heads).
+// G-th group of the layer output = columns 32G..32G+31; bias_off / head_w_off are float offsets into the constants.
+template <int NG, int HEADS, bool RELU, bool WMASK>
 __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int g0, int bias_off, int head_w_off,
-                                              int n, float relu_lo, uint32_t (&mb)[4], float& h0, float& h1, float& h2) {
+                                              int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2) {
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    const int G = g0 + g;                      // 32-column group index within the layer output
+    const int G = g0 + g;
     uint32_t v[32];
     tmem_ld_x32(t_addr + g * 32, v);
     tmem_ld_wait();
     uint8_t* box = s_tile + (G >> 1) * kChunkBytes + row * 128;
+    const int b2 = (bias_off >> 1) + G * 16;           // float2 index of this group's first bias pair
     uint32_t outbits = 0u;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       const int lchunk = (G & 1) * 4 + cc;
       uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
-      const int j0 = G * 32 + cc * 8;
-      float x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[cc * 8 + e]) + c_pair_consts[bias_off + j0 + e], relu_lo);
-      if (WMASK) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << (cc * 8 + e)) : 0u;
-      }
       uint32_t packed[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        __nv_bfloat162 pk = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+        const int i = cc * 4 + e;                       // column pair within the group
+        const uint64_t r = fadd2(v[2 * i], v[2 * i + 1], c_pair_consts2[b2 + i]);
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+        __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+        if (RELU) pk = __hmax2(pk, __float2bfloat162_rn(0.f));
         packed[e] = *reinterpret_cast<uint32_t*>(&pk);
+        // after the ReLU both halves are +0 or positive: adding 0x7FFF sets bit 15 / 31 exactly for the non-zero ones
+        if (WMASK) outbits |= ((packed[e] + 0x7FFF7FFFu) & 0x80008000u) >> i;
       }
       if (HEADS > 0) {
         // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation, as the per-layer kernel does
+        const int j0 = G * 32 + cc * 8;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xFFFF0000u);
@@ -146,7 +160,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
   uint64_t* empty_b = bars + 4;          // [4]  each CTA: stage consumed (multicast commit)
   uint64_t* aux_full = bars + 8;         // [2]  leader
   uint64_t* aux_empty = bars + 10;       // [2]  each CTA (multicast commit)
-  uint64_t* act_ready = bars + 12;       // [2]  leader: 16 epilogue warps (both CTAs) wrote the tile and drained TMEM
+  uint64_t* act_ready = bars + 12;       // [2]  leader: 32 epilogue warps (both CTAs) wrote the tile and drained TMEM
   uint64_t* tmem_full = bars + 14;       // [2]  each CTA (multicast commit)
   uint64_t* staged = bars + 16;          // [2]  epilogue -> store warp (training)
   uint64_t* store_done = bars + 18;      // [2]  store warp -> epilogue: the tile has been read out, overwrite allowed
@@ -164,8 +178,8 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     for (int i = 0; i < kNBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&aux_full[i], 1); mbar_init(&aux_empty[i], 1);
-      mbar_init(&act_ready[i], 16); mbar_init(&tmem_full[i], 1);
-      mbar_init(&staged[i], 8); mbar_init(&store_done[i], 1);
+      mbar_init(&act_ready[i], 32); mbar_init(&tmem_full[i], 1);
+      mbar_init(&staged[i], 16); mbar_init(&store_done[i], 1);
     }
     fence_mbar_init();
   }
@@ -263,10 +277,10 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
         }
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 18) {
     // ---------------- epilogue warps ----------------
     const int q = warp & 3;                       // TMEM lane quarter
-    const int ch = (warp - 2) >> 2;               // column half of the layer output
+    const int cq = (warp - 2) >> 2;               // column quarter of the layer output
     const int row = q * 32 + lane;
     const uint32_t act_ready_leader = mapa_u32(smem_u32(act_ready), 0);
     uint32_t it0 = 0, it1 = 0;
@@ -274,7 +288,6 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
       for (int l = 0; l < p.n_layers; ++l) {
         const PairLayer L = p.L[l];
-        const float relu_lo = L.relu ? 0.f : -3.0e38f;
         for (int slot = 0; slot < tiles_here; ++slot) {
           const uint32_t i = slot ? it1++ : it0++;
           const int64_t gr = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128 + row;
@@ -283,19 +296,20 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
           if (TRAIN && i > 0) mbar_wait(&store_done[slot], (i - 1) & 1u);   // the previous activation has been stored
           tcgen05_fence_after();
           uint8_t* s_tile = s_act + slot * kActBytes;
-          const uint32_t t_addr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + ch * (L.n >> 1);
+          const uint32_t t_addr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + cq * (L.n >> 2);
           float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-          uint32_t mb[4] = {0u, 0u, 0u, 0u};
+          uint32_t mb[2] = {0u, 0u};
           if RN_PDBG(p, 16) { }
           else if RN_PDBG(p, 8) {
 #pragma unroll 1
-            for (int g = 0; g < (L.n >> 6); ++g) { uint32_t v[32]; tmem_ld_x32(t_addr + g * 32, v); tmem_ld_wait(); if (v[0] == 0x7fc12345u) mb[0] ^= v[1]; }
+            for (int g = 0; g < (L.n >> 7); ++g) { uint32_t v[32]; tmem_ld_x32(t_addr + g * 32, v); tmem_ld_wait(); if (v[0] == 0x7fc12345u) mb[0] ^= v[1]; }
           }
           else if (L.n == 256) {
-            if (L.heads == 1) pair_epilogue<4, 1, TRAIN>(t_addr, s_tile, row, ch * 4, L.bias_off, L.head_w_off, 256, relu_lo, mb, h0, h1, h2);
-            else pair_epilogue<4, 0, TRAIN>(t_addr, s_tile, row, ch * 4, L.bias_off, L.head_w_off, 256, relu_lo, mb, h0, h1, h2);
+            if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2);
+            else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2);
+            else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2);
           } else {
-            pair_epilogue<2, 3, false>(t_addr, s_tile, row, ch * 2, L.bias_off, L.head_w_off, 128, relu_lo, mb, h0, h1, h2);
+            pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, L.bias_off, L.head_w_off, 128, mb, h0, h1, h2);
           }
           tcgen05_fence_before();
           fence_proxy_async_smem();
@@ -305,26 +319,34 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
             if (TRAIN) mbar_arrive(&staged[slot]);
           }
           if (TRAIN && L.mask_out && row_ok)
-            *reinterpret_cast<uint4*>(L.mask_out + gr * 8 + ch * 4) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
+            *reinterpret_cast<uint2*>(L.mask_out + gr * 8 + cq * 2) = make_uint2(mb[0], mb[1]);
           if (L.heads > 0) {
-            // the two warps of a row quarter each hold half of the head dot products: combine through shared memory
-            if (ch == 1) {
-              s_hx[row] = h0;
-              if (L.heads == 3) { s_hx[128 + row] = h1; s_hx[256 + row] = h2; }
+            // the four warps of a row quarter each hold a quarter of the head dot products: summed through shared memory
+            // in a fixed order (column quarter 3, 2, 1, 0) -> deterministic
+            const int nh = L.heads;
+#pragma unroll 1
+            for (int step = 3; step >= 1; --step) {
+              if (cq == step) {
+                s_hx[row] = (step == 3 ? 0.f : s_hx[row]) + h0;
+                if (nh == 3) {
+                  s_hx[128 + row] = (step == 3 ? 0.f : s_hx[128 + row]) + h1;
+                  s_hx[256 + row] = (step == 3 ? 0.f : s_hx[256 + row]) + h2;
+                }
+              }
+              named_bar_sync(1 + q, 128);
             }
-            named_bar_sync(1 + q, 64);
-            if (ch == 0 && row_ok) {
+            if (cq == 0 && row_ok) {
               const float* hb = c_pair_consts + L.head_b_off;
               float* o = p.raw + gr * 4 + L.head_col;
               o[0] = h0 + s_hx[row] + hb[0];
-              if (L.heads == 3) { o[1] = h1 + s_hx[128 + row] + hb[1]; o[2] = h2 + s_hx[256 + row] + hb[2]; }
+              if (nh == 3) { o[1] = h1 + s_hx[128 + row] + hb[1]; o[2] = h2 + s_hx[256 + row] + hb[2]; }
             }
-            named_bar_sync(1 + q, 64);
+            named_bar_sync(1 + q, 128);
           }
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 18) {
     // ---------------- store warp (training): activation tiles -> global for the backward pass ----------------
     if (TRAIN && lane == 0) {
       uint32_t it0 = 0, it1 = 0;
@@ -374,6 +396,8 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
     const ChainLayerHost& h = layers[l];
     RN_REQUIRE((h.n == 256 || h.n == 128) && (h.k == 64 || h.k == 256 || h.k == 320));
     RN_REQUIRE(!(h.mask_out && h.n != 256) && !(h.n == 128 && h.heads != 3) && !(h.n == 256 && h.heads == 3));
+    RN_REQUIRE(h.relu || (!h.mask_out && h.heads == 0));      // mask bits and fused heads assume a ReLU output
+    RN_REQUIRE(h.bias_off % 2 == 0);
     if ((rc = make_tmap(&p.tmB[l], h.B, h.k, h.n, h.ldb, h.n / 2)) != RN_OK) return rc;
     if (training && (rc = make_tmap(&p.tmD[l], h.D, h.n, M, h.ldd, 128)) != RN_OK) return rc;
     PairLayer& L = p.L[l];
@@ -405,7 +429,7 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
     configured = true;
   }
-  RN_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pair_consts, consts, layout::kF32Elems * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
+  RN_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pair_consts2, consts, layout::kF32Elems * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
   const int n_groups = (p.n_ptiles + 1) / 2;
   const int max_clusters = num_sms() / 2;
   const int grid = 2 * (n_groups < max_clusters ? n_groups : max_clusters);

@@ -271,11 +271,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 x[6] = fmaxf(x[6] + b1.z, relu_lo); x[7] = fmaxf(x[7] + b1.w, relu_lo);
                 if (WMASK) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << (cc * 8 + e)) : 0u;
+                  for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << layout::relu_mask_bit(cc * 8 + e)) : 0u;
                 }
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = ((word >> (cc * 8 + e)) & 1u) ? x[e] : 0.f;
+                for (int e = 0; e < 8; ++e) x[e] = ((word >> layout::relu_mask_bit(cc * 8 + e)) & 1u) ? x[e] : 0.f;
               }
               uint32_t packed[4];
 #pragma unroll
@@ -738,7 +738,7 @@ __device__ __forceinline__ void chain_epilogue_half(uint32_t t_half, uint8_t* s_
       x[6] = fmaxf(x[6] + b1.z, relu_lo); x[7] = fmaxf(x[7] + b1.w, relu_lo);
       if (WMASK) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << (cc * 8 + e)) : 0u;
+        for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << layout::relu_mask_bit(cc * 8 + e)) : 0u;
       }
       uint32_t packed[4];
 #pragma unroll
