@@ -69,7 +69,30 @@ extern int g_chain_dbg;
 #else
 #define RN_PDBG(p, bit) (0)
 #endif
+#ifdef RN_EXPERIMENTS
+// timeline of cluster 0 (scripts/pair_timeline.py): role r of CTA rank c appends (tag, clock64, globaltimer) triples
+constexpr int kTlRoles = 4, kTlEntries = 2048;
+long long* g_pair_timeline = nullptr;        // [2 ranks][kTlRoles][kTlEntries][3]
+struct Tl {
+  long long* base; int n;
+  __device__ __forceinline__ void init(long long* buf, int rank, int role, bool on) {
+    base = (on && buf) ? buf + ((size_t)(rank * kTlRoles + role) * kTlEntries) * 3 : nullptr; n = 0;
+  }
+  __device__ __forceinline__ void rec(int tag) {
+    if (base && n < kTlEntries) {
+      unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+      base[n * 3] = tag; base[n * 3 + 1] = clock64(); base[n * 3 + 2] = (long long)g; ++n;
+    }
+  }
+};
+#define RN_TL_DECL(name, role, cond) Tl name; name.init(p.timeline, (int)rank, role, (cond) && cluster_id == 0)
+#define RN_TL(name, tag) name.rec(tag)
+#else
+#define RN_TL_DECL(name, role, cond)
+#define RN_TL(name, tag)
+#endif
 struct PairParams {
+  long long* timeline;
   int dbg;
   CUtensorMap tmB[kPairMaxLayers], tmD[kPairMaxLayers], tmAux[2];
   PairLayer L[kPairMaxLayers];
@@ -95,19 +118,39 @@ __device__ __forceinline__ uint64_t fadd2(uint32_t a_lo, uint32_t a_hi, float2 b
   return r;
 }
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ua, ub, uc, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(ua), "l"(ub), "l"(uc));
+  float2 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+  return o;
+}
+
 // NG groups of 32 accumulator columns of one row: TMEM -> bias (+ReLU) -> bf16 -> in-place activation tile (+ mask, heads).
 // G-th group of the layer output = columns 32G..32G+31; bias_off / head_w_off are float offsets into the constants.
-template <int NG, int HEADS, bool RELU, bool WMASK>
-__device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int g0, int bias_off, int head_w_off,
-                                              int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2) {
+// G0 (first group of this warp) is a template parameter: with it every bias / head-weight address is "uniform base +
+// immediate", which the compiler turns into uniform-datapath constant loads (one per warp, off the LSU and ALU pipes).
+template <int NG, int G0, int HEADS, bool RELU, bool WMASK, bool NOBIAS = false>
+__device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int bias_off, int head_w_off,
+                                              int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2, int dbg = 0) {
+  // every TMEM load of the item is issued before the first use: under a running MMA a tcgen05.ld takes several hundred
+  // cycles (the tensor core's accumulator traffic has priority), and a load -> wait -> math sequence per 32 columns exposed
+  // that latency once per group (profiles/r01_pair_experiments.md)
+  uint32_t v[NG][32];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) tmem_ld_x32(t_addr + g * 32, v[g]);
+  tmem_ld_wait();
+  float2 hh0 = make_float2(0.f, 0.f), hh1 = make_float2(0.f, 0.f), hh2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    const int G = g0 + g;
-    uint32_t v[32];
-    tmem_ld_x32(t_addr + g * 32, v);
-    tmem_ld_wait();
+    constexpr int kG0 = G0;
+    const int G = kG0 + g;
     uint8_t* box = s_tile + (G >> 1) * kChunkBytes + row * 128;
     const int b2 = (bias_off >> 1) + G * 16;           // float2 index of this group's first bias pair
+    const int w2 = (head_w_off >> 1) + G * 16;         // float2 index of this group's first head-weight pair
     uint32_t outbits = 0u;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
@@ -117,7 +160,11 @@ __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = cc * 4 + e;                       // column pair within the group
-        const uint64_t r = fadd2(v[2 * i], v[2 * i + 1], c_pair_consts2[b2 + i]);
+#ifdef RN_EXPERIMENTS
+        const uint64_t r = fadd2(v[g][2 * i], v[g][2 * i + 1], NOBIAS ? make_float2(0.5f, 0.25f) : c_pair_consts2[b2 + i]);
+#else
+        const uint64_t r = fadd2(v[g][2 * i], v[g][2 * i + 1], c_pair_consts2[b2 + i]);
+#endif
         float lo, hi;
         asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
         __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
@@ -125,25 +172,26 @@ __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, 
         packed[e] = *reinterpret_cast<uint32_t*>(&pk);
         // after the ReLU both halves are +0 or positive: adding 0x7FFF sets bit 15 / 31 exactly for the non-zero ones
         if (WMASK) outbits |= ((packed[e] + 0x7FFF7FFFu) & 0x80008000u) >> i;
-      }
-      if (HEADS > 0) {
-        // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation, as the per-layer kernel does
-        const int j0 = G * 32 + cc * 8;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xFFFF0000u);
-          const int j = j0 + 2 * e;
-          h0 = fmaf(r0, c_pair_consts[head_w_off + j], h0); h0 = fmaf(r1, c_pair_consts[head_w_off + j + 1], h0);
+        if (HEADS > 0) {
+          // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation; even and odd columns accumulate in
+          // the two halves of a packed fp32 pair
+          const float2 a = make_float2(__uint_as_float(packed[e] << 16), __uint_as_float(packed[e] & 0xFFFF0000u));
+          hh0 = ffma2(a, c_pair_consts2[w2 + i], hh0);
           if (HEADS == 3) {
-            h1 = fmaf(r0, c_pair_consts[head_w_off + n + j], h1); h1 = fmaf(r1, c_pair_consts[head_w_off + n + j + 1], h1);
-            h2 = fmaf(r0, c_pair_consts[head_w_off + 2 * n + j], h2); h2 = fmaf(r1, c_pair_consts[head_w_off + 2 * n + j + 1], h2);
+            hh1 = ffma2(a, c_pair_consts2[w2 + (n >> 1) + i], hh1);
+            hh2 = ffma2(a, c_pair_consts2[w2 + n + i], hh2);
           }
         }
       }
+#ifdef RN_EXPERIMENTS
+      if (dbg & 32) { if (packed[0] == 0x12345678u) *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]); }
+      else
+#endif
       *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
     mb[g] = outbits;
   }
+  if (HEADS > 0) { h0 = hh0.x + hh0.y; h1 = hh1.x + hh1.y; h2 = hh2.x + hh2.y; }
 }
 
 template <bool TRAIN>
@@ -197,6 +245,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     const uint32_t aux_full_leader = mapa_u32(smem_u32(aux_full), 0);
     int s = 0; uint32_t ph = 0;
     uint32_t aux_n0 = 0, aux_n1 = 0;
+    RN_TL_DECL(tl, 3, lane == 0);
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
       for (int l = 0; l < p.n_layers; ++l) {
@@ -215,8 +264,11 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
             }
             __syncwarp();
           }
+          // a layer whose chunks all fit the ring is loaded ONCE per group and used by both tile slots
+          if (slot == 1 && k_chunks <= kNBStages) continue;
           for (int kc = 0; kc < k_chunks; ++kc) {
             mbar_wait(&empty_b[s], ph ^ 1);
+            RN_TL(tl, 3000 + l * 10 + kc);                 // stage free, load issued
             if (elect_one()) {
               if RN_PDBG(p, 1) { if (rank == 0) mbar_arrive(&full_b[s]); }
               else {
@@ -237,8 +289,9 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
       const uint32_t act_lo0 = desc_lo_sw128(smem_u32(s_act), 16);
       const uint32_t aux_lo0 = desc_lo_sw128(smem_u32(s_aux), 16);
       const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_b), 16);
-      int s = 0; uint32_t ph = 0;
+      int s = 0, s_mark = 0; uint32_t ph = 0, ph_mark = 0;
       uint32_t it0 = 0, it1 = 0, aux_n0 = 0, aux_n1 = 0;
+      RN_TL_DECL(tl, 0, lane == 0);
       for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
         const int tiles_here = min(2, p.n_ptiles - grp * 2);
         for (int l = 0; l < p.n_layers; ++l) {
@@ -247,14 +300,22 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
           const int k_chunks = L.k_chunks;
           for (int slot = 0; slot < tiles_here; ++slot) {
             const uint32_t i = slot ? it1++ : it0++;
-            if (i > 0) mbar_wait_cluster(&act_ready[slot], (i - 1) & 1u);     // input tile written, accumulator drained
+            RN_TL(tl, 100 + l * 10 + slot);                // item reached
+            if (i > 0) mbar_wait(&act_ready[slot], (i - 1) & 1u);             // input tile written, accumulator drained
+            RN_TL(tl, 300 + l * 10 + slot);                // input ready
             if (L.aux_load) {
               const uint32_t j = slot ? aux_n1++ : aux_n0++;
               mbar_wait(&aux_full[slot], j & 1u);
             }
             const uint32_t d_tmem = tmem_base + slot * 256;
+            // weight stages of a layer that fits the ring are shared by the two slots: slot 0 consumes them without
+            // releasing, slot 1 rewinds to the same stages and releases them
+            const bool shared = (k_chunks <= kNBStages) && (tiles_here == 2);
+            if (shared && slot == 1) { s = s_mark; ph = ph_mark; }
+            s_mark = s; ph_mark = ph;
             for (int kc = 0; kc < k_chunks; ++kc) {
-              mbar_wait(&full_b[s], ph);
+              if (!(shared && slot == 1)) mbar_wait(&full_b[s], ph);
+              RN_TL(tl, 1000 + l * 100 + slot * 10 + kc);  // weight chunk present
               tcgen05_fence_after();
               if (elect_one()) {
                 const int src = L.a_src[kc];
@@ -264,7 +325,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
                 umma_bf16_pair(d_tmem, pack64(al, kHi), pack64(bl, kHi), idesc, kc != 0);
 #pragma unroll
                 for (int k = 1; k < 4; ++k) umma_bf16_pair(d_tmem, pack64(al + 2 * k, kHi), pack64(bl + 2 * k, kHi), idesc, 1u);
-                umma_commit_pair(&empty_b[s]);
+                if (!(shared && slot == 0)) umma_commit_pair(&empty_b[s]);
                 if (kc == k_chunks - 1) {
                   umma_commit_pair(&tmem_full[slot]);
                   if (L.aux_release) umma_commit_pair(&aux_empty[slot]);
@@ -284,6 +345,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     const int row = q * 32 + lane;
     const uint32_t act_ready_leader = mapa_u32(smem_u32(act_ready), 0);
     uint32_t it0 = 0, it1 = 0;
+    RN_TL_DECL(tl, (warp == 2 ? 1 : 2), lane == 0 && (warp == 2 || warp == 17));
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
       for (int l = 0; l < p.n_layers; ++l) {
@@ -292,8 +354,11 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
           const uint32_t i = slot ? it1++ : it0++;
           const int64_t gr = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128 + row;
           const bool row_ok = gr < p.m_rows;
+          RN_TL(tl, 100 + l * 10 + slot);
           mbar_wait(&tmem_full[slot], i & 1u);
+          RN_TL(tl, 300 + l * 10 + slot);                  // accumulator complete
           if (TRAIN && i > 0) mbar_wait(&store_done[slot], (i - 1) & 1u);   // the previous activation has been stored
+          RN_TL(tl, 500 + l * 10 + slot);
           tcgen05_fence_after();
           uint8_t* s_tile = s_act + slot * kActBytes;
           const uint32_t t_addr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + cq * (L.n >> 2);
@@ -304,20 +369,29 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
 #pragma unroll 1
             for (int g = 0; g < (L.n >> 7); ++g) { uint32_t v[32]; tmem_ld_x32(t_addr + g * 32, v); tmem_ld_wait(); if (v[0] == 0x7fc12345u) mb[0] ^= v[1]; }
           }
-          else if (L.n == 256) {
-            if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2);
-            else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2);
-            else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2);
-          } else {
-            pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, L.bias_off, L.head_w_off, 128, mb, h0, h1, h2);
+          else {
+#define RN_EPI(CQ)                                                                                                          \
+  if (L.n == 256) {                                                                                                         \
+    if (L.heads == 1) pair_epilogue<2, 2 * CQ, 1, true, TRAIN>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2, p.dbg); \
+    else if (L.relu && RN_PDBG(p, 64)) pair_epilogue<2, 2 * CQ, 0, true, TRAIN, true>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);  \
+    else if (L.relu) pair_epilogue<2, 2 * CQ, 0, true, TRAIN>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);  \
+    else pair_epilogue<2, 2 * CQ, 0, false, false>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);     \
+  } else {                                                                                                                  \
+    pair_epilogue<1, CQ, 3, true, false>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 128, mb, h0, h1, h2, p.dbg);               \
+  }
+            if (cq == 0) { RN_EPI(0) } else if (cq == 1) { RN_EPI(1) } else if (cq == 2) { RN_EPI(2) } else { RN_EPI(3) }
+#undef RN_EPI
           }
+          RN_TL(tl, 600 + l * 10 + slot);                  // math done
           tcgen05_fence_before();
-          fence_proxy_async_smem();
+          if (!RN_PDBG(p, 128)) fence_proxy_async_smem();
+          RN_TL(tl, 650 + l * 10 + slot);                  // fences done
           __syncwarp();
           if (lane == 0) {
             mbar_arrive_cluster(act_ready_leader + slot * 8);
             if (TRAIN) mbar_arrive(&staged[slot]);
           }
+          RN_TL(tl, 700 + l * 10 + slot);                  // tile written, arrived
           if (TRAIN && L.mask_out && row_ok)
             *reinterpret_cast<uint2*>(L.mask_out + gr * 8 + cq * 2) = make_uint2(mb[0], mb[1]);
           if (L.heads > 0) {
@@ -397,7 +471,7 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
     RN_REQUIRE((h.n == 256 || h.n == 128) && (h.k == 64 || h.k == 256 || h.k == 320));
     RN_REQUIRE(!(h.mask_out && h.n != 256) && !(h.n == 128 && h.heads != 3) && !(h.n == 256 && h.heads == 3));
     RN_REQUIRE(h.relu || (!h.mask_out && h.heads == 0));      // mask bits and fused heads assume a ReLU output
-    RN_REQUIRE(h.bias_off % 2 == 0);
+    RN_REQUIRE(h.bias_off % 2 == 0 && h.head_w_off % 2 == 0);
     if ((rc = make_tmap(&p.tmB[l], h.B, h.k, h.n, h.ldb, h.n / 2)) != RN_OK) return rc;
     if (training && (rc = make_tmap(&p.tmD[l], h.D, h.n, M, h.ldd, 128)) != RN_OK) return rc;
     PairLayer& L = p.L[l];
@@ -417,8 +491,10 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
   }
 #ifdef RN_EXPERIMENTS
   p.dbg = g_chain_dbg;
+  p.timeline = g_pair_timeline;
 #else
   p.dbg = 0;
+  p.timeline = nullptr;
 #endif
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
@@ -444,3 +520,8 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
 }
 
 }  // namespace rn
+
+#ifdef RN_EXPERIMENTS
+extern "C" int rn_pair_timeline(long long* device_buffer) { rn::g_pair_timeline = device_buffer; return 0; }
+extern "C" int rn_pair_timeline_dims(int* roles, int* entries) { *roles = rn::kTlRoles; *entries = rn::kTlEntries; return 0; }
+#endif

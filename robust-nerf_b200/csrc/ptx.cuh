@@ -39,15 +39,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU box -- after 2^27 failed probes (seconds) trap (sticky error).
-// The hot path is one try_wait and a branch: this sits inside the single-thread MMA issue loop, where every extra
-// instruction shows up as tensor-pipe idle time (scripts/umma_bench.cu).
+// Bounded wait: a protocol bug must not hang the GPU box -- after ~4 s of wall time trap (sticky error).  A failed
+// try_wait can suspend the thread for microseconds, so the bound is taken from %globaltimer (read only on the slow path,
+// every 32nd failed probe); the hot path is one try_wait and a branch: this sits inside the single-thread MMA issue
+// loop, where every extra instruction shows up as tensor-pipe idle time (scripts/umma_bench.cu).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void mbar_timeout_trap() {
+  printf("rnerf_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 27)) {
-      printf("rnerf_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+    if ((++spins & 31u) == 0) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) mbar_timeout_trap();
     }
   }
 }
@@ -126,8 +139,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Default (CTA-scope release) semantics, as CUTLASS's 2-SM
+// accumulator pipeline uses: what the waiter consumes is ordered by the fences the arriver executed before
+// (tcgen05.fence::before_thread_sync for its TMEM reads, fence.proxy.async for its shared-memory writes, which only
+// this CTA's own tensor core reads); a .release.cluster arrive costs ~1,300 cycles on the chain's critical path
+// (profiles/r01_pair_experiments.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -141,10 +159,12 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 // wait on a barrier that receives arrivals from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 27)) {
-      printf("rnerf_b200: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+    if ((++spins & 31u) == 0) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) mbar_timeout_trap();
     }
   }
 }
