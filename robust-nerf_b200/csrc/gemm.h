@@ -17,6 +17,17 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
                    size_t scratch_bytes, TnInfo* info, cudaStream_t st);
 int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int col0, int ncols, float* dst, int64_t dst_ld,
                    float* colsum_dst, cudaStream_t st);
+// Batched form: the backward pass gives every weight-gradient launch its own partial-tile region and reduces all of
+// them (14 scatters per network) in ONE launch at the end instead of one small latency-bound launch each.
+constexpr int kTnBatchMax = 16;
+struct TnReduceDesc {
+  const float* partial; float* dst; float* colsum_dst; int64_t dst_ld;
+  int m_tiles, splits, BN, row0, nrows, col0, ncols, block0;
+};
+struct TnBatch { TnReduceDesc d[kTnBatchMax]; int n, total_blocks; };
+int tn_batch_add(TnBatch* b, const TnInfo& info, int row0, int nrows, int col0, int ncols, float* dst, int64_t dst_ld,
+                 float* colsum_dst);
+int gemm_tn_reduce_batch(const TnBatch& b, cudaStream_t st);
 
 // one layer of the chained forward (mlp_chain_forward): D[M,n] = act(A[M,k] B[n,k]^T + bias), bf16 views
 struct ChainLayerHost {

@@ -432,14 +432,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // (each takes every 8th split), then combined in a fixed order -> bit-reproducible, and 8x the loads in flight
 // of a thread-per-element loop (the partial tiles total up to 19 MB per layer).
 constexpr int kRedParts = 8;
-__global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float* __restrict__ partial, int m_tiles, int splits, int BN, int row0, int nrows, int col0,
-                     int ncols, float* __restrict__ dst, int64_t dst_ld, float* __restrict__ colsum_dst) {
+__device__ __forceinline__ void splitk_reduce_block(const float* __restrict__ partial, int m_tiles, int splits, int BN, int row0,
+                                                    int nrows, int col0, int ncols, float* __restrict__ dst, int64_t dst_ld,
+                                                    float* __restrict__ colsum_dst, int block) {
   __shared__ float s_part[kRedParts][32];
   const int e = threadIdx.x & 31;            // element within the CTA's 32-element block
   const int part = threadIdx.x >> 5;         // which splits this thread sums
   const int total = nrows * ncols;
-  const int o = blockIdx.x * 32 + e;
+  const int o = block * 32 + e;
   const size_t blk = (size_t)kBlockM * (BN + 1);
   float acc = 0.f;
   bool live = false;
@@ -469,6 +469,18 @@ splitk_reduce_kernel(const float* __restrict__ partial, int m_tiles, int splits,
     if (o < total) dst[(int64_t)(o / ncols) * dst_ld + (o % ncols)] = t;
     else colsum_dst[o - total] = t;
   }
+}
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int m_tiles, int splits, int BN, int row0, int nrows, int col0,
+                     int ncols, float* __restrict__ dst, int64_t dst_ld, float* __restrict__ colsum_dst) {
+  splitk_reduce_block(partial, m_tiles, splits, BN, row0, nrows, col0, ncols, dst, dst_ld, colsum_dst, blockIdx.x);
+}
+__global__ void __launch_bounds__(256) splitk_reduce_batch_kernel(const __grid_constant__ TnBatch b) {
+  int i = 0;
+  while (i + 1 < b.n && (int)blockIdx.x >= b.d[i + 1].block0) ++i;
+  const TnReduceDesc& d = b.d[i];
+  splitk_reduce_block(d.partial, d.m_tiles, d.splits, d.BN, d.row0, d.nrows, d.col0, d.ncols, d.dst, d.dst_ld, d.colsum_dst,
+                      (int)blockIdx.x - d.block0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -652,6 +664,24 @@ int gemm_tn_reduce(const TnInfo& info, int row0, int nrows, int col0, int ncols,
   const int total = nrows * ncols + nrows;
   splitk_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(info.scratch, info.m_tiles, info.splits, info.N, row0, nrows,
                                                            col0, ncols, dst, dst_ld, colsum_dst);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int tn_batch_add(TnBatch* b, const TnInfo& info, int row0, int nrows, int col0, int ncols, float* dst, int64_t dst_ld,
+                 float* colsum_dst) {
+  RN_REQUIRE(b && b->n < kTnBatchMax && row0 >= 0 && nrows > 0 && col0 >= 0 && ncols > 0 && col0 + ncols <= info.N &&
+             row0 + nrows <= info.m_tiles * kBlockM);
+  TnReduceDesc& d = b->d[b->n++];
+  d.partial = info.scratch; d.dst = dst; d.colsum_dst = colsum_dst; d.dst_ld = dst_ld;
+  d.m_tiles = info.m_tiles; d.splits = info.splits; d.BN = info.N; d.row0 = row0; d.nrows = nrows; d.col0 = col0; d.ncols = ncols;
+  d.block0 = b->total_blocks;
+  b->total_blocks += (nrows * ncols + nrows + 31) / 32;
+  return RN_OK;
+}
+int gemm_tn_reduce_batch(const TnBatch& b, cudaStream_t st) {
+  if (b.n == 0) return RN_OK;
+  splitk_reduce_batch_kernel<<<b.total_blocks, 256, 0, st>>>(b);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

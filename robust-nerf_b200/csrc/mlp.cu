@@ -32,11 +32,12 @@ struct TrainWs {
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+constexpr int kTnLaunches = 10;      // weight-gradient launches per backward pass: each keeps its own partial-tile region
 
 static size_t workspace_bytes(int64_t M, int training) {
   const size_t elems = training ? (size_t)(kTrainFwdElems + kTrainBwdElems) : (size_t)kInferElems;
   size_t b = align_up((size_t)M * elems * 2, 256);
-  if (training) b += align_up(gemm_tn_scratch_bytes(), 256) + align_up(heads_bwd_scratch_bytes(M), 256);
+  if (training) b += kTnLaunches * align_up(gemm_tn_scratch_bytes(), 256) + align_up(heads_bwd_scratch_bytes(M), 256);
   return b + 256;
 }
 
@@ -54,7 +55,7 @@ static void carve_train(void* ws, int64_t M, TrainWs* w) {
   uint8_t* q = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(p), 256));
   w->scratch = reinterpret_cast<float*>(q);
   w->scratch_bytes = gemm_tn_scratch_bytes();
-  w->heads_scratch = reinterpret_cast<float*>(q + align_up(w->scratch_bytes, 256));
+  w->heads_scratch = reinterpret_cast<float*>(q + kTnLaunches * align_up(w->scratch_bytes, 256));
 }
 
 static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimension of H[l]
@@ -138,19 +139,23 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   carve_train(ws, M, &w);
   const bool need_in = (g_pts != nullptr) || (g_dirs != nullptr);
   TnInfo ti;
+  TnBatch batch{};
+  int tn_k = 0;
+  const size_t region = align_up(w.scratch_bytes, 256) / sizeof(float);
+  auto scratch_k = [&]() { return w.scratch + (size_t)(tn_k++) * region; };
   // heads: dHC, dFS[:, 256:272], rgb_linear grads
   RN_TRY(launch_heads_bwd(g_raw, w.HC, M, F, w.dHC, w.dFS, 272, w.heads_scratch, G + kG_WRgb, G + kG_BRgb, st));
   // dir_linear: weight grads over [feat(256) | d_enc(27)] and bias
   // one launch over the whole 320-wide input [feat(256) | d_enc(27) | 0]
-  RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 320, M, w.scratch, w.scratch_bytes, &ti, st));
-  RN_TRY(gemm_tn_reduce(ti, 0, 128, 0, 283, G + kG_WD, 283, G + kG_BD, st));
+  RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
+  RN_TRY(tn_batch_add(&batch, ti, 0, 128, 0, 283, G + kG_WD, 283, G + kG_BD));
   // d feat = dHC x WD[:, 0:256]  -> dFS[:, 0:256]   (feature_linear has no activation: no mask)
   RN_TRY(gemm_nn(w.dHC, 128, W + kWD, 320, w.dFS, 272, M, 256, 128, nullptr, st));
   if (g_dirs) RN_TRY(gemm_nn(w.dHC, 128, W + kWD + 256, 320, w.dDE, 64, M, 64, 128, nullptr, st));
   // feature_linear + sigma_linear (row 256 of dFS^T): weights, biases
-  RN_TRY(gemm_tn_launch(w.dFS, 272, 272, w.H[7], 256, 256, M, w.scratch, w.scratch_bytes, &ti, st));
-  RN_TRY(gemm_tn_reduce(ti, 0, 256, 0, 256, G + kG_WF, 256, G + kG_BF, st));
-  RN_TRY(gemm_tn_reduce(ti, 256, 1, 0, 256, G + kG_WSig, 256, G + kG_BSig, st));
+  RN_TRY(gemm_tn_launch(w.dFS, 272, 272, w.H[7], 256, 256, M, scratch_k(), w.scratch_bytes, &ti, st));
+  RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 256, G + kG_WF, 256, G + kG_BF));
+  RN_TRY(tn_batch_add(&batch, ti, 256, 1, 0, 256, G + kG_WSig, 256, G + kG_BSig));
   // dH7 = [dF | dsigma] x WFS, masked by H7 > 0
   RN_TRY(gemm_nn(w.dFS, 272, W + kWFS, 256, w.dA, 256, M, 256, 272, w.MB[7], st));
   bf16* dY = w.dA;
@@ -159,23 +164,25 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
     if (l == 5) {
       // input = XC = [x_enc(64) | H4(256)]
       // one launch over the whole 320-wide input; the zero pad column 63 is dropped by the two scatters
-      RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 320, M, w.scratch, w.scratch_bytes, &ti, st));
-      RN_TRY(gemm_tn_reduce(ti, 0, 256, 0, 63, G + trunk_gw(5), 319, nullptr, st));
-      RN_TRY(gemm_tn_reduce(ti, 0, 256, 64, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5), st));
+      RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
+      RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(5), 319, nullptr));
+      RN_TRY(tn_batch_add(&batch, ti, 0, 256, 64, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5)));
       RN_TRY(gemm_nn(dY, 256, W + kW5 + 64, 320, dN, 256, M, 256, 256, w.MB[4], st));
       if (need_in) RN_TRY(gemm_nn(dY, 256, W + kW5, 320, w.dXE5, 64, M, 64, 256, nullptr, st));
     } else {
       const bf16* in = w.H[l - 1];
       const int ldin = ld_of(l - 1);
-      RN_TRY(gemm_tn_launch(dY, 256, 256, in, ldin, 256, M, w.scratch, w.scratch_bytes, &ti, st));
-      RN_TRY(gemm_tn_reduce(ti, 0, 256, 0, 256, G + trunk_gw(l), 256, G + trunk_gb(l), st));
+      RN_TRY(gemm_tn_launch(dY, 256, 256, in, ldin, 256, M, scratch_k(), w.scratch_bytes, &ti, st));
+      RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 256, G + trunk_gw(l), 256, G + trunk_gb(l)));
       RN_TRY(gemm_nn(dY, 256, W + trunk_w(l), 256, dN, 256, M, 256, 256, w.MB[l - 1], st));
     }
     bf16* t = dY; dY = dN; dN = t;
   }
   // layer 0: input = x_enc
-  RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, w.scratch, w.scratch_bytes, &ti, st));
-  RN_TRY(gemm_tn_reduce(ti, 0, 256, 0, 63, G + trunk_gw(0), 63, G + trunk_gb(0), st));
+  RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, scratch_k(), w.scratch_bytes, &ti, st));
+  RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(0), 63, G + trunk_gb(0)));
+  RN_REQUIRE(tn_k <= kTnLaunches);
+  RN_TRY(gemm_tn_reduce_batch(batch, st));
   if (need_in) {
     RN_TRY(gemm_nn(dY, 256, W + kW0, 64, w.dXE0, 64, M, 64, 256, nullptr, st));
     if (!g_pts) { /* dirs only */ }
