@@ -454,6 +454,326 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
   }
 }
 
+// =====================================================================================================
+// Data-gradient chain (backward of the trunk): dX_{l-1} = (dX_l W_l) .* (H_{l-1} > 0), nine layers in one launch.
+//
+// Same pair / two-slot / in-place structure as the forward chain.  Differences: the weights are read MN-major (the
+// forward's [out][in] matrices serve as B[K = out][N = in] without a transposed copy); the epilogue applies the packed
+// ReLU mask the forward stored (8 bytes per row and warp) instead of bias + ReLU; every layer's output is TMA-stored
+// because the weight-gradient GEMMs read it afterwards; the first layer's input (dHC, 128 wide) is TMA-loaded into the
+// activation buffer, and the sigma-gradient column block of dFS enters as a side chunk.  HBM traffic per point and layer:
+// 512 B written (+ 8 x 4 B of mask read) instead of 512 B read + 512 B written by the per-layer kernel.
+// =====================================================================================================
+struct BwdLayer {
+  int k_chunks;                // 64-wide K chunks of the A operand
+  int8_t a_src[kPairMaxChunks];
+  int last_ksteps;             // 16-wide k steps of the last chunk (1..4)
+  int n_off;                   // first weight column (N offset inside the weight matrix)
+  int aux_load, aux_col;       // side chunk: 0 / 1 + tensor map index, first column
+  int act_load_chunks;         // >0: the layer input is TMA-loaded from tmIn into the activation buffer
+  const uint32_t* mask_in;     // packed ReLU mask of the layer OUTPUT rows [M][8], or null
+};
+struct BwdParams {
+  CUtensorMap tmB[kPairMaxLayers], tmD[kPairMaxLayers], tmIn, tmAux;
+  BwdLayer L[kPairMaxLayers];
+  int n_layers, n_ptiles;
+  int64_t m_rows;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_act = smem;
+  uint8_t* s_aux = smem + 2 * kActBytes;
+  uint8_t* s_b = s_aux + 2 * kAuxBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kNBStages * kBStageBytes);
+  uint64_t* full_b = bars;               // [4]  leader
+  uint64_t* empty_b = bars + 4;          // [4]  each CTA (multicast commit)
+  uint64_t* aux_full = bars + 8;         // [2]  leader
+  uint64_t* aux_empty = bars + 10;       // [2]  each CTA
+  uint64_t* act_ready = bars + 12;       // [2]  leader: 32 epilogue warps
+  uint64_t* tmem_full = bars + 14;       // [2]  each CTA
+  uint64_t* staged = bars + 16;          // [2]  epilogue -> store warp
+  uint64_t* store_done = bars + 18;      // [2]  store warp -> epilogue and producer
+  uint64_t* act_full = bars + 20;        // [2]  leader: TMA-loaded layer input landed in both CTAs
+  uint64_t* act_free = bars + 22;        // [2]  store warp -> producer, ONCE PER TILE: the last layer's tile has been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int l = 0; l < p.n_layers; ++l) { prefetch_tmap(&p.tmB[l]); prefetch_tmap(&p.tmD[l]); }
+    prefetch_tmap(&p.tmIn); prefetch_tmap(&p.tmAux);
+    for (int i = 0; i < kNBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&aux_full[i], 1); mbar_init(&aux_empty[i], 1);
+      mbar_init(&act_ready[i], 32); mbar_init(&tmem_full[i], 1);
+      mbar_init(&staged[i], 16); mbar_init(&store_done[i], 1);
+      mbar_init(&act_full[i], 1); mbar_init(&act_free[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_groups = (p.n_ptiles + 1) >> 1;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    const uint32_t full_b_leader = mapa_u32(smem_u32(full_b), 0);
+    const uint32_t aux_full_leader = mapa_u32(smem_u32(aux_full), 0);
+    const uint32_t act_full_leader = mapa_u32(smem_u32(act_full), 0);
+    int s = 0; uint32_t ph = 0;
+    uint32_t aux_n0 = 0, aux_n1 = 0, in_n0 = 0, in_n1 = 0;
+    for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+      const int tiles_here = min(2, p.n_ptiles - grp * 2);
+      for (int l = 0; l < p.n_layers; ++l) {
+        const int k_chunks = p.L[l].k_chunks, aux_load = p.L[l].aux_load, act_chunks = p.L[l].act_load_chunks;
+        const int n_off = p.L[l].n_off, aux_col = p.L[l].aux_col;
+        for (int slot = 0; slot < tiles_here; ++slot) {
+          const int row0 = ((grp * 2 + slot) * 2 + (int)rank) * 128;
+          if (act_chunks) {
+            // the buffer still feeds the TMA store of the previous tile's last layer.  (store_done completes once per
+            // layer and this warp runs about a layer ahead of the stores: its parity would alias; act_free completes
+            // once per tile.)
+            const uint32_t j = slot ? in_n1++ : in_n0++;
+            if (j > 0) mbar_wait(&act_free[slot], (j - 1) & 1u);
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(&act_full[slot], (uint32_t)(2 * act_chunks * kChunkBytes));
+              for (int c = 0; c < act_chunks; ++c)
+                tma_load_2d_pair(s_act + slot * kActBytes + c * kChunkBytes, &p.tmIn, act_full_leader + slot * 8, c * 64, row0);
+            }
+            __syncwarp();
+          }
+          if (aux_load) {
+            const uint32_t j = slot ? aux_n1++ : aux_n0++;
+            if (j > 0) mbar_wait(&aux_empty[slot], (j - 1) & 1u);
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(&aux_full[slot], 2 * kAuxBytes);
+              tma_load_2d_pair(s_aux + slot * kAuxBytes, &p.tmAux, aux_full_leader + slot * 8, aux_col, row0);
+            }
+            __syncwarp();
+          }
+          if (slot == 1 && k_chunks <= kNBStages) continue;          // weight stages shared by the two slots
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(&empty_b[s], ph ^ 1);
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_b[s], 2u * kBStageBytes);
+              // this CTA's half of the 256 output columns: two [64 k rows][64 columns] boxes
+              uint8_t* dst = s_b + s * kBStageBytes;
+              const int c0 = n_off + (int)rank * 128;
+              tma_load_2d_pair(dst, &p.tmB[l], full_b_leader + s * 8, c0, kc * 64);
+              tma_load_2d_pair(dst + 8192, &p.tmB[l], full_b_leader + s * 8, c0 + 64, kc * 64);
+            }
+            __syncwarp();
+            if (++s == kNBStages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (leader CTA) ----------------
+    if (rank == 0) {
+      constexpr uint32_t kHi = desc_hi_sw128(1024);
+      constexpr uint32_t idesc = make_idesc_bf16(256, 256, 0, 1);
+      const uint32_t act_lo0 = desc_lo_sw128(smem_u32(s_act), 16);
+      const uint32_t aux_lo0 = desc_lo_sw128(smem_u32(s_aux), 16);
+      const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_b), 8192);
+      int s = 0, s_mark = 0; uint32_t ph = 0, ph_mark = 0;
+      uint32_t it0 = 0, it1 = 0, aux_n0 = 0, aux_n1 = 0, in_n0 = 0, in_n1 = 0;
+      for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+        const int tiles_here = min(2, p.n_ptiles - grp * 2);
+        for (int l = 0; l < p.n_layers; ++l) {
+          const BwdLayer& L = p.L[l];
+          const int k_chunks = L.k_chunks;
+          for (int slot = 0; slot < tiles_here; ++slot) {
+            const uint32_t i = slot ? it1++ : it0++;
+            if (i > 0) mbar_wait(&act_ready[slot], (i - 1) & 1u);             // accumulator drained (and input written)
+            if (L.act_load_chunks) {
+              const uint32_t j = slot ? in_n1++ : in_n0++;
+              mbar_wait(&act_full[slot], j & 1u);
+            }
+            if (L.aux_load) {
+              const uint32_t j = slot ? aux_n1++ : aux_n0++;
+              mbar_wait(&aux_full[slot], j & 1u);
+            }
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            const bool shared = (k_chunks <= kNBStages) && (tiles_here == 2);
+            if (shared && slot == 1) { s = s_mark; ph = ph_mark; }
+            s_mark = s; ph_mark = ph;
+            for (int kc = 0; kc < k_chunks; ++kc) {
+              if (!(shared && slot == 1)) mbar_wait(&full_b[s], ph);
+              tcgen05_fence_after();
+              if (elect_one()) {
+                const int src = L.a_src[kc];
+                const uint32_t al = (src == 4) ? aux_lo0 + slot * (kAuxBytes >> 4)
+                                               : act_lo0 + slot * (kActBytes >> 4) + src * (kChunkBytes >> 4);
+                const uint32_t bl = b_lo0 + s * (kBStageBytes >> 4);
+                const int ksteps = (kc == k_chunks - 1) ? L.last_ksteps : 4;
+                umma_bf16_pair(d_tmem, pack64(al, kHi), pack64(bl, kHi), idesc, kc != 0);
+#pragma unroll
+                for (int k = 1; k < 4; ++k)
+                  if (k < ksteps) umma_bf16_pair(d_tmem, pack64(al + 2 * k, kHi), pack64(bl + 128 * k, kHi), idesc, 1u);
+                if (!(shared && slot == 0)) umma_commit_pair(&empty_b[s]);
+                if (kc == k_chunks - 1) {
+                  umma_commit_pair(&tmem_full[slot]);
+                  if (L.aux_load) umma_commit_pair(&aux_empty[slot]);
+                }
+              }
+              __syncwarp();
+              if (++s == kNBStages) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 18) {
+    // ---------------- epilogue warps: accumulator .* ReLU mask -> bf16 -> in-place tile ----------------
+    const int q = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t act_ready_leader = mapa_u32(smem_u32(act_ready), 0);
+    uint32_t it0 = 0, it1 = 0;
+    for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+      const int tiles_here = min(2, p.n_ptiles - grp * 2);
+      for (int l = 0; l < p.n_layers; ++l) {
+        const uint32_t* mask_in = p.L[l].mask_in;
+        for (int slot = 0; slot < tiles_here; ++slot) {
+          const uint32_t i = slot ? it1++ : it0++;
+          const int64_t gr = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128 + row;
+          uint2 mw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+          if (mask_in && gr < p.m_rows) mw = __ldg(reinterpret_cast<const uint2*>(mask_in + gr * 8 + cq * 2));
+          mbar_wait(&tmem_full[slot], i & 1u);
+          if (i > 0) mbar_wait(&store_done[slot], (i - 1) & 1u);
+          tcgen05_fence_after();
+          uint8_t* s_tile = s_act + slot * kActBytes;
+          const uint32_t t_addr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + cq * 64;
+          uint32_t v[2][32];
+          tmem_ld_x32(t_addr, v[0]);
+          tmem_ld_x32(t_addr + 32, v[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int G = cq * 2 + g;
+            const uint32_t word = g ? mw.y : mw.x;
+            uint8_t* box = s_tile + (G >> 1) * kChunkBytes + row * 128;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const int lchunk = (G & 1) * 4 + cc;
+              uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
+              uint32_t packed[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int pi = cc * 4 + e;                // column pair: flags at bits 15 - pi and 31 - pi of the word
+                __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[g][2 * pi]), __uint_as_float(v[g][2 * pi + 1]));
+                const uint32_t keep = ((word >> (15 - pi)) & 0x00010001u) * 0xFFFFu;
+                packed[e] = *reinterpret_cast<uint32_t*>(&pk) & keep;
+              }
+              *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+          }
+          tcgen05_fence_before();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(act_ready_leader + slot * 8);
+            mbar_arrive(&staged[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 18) {
+    // ---------------- store warp: every layer's data gradient goes to global for the weight-gradient GEMMs ----------------
+    if (lane == 0) {
+      uint32_t it0 = 0, it1 = 0;
+      for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+        const int tiles_here = min(2, p.n_ptiles - grp * 2);
+        for (int l = 0; l < p.n_layers; ++l) {
+          for (int slot = 0; slot < tiles_here; ++slot) {
+            const uint32_t i = slot ? it1++ : it0++;
+            const int row0 = ((grp * 2 + slot) * 2 + (int)rank) * 128;
+            mbar_wait(&staged[slot], i & 1u);
+            for (int c = 0; c < 4; ++c)
+              tma_store_2d(&p.tmD[l], s_act + slot * kActBytes + c * kChunkBytes, c * 64, row0);
+            tma_store_commit();
+            tma_store_wait_read0();
+            mbar_arrive(&store_done[slot]);
+            if (l == p.n_layers - 1) mbar_arrive(&act_free[slot]);
+          }
+        }
+      }
+      tma_store_wait_all0();
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+// Host launcher of the data-gradient chain.  Layer l: D_l[M,256] = (A_l[M,K_l] B_l[K_l, n_off : n_off+256]) .* mask_l with
+// A_0 = `in` (in_cols wide, TMA-loaded), A_l = D_{l-1} (+ the side chunk `aux` at column aux_col as LAST K chunk when
+// layers[l].aux_kind == 2).
+int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M, const void* in, int64_t ld_in, int in_cols,
+                            const void* aux, int64_t ld_aux, int aux_cols, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != RN_OK) return rc;
+  RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kPairMaxLayers && M > 0 && in && (in_cols == 128 || in_cols == 256));
+  static BwdParams p;
+  double flops = 0.0;
+  if ((rc = make_tmap(&p.tmIn, in, in_cols, M, ld_in, 128)) != RN_OK) return rc;
+  if ((rc = make_tmap(&p.tmAux, aux ? aux : in, aux ? aux_cols : in_cols, M, aux ? ld_aux : ld_in, 128)) != RN_OK) return rc;
+  for (int l = 0; l < n_layers; ++l) {
+    const BwdLayerHost& h = layers[l];
+    RN_REQUIRE(h.B && h.D && h.k > 0 && h.k % 16 == 0 && h.k <= 320);
+    // weights [k rows][ldb columns], MN-major B operand: boxes of [64 k rows][64 columns]
+    if ((rc = make_tmap(&p.tmB[l], h.B, h.b_cols, h.k, h.ldb, 64)) != RN_OK) return rc;
+    if ((rc = make_tmap(&p.tmD[l], h.D, 256, M, h.ldd, 128)) != RN_OK) return rc;
+    BwdLayer& L = p.L[l];
+    L = BwdLayer{};
+    L.k_chunks = (h.k + 63) / 64;
+    L.last_ksteps = ((h.k - (L.k_chunks - 1) * 64) + 15) / 16;
+    int c = 0;
+    for (int a = 0; c < L.k_chunks - (h.aux_kind == 2 ? 1 : 0); ++a) L.a_src[c++] = (int8_t)a;
+    if (h.aux_kind == 2) { RN_REQUIRE(aux != nullptr); L.a_src[c++] = 4; L.aux_load = 1; L.aux_col = h.aux_col; }
+    L.n_off = h.n_off;
+    L.act_load_chunks = (l == 0) ? in_cols / 64 : 0;
+    L.mask_in = h.mask_in;
+    RN_REQUIRE(h.n_off + 256 <= h.b_cols);
+    flops += 2.0 * (double)M * 256 * h.k;
+  }
+  p.n_layers = n_layers;
+  p.n_ptiles = (int)ceil_div(M, 256);
+  p.m_rows = M;
+  static bool configured = false;
+  if (!configured) {
+    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+    configured = true;
+  }
+  const int n_groups = (p.n_ptiles + 1) / 2;
+  const int max_clusters = num_sms() / 2;
+  const int grid = 2 * (n_groups < max_clusters ? n_groups : max_clusters);
+  g_prof_next_flops = flops;
+  int slot;
+  prof_begin(1 /*MODE_NN*/, st, &slot);
+  mlp_chain_pair_bwd_kernel<<<grid, kPairThreads, kPairSmem, st>>>(p);
+  prof_end(slot, st);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
 // Host launcher.  layers[l] uses the ChainLayerHost description of the per-layer chain (gemm.h); the pair kernel derives
 // where each K chunk of A lives: activation chunks for the part produced by the previous layer, the side buffer for
 // x_enc (first chunk of layers 0 and 5) and d_enc (last chunk of the view layer).

@@ -40,6 +40,16 @@ struct ChainLayerHost {
 };
 int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const void* x_enc, int64_t ld_x,
                            const void* d_enc, int64_t ld_d, const float* consts, float* raw, bool training, cudaStream_t st);
+// one layer of the data-gradient chain (chain_pair.cu): D[M,256] = (A[M,k] B[k, n_off : n_off+256]) .* mask
+struct BwdLayerHost {
+  const void* B; int64_t ldb; int b_cols;      // weight matrix [k rows][b_cols], leading dimension ldb
+  int k, n_off;
+  void* D; int64_t ldd;
+  const uint32_t* mask_in;                     // packed ReLU mask of the rows of D, or null
+  int aux_kind, aux_col;                       // 2: the last K chunk is the side chunk starting at column aux_col
+};
+int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M, const void* in, int64_t ld_in, int in_cols,
+                            const void* aux, int64_t ld_aux, int aux_cols, cudaStream_t st);
 int mlp_chain_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const float* consts, float* raw, bool wmask,
                       cudaStream_t st);
 

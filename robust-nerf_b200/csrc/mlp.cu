@@ -24,7 +24,7 @@ using namespace layout;
 typedef __nv_bfloat16 bf16;
 
 struct TrainWs {
-  bf16 *XC, *H[8], *FD, *HC, *dHC, *dFS, *dA, *dB, *dXE0, *dXE5, *dDE;
+  bf16 *XC, *H[8], *FD, *HC, *dHC, *dFS, *dH[8], *dXE0, *dXE5, *dDE;     // dH[l] = gradient w.r.t. the output of trunk layer l
   uint32_t* MB[8];          // packed ReLU masks of H0..H7, [M][8] words each (written by the forward epilogues)
   float* scratch;
   size_t scratch_bytes;
@@ -50,7 +50,8 @@ static void carve_train(void* ws, int64_t M, TrainWs* w) {
   w->H[5] = take(256); w->H[6] = take(256); w->H[7] = take(256);
   w->FD = take(320); w->HC = take(128);
   for (int i = 0; i < 8; ++i) w->MB[i] = reinterpret_cast<uint32_t*>(take(16));
-  w->dHC = take(128); w->dFS = take(272); w->dA = take(256); w->dB = take(256);
+  w->dHC = take(128); w->dFS = take(272);
+  for (int i = 0; i < 8; ++i) w->dH[i] = take(256);
   w->dXE0 = take(64); w->dXE5 = take(64); w->dDE = take(64);
   uint8_t* q = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(p), 256));
   w->scratch = reinterpret_cast<float*>(q);
@@ -70,6 +71,7 @@ static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimen
 extern int g_chain_dbg;
 #endif
 extern int g_chain_ring;
+int g_chain_bwd = 1;      // rn_set_flag(3, v): 1 = data gradients as one CTA-pair chain launch (chain_pair.cu), 0 = one launch per layer
 // rn_set_flag(0, v): 0 = one launch per layer, 1 = layer-chained persistent launch (activations round-trip through L2),
 // 2 = CTA-pair chain with shared-memory-resident activations (chain_pair.cu; default)
 int g_chain_fwd = 2;
@@ -145,47 +147,53 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   auto scratch_k = [&]() { return w.scratch + (size_t)(tn_k++) * region; };
   // heads: dHC, dFS[:, 256:272], rgb_linear grads
   RN_TRY(launch_heads_bwd(g_raw, w.HC, M, F, w.dHC, w.dFS, 272, w.heads_scratch, G + kG_WRgb, G + kG_BRgb, st));
-  // dir_linear: weight grads over [feat(256) | d_enc(27)] and bias
-  // one launch over the whole 320-wide input [feat(256) | d_enc(27) | 0]
+  if (g_chain_bwd) {
+    // ---- all data gradients in one launch: dHC -> dF -> dH7 -> ... -> dH0 ----
+    BwdLayerHost L[9];
+    L[0] = BwdLayerHost{W + kWD, 320, 320, 128, 0, w.dFS, 272, nullptr, 0, 0};            // d feat = dHC x WD[:, 0:256]
+    L[1] = BwdLayerHost{W + kWFS, 256, 256, 272, 0, w.dH[7], 256, w.MB[7], 2, 256};       // dH7 = [dF | dsigma] x WFS .* mask
+    for (int l = 7; l >= 1; --l) {
+      const bool skip = (l == 5);                                                         // dH4 = dH5 x W5[:, 63:] (packed cols 64..)
+      L[9 - l] = BwdLayerHost{W + trunk_w(l), skip ? 320 : 256, skip ? 320 : 256, 256, skip ? 64 : 0, w.dH[l - 1], 256,
+                              w.MB[l - 1], 0, 0};
+    }
+    RN_TRY(mlp_chain_pair_backward(L, 9, M, w.dHC, 128, 128, w.dFS, 272, 272, st));
+  } else {
+    RN_TRY(gemm_nn(w.dHC, 128, W + kWD, 320, w.dFS, 272, M, 256, 128, nullptr, st));
+    RN_TRY(gemm_nn(w.dFS, 272, W + kWFS, 256, w.dH[7], 256, M, 256, 272, w.MB[7], st));
+    for (int l = 7; l >= 1; --l)
+      RN_TRY(gemm_nn(w.dH[l], 256, W + trunk_w(l) + (l == 5 ? 64 : 0), l == 5 ? 320 : 256, w.dH[l - 1], 256, M, 256, 256,
+                     w.MB[l - 1], st));
+  }
+  // ---- weight / bias gradients: one split-K GEMM per layer, reduced together below ----
+  // dir_linear: one launch over the whole 320-wide input [feat(256) | d_enc(27) | 0]
   RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
   RN_TRY(tn_batch_add(&batch, ti, 0, 128, 0, 283, G + kG_WD, 283, G + kG_BD));
-  // d feat = dHC x WD[:, 0:256]  -> dFS[:, 0:256]   (feature_linear has no activation: no mask)
-  RN_TRY(gemm_nn(w.dHC, 128, W + kWD, 320, w.dFS, 272, M, 256, 128, nullptr, st));
-  if (g_dirs) RN_TRY(gemm_nn(w.dHC, 128, W + kWD + 256, 320, w.dDE, 64, M, 64, 128, nullptr, st));
-  // feature_linear + sigma_linear (row 256 of dFS^T): weights, biases
+  // feature_linear + sigma_linear (row 256 of dFS^T)
   RN_TRY(gemm_tn_launch(w.dFS, 272, 272, w.H[7], 256, 256, M, scratch_k(), w.scratch_bytes, &ti, st));
   RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 256, G + kG_WF, 256, G + kG_BF));
   RN_TRY(tn_batch_add(&batch, ti, 256, 1, 0, 256, G + kG_WSig, 256, G + kG_BSig));
-  // dH7 = [dF | dsigma] x WFS, masked by H7 > 0
-  RN_TRY(gemm_nn(w.dFS, 272, W + kWFS, 256, w.dA, 256, M, 256, 272, w.MB[7], st));
-  bf16* dY = w.dA;
-  bf16* dN = w.dB;
   for (int l = 7; l >= 1; --l) {
     if (l == 5) {
-      // input = XC = [x_enc(64) | H4(256)]
-      // one launch over the whole 320-wide input; the zero pad column 63 is dropped by the two scatters
-      RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
+      // input = XC = [x_enc(64) | H4(256)]: one launch over the 320-wide input; the zero pad column 63 is dropped
+      RN_TRY(gemm_tn_launch(w.dH[5], 256, 256, w.XC, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
       RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(5), 319, nullptr));
       RN_TRY(tn_batch_add(&batch, ti, 0, 256, 64, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5)));
-      RN_TRY(gemm_nn(dY, 256, W + kW5 + 64, 320, dN, 256, M, 256, 256, w.MB[4], st));
-      if (need_in) RN_TRY(gemm_nn(dY, 256, W + kW5, 320, w.dXE5, 64, M, 64, 256, nullptr, st));
     } else {
-      const bf16* in = w.H[l - 1];
-      const int ldin = ld_of(l - 1);
-      RN_TRY(gemm_tn_launch(dY, 256, 256, in, ldin, 256, M, scratch_k(), w.scratch_bytes, &ti, st));
+      RN_TRY(gemm_tn_launch(w.dH[l], 256, 256, w.H[l - 1], ld_of(l - 1), 256, M, scratch_k(), w.scratch_bytes, &ti, st));
       RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 256, G + trunk_gw(l), 256, G + trunk_gb(l)));
-      RN_TRY(gemm_nn(dY, 256, W + trunk_w(l), 256, dN, 256, M, 256, 256, w.MB[l - 1], st));
     }
-    bf16* t = dY; dY = dN; dN = t;
   }
   // layer 0: input = x_enc
-  RN_TRY(gemm_tn_launch(dY, 256, 256, w.XC, 320, 64, M, scratch_k(), w.scratch_bytes, &ti, st));
+  RN_TRY(gemm_tn_launch(w.dH[0], 256, 256, w.XC, 320, 64, M, scratch_k(), w.scratch_bytes, &ti, st));
   RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(0), 63, G + trunk_gb(0)));
   RN_REQUIRE(tn_k <= kTnLaunches);
   RN_TRY(gemm_tn_reduce_batch(batch, st));
   if (need_in) {
-    RN_TRY(gemm_nn(dY, 256, W + kW0, 64, w.dXE0, 64, M, 64, 256, nullptr, st));
-    if (!g_pts) { /* dirs only */ }
+    // gradients w.r.t. the encodings (pose optimisation only): three 64-wide data-gradient GEMMs
+    if (g_dirs) RN_TRY(gemm_nn(w.dHC, 128, W + kWD + 256, 320, w.dDE, 64, M, 64, 128, nullptr, st));
+    RN_TRY(gemm_nn(w.dH[5], 256, W + kW5, 320, w.dXE5, 64, M, 64, 256, nullptr, st));
+    RN_TRY(gemm_nn(w.dH[0], 256, W + kW0, 64, w.dXE0, 64, M, 64, 256, nullptr, st));
     RN_TRY(launch_encode_bwd(pts, dirs, M, group, w.dXE0, w.dXE5, w.dDE, g_pts, g_dirs, st));
   }
   return RN_OK;
@@ -203,6 +211,7 @@ int rn_set_flag(int flag, int value) {
   if (flag == 1) { g_chain_dbg = value; return RN_OK; }
 #endif
   if (flag == 2) { g_chain_ring = value; return RN_OK; }
+  if (flag == 3) { g_chain_bwd = value; return RN_OK; }
   return RN_ERR_INVALID_ARG;
 }
 

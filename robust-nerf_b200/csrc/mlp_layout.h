@@ -71,9 +71,10 @@ constexpr int relu_mask_bit(int j) { return (j & 1) ? 31 - (j >> 1) : 15 - (j >>
 
 // ---- activation workspace (bf16 elements per point) ----
 // training: XC[320] H0 H1 H2 H3 H5 H6 H7 (7 x 256) FD[320] HC[128] MB0..MB7 (packed masks) | backward: dHC[128] dFS[272] dA[256] dB[256]
-//           dXE0[64] dXE5[64] dDE[64]
+//           dXE0[64] dXE5[64] dDE[64]   (dA/dB of the per-layer design became one buffer per layer, dH0..dH7[256]: the
+//           chained data-gradient kernel produces all of them before the weight-gradient GEMMs read them)
 constexpr int kTrainFwdElems = 320 + 7 * 256 + 320 + 128 + 8 * 16;  // 2688 (last term: 8 packed ReLU masks, 32 B/point each)
-constexpr int kTrainBwdElems = 128 + 272 + 256 + 256 + 64 + 64 + 64; // 1104
+constexpr int kTrainBwdElems = 128 + 272 + 8 * 256 + 64 + 64 + 64;  // 2640: dHC dFS dH0..dH7 dXE0 dXE5 dDE
 constexpr int kInferElems = 320 + 256 + 256 + 320 + 128;            // 1280
 
 }  // namespace layout

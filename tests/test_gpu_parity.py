@@ -703,6 +703,40 @@ def test_chained_forward_equals_per_layer_forward(rn, dev):
         lib.rn_set_flag(0, 2)
 
 
+def test_chained_data_gradients_equal_per_layer(rn, dev):
+    """The CTA-pair data-gradient chain (one launch: dHC -> dF -> dH7 ... dH0, masks applied from the packed bits)
+    must reproduce the per-layer NN GEMM chain bit for bit -- same MMAs in the same K order, same mask, same bf16
+    rounding -- for parameter gradients and for the gradients w.r.t. points and directions (pose optimisation)."""
+    from robust_nerf_b200 import _lib
+    lib = _lib.lib()
+    w = O.make_weights(17, sharpen=True)
+    net = load_net(rn, w, dev)
+    rng = np.random.default_rng(9)
+    try:
+        for M in (1, 255, 256, 257, 1000, 40000, 151808):
+            pts = T(rng.uniform(-3, 3, (M, 3)).astype(np.float32), dev)
+            dirs = T(rng.standard_normal((M, 3)).astype(np.float32), dev)
+            gout = T(rng.standard_normal((M, 4)).astype(np.float32), dev)
+            outs = {}
+            for chain in (0, 1):
+                lib.rn_set_flag(3, chain)
+                net.zero_grad()
+                x = pts.clone().requires_grad_(True)
+                d = dirs.clone().requires_grad_(True)
+                raw = net.forward_raw(x, d, 1)
+                (raw * gout).sum().backward()
+                outs[("grad", chain)] = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+                outs[("dx", chain)] = x.grad.clone()
+                outs[("dd", chain)] = d.grad.clone()
+            torch.cuda.synchronize()
+            for k in ("grad", "dx", "dd"):
+                assert torch.isfinite(outs[(k, 1)]).all()
+                assert torch.equal(outs[(k, 0)], outs[(k, 1)]), (M, k, (outs[(k, 0)] - outs[(k, 1)]).abs().max().item())
+            assert outs[("grad", 1)].abs().max().item() > 0
+    finally:
+        lib.rn_set_flag(3, 1)
+
+
 def test_trainer_cuda_graph_step(rn, dev):
     """The CUDA-graph replayed step trains like the eager step (same kernels; only the Philox offsets differ)."""
     data, ds, sampler, pb = _scene_batch(rn, dev, 512, seed=21)
