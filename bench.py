@@ -323,7 +323,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": RAYS_PER_GPU * 9 * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / K_},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "rn::gemm_kernel<BN,MODE> (tcgen05 NT/NN/TN GEMMs of the MLP)",
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM kernels of the MLP: rn::mlp_chain_pair_kernel (forward chain), rn::mlp_chain_pair_bwd_kernel (data-gradient chain), rn::gemm_kernel<BN,2> (split-K weight gradients)",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic,
                          "peak_source": peaks["source"],

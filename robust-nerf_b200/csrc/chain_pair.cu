@@ -106,7 +106,7 @@ struct PairParams {
 // launching stream before each launch.  Every lane of an epilogue warp needs the SAME bias values: read through the
 // constant cache they cost no LSU/L1 cycles (a uniform LDG.128 per 4 columns made the load/store unit -- shared with the
 // tensor core's operand reads -- the bottleneck of the epilogue, profiles/r01_pair_experiments.md).
-__constant__ float2 c_pair_consts2[1664];
+__constant__ float2 c_pair_consts2[1664 + 128];   // + slack: the bias staging copies 256 floats from any bias offset
 #define c_pair_consts (reinterpret_cast<const float*>(c_pair_consts2))
 static_assert(layout::kF32Elems <= 3328, "constant staging buffer too small");
 
@@ -131,11 +131,13 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 
 // NG groups of 32 accumulator columns of one row: TMEM -> bias (+ReLU) -> bf16 -> in-place activation tile (+ mask, heads).
 // G-th group of the layer output = columns 32G..32G+31; bias_off / head_w_off are float offsets into the constants.
-// G0 (first group of this warp) is a template parameter: with it every bias / head-weight address is "uniform base +
-// immediate", which the compiler turns into uniform-datapath constant loads (one per warp, off the LSU and ALU pipes).
-template <int NG, int G0, int HEADS, bool RELU, bool WMASK, bool NOBIAS = false>
-__device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int bias_off, int head_w_off,
-                                              int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2, int dbg = 0) {
+// g0 = first group of this warp.  It stays a run-time value on purpose: all sixteen epilogue warps then execute ONE
+// instruction stream per layer type (a variant specialised per column quarter made the four warps of each scheduler run
+// four different code copies).
+template <int NG, int HEADS, bool RELU, bool WMASK, bool NOBIAS = false>
+__device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int g0, const float* s_bias,
+                                              int head_w_off, int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2,
+                                              int dbg = 0) {
   // every TMEM load of the item is issued before the first use: under a running MMA a tcgen05.ld takes several hundred
   // cycles (the tensor core's accumulator traffic has priority), and a load -> wait -> math sequence per 32 columns exposed
   // that latency once per group (profiles/r01_pair_experiments.md)
@@ -146,10 +148,8 @@ __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, 
   float2 hh0 = make_float2(0.f, 0.f), hh1 = make_float2(0.f, 0.f), hh2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    constexpr int kG0 = G0;
-    const int G = kG0 + g;
+    const int G = g0 + g;
     uint8_t* box = s_tile + (G >> 1) * kChunkBytes + row * 128;
-    const int b2 = (bias_off >> 1) + G * 16;           // float2 index of this group's first bias pair
     const int w2 = (head_w_off >> 1) + G * 16;         // float2 index of this group's first head-weight pair
     uint32_t outbits = 0u;
 #pragma unroll
@@ -157,14 +157,15 @@ __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, 
       const int lchunk = (G & 1) * 4 + cc;
       uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
       uint32_t packed[4];
+      // the bias of these 8 columns: two broadcast LDS.128 from the per-layer staging buffer.  (Indexed constant loads of
+      // the 13 KB bias table were a third of the epilogue's stall samples, profiles/r01_pair_chain_ncu.md.)
+      const float4 bA = NOBIAS ? make_float4(0.5f, 0.25f, 0.5f, 0.25f) : *reinterpret_cast<const float4*>(s_bias + G * 32 + cc * 8);
+      const float4 bB = NOBIAS ? make_float4(0.5f, 0.25f, 0.5f, 0.25f) : *reinterpret_cast<const float4*>(s_bias + G * 32 + cc * 8 + 4);
+      const float2 bsel[4] = {make_float2(bA.x, bA.y), make_float2(bA.z, bA.w), make_float2(bB.x, bB.y), make_float2(bB.z, bB.w)};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = cc * 4 + e;                       // column pair within the group
-#ifdef RN_EXPERIMENTS
-        const uint64_t r = fadd2(v[g][2 * i], v[g][2 * i + 1], NOBIAS ? make_float2(0.5f, 0.25f) : c_pair_consts2[b2 + i]);
-#else
-        const uint64_t r = fadd2(v[g][2 * i], v[g][2 * i + 1], c_pair_consts2[b2 + i]);
-#endif
+        const uint64_t r = fadd2(v[g][2 * i], v[g][2 * i + 1], bsel[e]);
         float lo, hi;
         asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
         __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
@@ -213,6 +214,13 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
   uint64_t* staged = bars + 16;          // [2]  epilogue -> store warp (training)
   uint64_t* store_done = bars + 18;      // [2]  store warp -> epilogue: the tile has been read out, overwrite allowed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  // per-layer bias staging [256] fp32 in the last KiB of the allocation -- the alignment slack, which is free because the
+  // dynamic shared memory of a kernel without static shared memory starts 1 KiB-aligned (checked: trap otherwise)
+  float* s_bias = reinterpret_cast<float*>(smem + 2 * kActBytes + 2 * kAuxBytes + kNBStages * kBStageBytes + kPairMisc);
+  if (smem != smem_raw) {
+    if (threadIdx.x == 0) printf("rnerf_b200: dynamic shared memory is not 1 KiB aligned (block %d)\n", (int)blockIdx.x);
+    __trap();
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -350,6 +358,11 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
       for (int l = 0; l < p.n_layers; ++l) {
         const PairLayer L = p.L[l];
+        // stage this layer's bias: every epilogue warp has finished the previous layer (first barrier), 256 threads copy
+        // one value each out of the constant table, and the copies are visible to all (second barrier)
+        named_bar_sync(5, 512);
+        if (threadIdx.x - 64 < 256) s_bias[threadIdx.x - 64] = c_pair_consts[L.bias_off + (threadIdx.x - 64)];
+        named_bar_sync(5, 512);
         for (int slot = 0; slot < tiles_here; ++slot) {
           const uint32_t i = slot ? it1++ : it0++;
           const int64_t gr = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128 + row;
@@ -370,17 +383,16 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
             for (int g = 0; g < (L.n >> 7); ++g) { uint32_t v[32]; tmem_ld_x32(t_addr + g * 32, v); tmem_ld_wait(); if (v[0] == 0x7fc12345u) mb[0] ^= v[1]; }
           }
           else {
-#define RN_EPI(CQ)                                                                                                          \
-  if (L.n == 256) {                                                                                                         \
-    if (L.heads == 1) pair_epilogue<2, 2 * CQ, 1, true, TRAIN>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2, p.dbg); \
-    else if (L.relu && RN_PDBG(p, 64)) pair_epilogue<2, 2 * CQ, 0, true, TRAIN, true>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);  \
-    else if (L.relu) pair_epilogue<2, 2 * CQ, 0, true, TRAIN>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);  \
-    else pair_epilogue<2, 2 * CQ, 0, false, false>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);     \
-  } else {                                                                                                                  \
-    pair_epilogue<1, CQ, 3, true, false>(t_addr, s_tile, row, L.bias_off, L.head_w_off, 128, mb, h0, h1, h2, p.dbg);               \
-  }
-            if (cq == 0) { RN_EPI(0) } else if (cq == 1) { RN_EPI(1) } else if (cq == 2) { RN_EPI(2) } else { RN_EPI(3) }
-#undef RN_EPI
+            if (L.n == 256) {
+              if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);
+#ifdef RN_EXPERIMENTS
+              else if (L.relu && (p.dbg & 64)) pair_epilogue<2, 0, true, TRAIN, true>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);
+#endif
+              else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);
+              else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);
+            } else {
+              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, s_bias, L.head_w_off, 128, mb, h0, h1, h2, p.dbg);
+            }
           }
           RN_TL(tl, 600 + l * 10 + slot);                  // math done
           tcgen05_fence_before();

@@ -11,6 +11,20 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __constant__ float2 c_bias2[128];
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -32,11 +46,18 @@ __device__ __forceinline__ uint64_t fadd2(uint32_t a_lo, uint32_t a_hi, float2 b
 // VARIANT bits: 1 = scalar FADD instead of FADD2, 2 = truncating PRMT instead of F2FP, 4 = no HMNMX2, 8 = no STS,
 // 16 = no fence.proxy.async, 32 = only one LDTM per item consumed (math skipped)
 template <int VARIANT>
-__global__ void __launch_bounds__(640, 1) epi_kernel(int items, long long* out_cycles, uint32_t* sink, int spin_mode) {
+__global__ void __launch_bounds__(640, 1) epi_kernel(int items, long long* out_cycles, uint32_t* sink, int spin_mode, int mma_depth) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t mma_bar[16];
+  __shared__ volatile int epi_done;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar[i])));
+    epi_done = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -53,7 +74,7 @@ __global__ void __launch_bounds__(640, 1) epi_kernel(int items, long long* out_c
     const int q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     const long long t0 = clock64();
     for (int it = 0; it < items; ++it) {
-      const int slot = it & 1;
+      const int slot = mma_depth ? 0 : (it & 1);
       uint8_t* s_tile = smem + slot * 65536;
       const uint32_t t_addr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + cq * 64;
 #pragma unroll
@@ -93,7 +114,29 @@ __global__ void __launch_bounds__(640, 1) epi_kernel(int items, long long* out_c
       if (!(VARIANT & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
     }
-    if (threadIdx.x == 0) out_cycles[blockIdx.x] = clock64() - t0;
+    if (threadIdx.x == 0) { out_cycles[blockIdx.x] = clock64() - t0; epi_done = 1; }
+  }
+  // concurrent MMA stream into the OTHER accumulator columns (as the other tile slot of the chain kernel), at most
+  // mma_depth chunks of 4 MMAs (512 cycles each) in flight
+  if (warp == 16 && mma_depth > 0) {
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 65536);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int c = 0;
+    while (!epi_done && c < 4000000) {
+      if (c >= mma_depth) {       // wait for chunk c - mma_depth
+        const int j = c - mma_depth; const uint32_t bar = smem_u32(&mma_bar[j & 15]), par = (j >> 4) & 1; uint32_t ok = 0;
+        while (!ok) asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(par) : "memory");
+      }
+      if (elect_one()) {
+        const uint32_t d = tmem_base + 256;       // columns 256..511: never read by the epilogue warps
+        for (int k = 0; k < 4; ++k)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                       ::"r"(d), "l"(desc_sw128(a_addr + k * 32)), "l"(desc_sw128(b_addr + k * 32)), "r"(idesc), "r"(1) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar[c & 15])) : "memory");
+      }
+      __syncwarp();
+      ++c;
+    }
   }
   __shared__ uint64_t spin_bar;
   __shared__ volatile int done_flag;
@@ -123,14 +166,14 @@ __global__ void __launch_bounds__(640, 1) epi_kernel(int items, long long* out_c
   if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 template <int VARIANT>
-static void run(const char* name, int spin_mode = 0) {
+static void run(const char* name, int spin_mode = 0, int mma_depth = 0) {
   const int items = 4000, grid = 148, smem = 2 * 65536 + 1024;
   auto kern = epi_kernel<VARIANT>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long* d_c; uint32_t* d_s;
   CK(cudaMalloc(&d_c, grid * 8)); CK(cudaMalloc(&d_s, 4));
-  kern<<<grid, 640, smem>>>(items, d_c, d_s, spin_mode);
-  kern<<<grid, 640, smem>>>(items, d_c, d_s, spin_mode);
+  kern<<<grid, 640, smem>>>(items, d_c, d_s, spin_mode, mma_depth);
+  kern<<<grid, 640, smem>>>(items, d_c, d_s, spin_mode, mma_depth);
   CK(cudaDeviceSynchronize());
   std::vector<long long> c(grid);
   CK(cudaMemcpy(c.data(), d_c, grid * 8, cudaMemcpyDeviceToHost));
@@ -157,5 +200,13 @@ int main() {
   run<0>("full + 3 warps spinning on try_wait with suspend hint", 2);
   run<0>("full + 3 warps spinning on try_wait (lane 0 only)", 3);
   run<0>("full + 3 warps spinning on try_wait + nanosleep(64)", 4);
+  run<32>("LDTM + wait only, MMAs in flight: 1 chunk (4 MMAs)", 0, 1);
+  run<32>("LDTM + wait only, MMAs in flight: 2 chunks", 0, 2);
+  run<32>("LDTM + wait only, MMAs in flight: 4 chunks", 0, 4);
+  run<32>("LDTM + wait only, MMAs in flight: 8 chunks", 0, 8);
+  run<0>("full epilogue, MMAs in flight: 1 chunk", 0, 1);
+  run<0>("full epilogue, MMAs in flight: 2 chunks", 0, 2);
+  run<0>("full epilogue, MMAs in flight: 4 chunks", 0, 4);
+  run<0>("full epilogue, MMAs in flight: 8 chunks", 0, 8);
   return 0;
 }
