@@ -43,6 +43,8 @@ def test_sass_uses_blackwell_tensor_path(rn):
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
         assert mnemonic in sass, mnemonic
+    assert "UTCHMMA.2CTA" in sass          # the chain kernels issue cta_group::2 MMAs (M = 256 per CTA pair)
+    assert "FADD2" in sass and "HMNMX2" in sass     # packed two-column epilogue arithmetic
     assert "HMMA.16816" not in sass        # no legacy mma.sync path
 
 
