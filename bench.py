@@ -315,7 +315,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "rays_per_gpu": RAYS_PER_GPU, "global_batch_rays": world * RAYS_PER_GPU,
                        "samples": f"{NC}+{NF}", "mlp": "8x256, PE L=10/4, bf16 tcgen05 operands, fp32 accumulate",
                        "parallelism": f"dp{world} (one all-reduce of the flat gradient buffer per step)" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: 7.7 GB of activations streamed per step vs 126 MB L2, no flush needed",
+                       "l2": "inputs larger than L2: 11 GB of activations and activation gradients streamed per step vs 126 MB L2, no flush needed",
                        "launch": "CUDA graph replay of the whole step" if use_graph else "eager (one launch per kernel)",
                        "eager_ms_per_step": eager_ms_per_step,
                        "loss": loss_val},
