@@ -202,27 +202,44 @@ heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restri
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
   const int64_t pstride = (int64_t)gridDim.x * (kHeadsBwdThreads / 16);
-  for (int64_t m = (int64_t)blockIdx.x * (kHeadsBwdThreads / 16) + pl; m < M; m += pstride) {
-    const float4 g = __ldg(g_raw + m);
-    const uint4 hv = __ldcs(reinterpret_cast<const uint4*>(HC + m * 128 + cg * 8));
-    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-    uint32_t outw[4];
+  // four points per thread and iteration, all loads issued before any dependent math: one uint4 per thread in flight
+  // (16 KB per SM) left this HBM-bound kernel at half of its bandwidth floor
+  constexpr int kU = 4;
+  for (int64_t m0 = (int64_t)blockIdx.x * (kHeadsBwdThreads / 16) + pl; m0 < M; m0 += kU * pstride) {
+    float4 gv[kU];
+    uint4 hvv[kU];
 #pragma unroll
-    for (int e2 = 0; e2 < 4; ++e2) {
-      const float h0 = bf16_lo(hw[e2]), h1 = bf16_hi(hw[e2]);
-      acc[0][2 * e2] = fmaf(g.x, h0, acc[0][2 * e2]); acc[0][2 * e2 + 1] = fmaf(g.x, h1, acc[0][2 * e2 + 1]);
-      acc[1][2 * e2] = fmaf(g.y, h0, acc[1][2 * e2]); acc[1][2 * e2 + 1] = fmaf(g.y, h1, acc[1][2 * e2 + 1]);
-      acc[2][2 * e2] = fmaf(g.z, h0, acc[2][2 * e2]); acc[2][2 * e2 + 1] = fmaf(g.z, h1, acc[2][2 * e2 + 1]);
-      const float d0 = h0 > 0.f ? (g.x * w[0][2 * e2] + g.y * w[1][2 * e2] + g.z * w[2][2 * e2]) : 0.f;
-      const float d1 = h1 > 0.f ? (g.x * w[0][2 * e2 + 1] + g.y * w[1][2 * e2 + 1] + g.z * w[2][2 * e2 + 1]) : 0.f;
-      outw[e2] = pack_bf16(d0, d1);
+    for (int u = 0; u < kU; ++u) {
+      const int64_t m = m0 + u * pstride;
+      if (m < M) {
+        gv[u] = __ldg(g_raw + m);
+        hvv[u] = __ldcs(reinterpret_cast<const uint4*>(HC + m * 128 + cg * 8));
+      }
     }
-    *reinterpret_cast<uint4*>(dHC + m * 128 + cg * 8) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
-    if (cg == 0) {
-      bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z;
-      *reinterpret_cast<uint4*>(dFS + m * ldfs + 256) = make_uint4(pack_bf16(g.w, 0.f), 0, 0, 0);
-    } else if (cg == 1) {
-      *reinterpret_cast<uint4*>(dFS + m * ldfs + 264) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t m = m0 + u * pstride;
+      if (m >= M) break;
+      const float4 g = gv[u];
+      const uint32_t hw[4] = {hvv[u].x, hvv[u].y, hvv[u].z, hvv[u].w};
+      uint32_t outw[4];
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        const float h0 = bf16_lo(hw[e2]), h1 = bf16_hi(hw[e2]);
+        acc[0][2 * e2] = fmaf(g.x, h0, acc[0][2 * e2]); acc[0][2 * e2 + 1] = fmaf(g.x, h1, acc[0][2 * e2 + 1]);
+        acc[1][2 * e2] = fmaf(g.y, h0, acc[1][2 * e2]); acc[1][2 * e2 + 1] = fmaf(g.y, h1, acc[1][2 * e2 + 1]);
+        acc[2][2 * e2] = fmaf(g.z, h0, acc[2][2 * e2]); acc[2][2 * e2 + 1] = fmaf(g.z, h1, acc[2][2 * e2 + 1]);
+        const float d0 = h0 > 0.f ? (g.x * w[0][2 * e2] + g.y * w[1][2 * e2] + g.z * w[2][2 * e2]) : 0.f;
+        const float d1 = h1 > 0.f ? (g.x * w[0][2 * e2 + 1] + g.y * w[1][2 * e2 + 1] + g.z * w[2][2 * e2 + 1]) : 0.f;
+        outw[e2] = pack_bf16(d0, d1);
+      }
+      *reinterpret_cast<uint4*>(dHC + m * 128 + cg * 8) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+      if (cg == 0) {
+        bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z;
+        *reinterpret_cast<uint4*>(dFS + m * ldfs + 256) = make_uint4(pack_bf16(g.w, 0.f), 0, 0, 0);
+      } else if (cg == 1) {
+        *reinterpret_cast<uint4*>(dFS + m * ldfs + 264) = make_uint4(0, 0, 0, 0);
+      }
     }
   }
   // fixed-order reduction over the 16 point lanes of the CTA
