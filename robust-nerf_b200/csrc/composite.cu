@@ -139,8 +139,12 @@ composite_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
   }
 }
 
-template <bool RAW, int MAXR>
-__global__ void __launch_bounds__(kCompWarps * 32)
+// LEAN: the training configuration (gradient from rgb_map only: no noise, no depth / weight gradients in, no ray-direction
+// gradient out).  Three of the ten per-round register arrays disappear (noise, depth, sigma -- the sigma > 0 test is
+// folded into the stored interval length), which takes the S = 384 instance from 151 to <= 128 registers and from one
+// to two resident CTAs per SM (profiles/r01_ncu_full_hbm_kernels.raw.csv: the kernel is latency-bound at 12 % warps active).
+template <bool RAW, int MAXR, bool LEAN>
+__global__ void __launch_bounds__(kCompWarps * 32, LEAN ? (MAXR <= 4 ? 4 : (MAXR <= 6 ? 3 : (MAXR <= 12 ? 2 : 1))) : 1)
 composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma, const float4* __restrict__ raw4,
                      const float* __restrict__ z, const float* __restrict__ rd, const float* __restrict__ noise,
                      int64_t B, int S, int white, const float* __restrict__ g_map, const float* __restrict__ g_depth,
@@ -163,9 +167,14 @@ composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
       c0[r] = c1[r] = c2[r] = 0.f; sg[r] = 0.f; ds[r] = 0.f; G[r] = 0.f; zz[r] = 0.f; nzv[r] = 0.f;
       const int s = r * 32 + lane;
       if (r < rounds && s < S) {
-        const Fetched f = fetch_sample<RAW>(rgb, sigma, raw4, z, noise, base, s, S);
-        c0[r] = f.a; c1[r] = f.b; c2[r] = f.c; sg[r] = f.sig; zz[r] = f.z; ds[r] = f.zn; nzv[r] = f.nz;
-        G[r] = g_w ? __ldcs(g_w + base + s) : 0.f;
+        const Fetched f = fetch_sample<RAW>(rgb, sigma, raw4, z, LEAN ? nullptr : noise, base, s, S);
+        c0[r] = f.a; c1[r] = f.b; c2[r] = f.c; sg[r] = f.sig;
+        if (LEAN) {
+          ds[r] = (s == S - 1) ? 1e10f : __fsub_rn(f.zn, f.z);      // interval length dz (rendering.py:67-72)
+        } else {
+          zz[r] = f.z; ds[r] = f.zn; nzv[r] = f.nz;
+          G[r] = g_w ? __ldcs(g_w + base + s) : 0.f;
+        }
       }
     }
     float carry = 1.0f;
@@ -177,7 +186,14 @@ composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
         const int s = r * 32 + lane;
         const bool valid = s < S;
         float t = 1.f;
-        if (valid) {
+        if (valid && LEAN) {
+          if (RAW) { c0[r] = sigmoidf_acc(c0[r]); c1[r] = sigmoidf_acc(c1[r]); c2[r] = sigmoidf_acc(c2[r]); }
+          const float dist = __fmul_rn(ds[r], nrm);                                                // rendering.py:75
+          al[r] = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(sg[r], 0.f), dist)));
+          t = __fadd_rn(__fsub_rn(1.0f, al[r]), 1e-10f);
+          ds[r] = (sg[r] > 0.f) ? dist : 0.f;             // d relu(sigma) folded in: sigma itself is not needed again
+          G[r] = gm0 * c0[r] + gm1 * c1[r] + gm2 * c2[r] + gconst;
+        } else if (valid) {
           Fetched f;
           f.a = c0[r]; f.b = c1[r]; f.c = c2[r]; f.sig = sg[r]; f.z = zz[r]; f.zn = ds[r]; f.nz = nzv[r];
           const SampleIn in = activate_sample<RAW>(f, noise != nullptr, s, S, nrm);
@@ -209,9 +225,9 @@ composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
           const float t = __fadd_rn(__fsub_rn(1.0f, al[r]), 1e-10f);
           const float d_alpha = G[r] * Tn[r] - R / t;
           const float one_m = 1.0f - al[r];
-          const float dsig = (sg[r] > 0.f) ? d_alpha * ds[r] * one_m : 0.f;
+          const float dsig = LEAN ? d_alpha * ds[r] * one_m : ((sg[r] > 0.f) ? d_alpha * ds[r] * one_m : 0.f);
           // dL/ddist * dz  (dz = dist / |d|)
-          dn += d_alpha * fmaxf(sg[r], 0.f) * one_m * (ds[r] / nrm);
+          if (!LEAN) dn += d_alpha * fmaxf(sg[r], 0.f) * one_m * (ds[r] / nrm);
           const float g0 = w * gm0, g1 = w * gm1, g2 = w * gm2;
           if (RAW) {
             float4 o;
@@ -225,7 +241,7 @@ composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
         }
       }
     }
-    if (d_rd) {
+    if (!LEAN && d_rd) {
       dn = warp_sum(dn);
       if (lane < 3) d_rd[b * 3 + lane] = dn * rd[b * 3 + lane] / nrm;
     }
@@ -260,9 +276,21 @@ static int launch_bwd(int rounds, dim3 grid, cudaStream_t st, const float* rgb, 
                       const float* z, const float* rd, const float* noise, int64_t B, int S, int white, const float* g_map,
                       const float* g_depth, const float* g_acc, const float* g_w, float* d_rgb, float* d_sigma,
                       float4* d_raw4, float* d_rd) {
-#define RN_BWD_CASE(R)                                                                                                  \
-  composite_bwd_kernel<RAW, R><<<grid, kCompWarps * 32, 0, st>>>(rgb, sigma, raw4, z, rd, noise, B, S, white, g_map,    \
-                                                                 g_depth, g_acc, g_w, d_rgb, d_sigma, d_raw4, d_rd)
+  const bool lean = !noise && !g_depth && !g_w && !d_rd;
+  // persistent grid-stride kernel: one wave of exactly the CTAs that are resident at this instantiation's register count
+  auto launch = [&](auto kern) {
+    int per_sm = 1;                        // host-side query (no device work; legal during stream capture)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCompWarps * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int64_t g = (int64_t)num_sms() * per_sm;
+    if (g > grid.x || grid.x <= 2 * g) g = grid.x;      // small batches: one CTA per 8 rays, let the hardware schedule the waves
+    kern<<<(unsigned)g, kCompWarps * 32, 0, st>>>(rgb, sigma, raw4, z, rd, noise, B, S, white, g_map, g_depth, g_acc, g_w, d_rgb,
+                                                  d_sigma, d_raw4, d_rd);
+  };
+#define RN_BWD_CASE(R)                                                     \
+  do {                                                                     \
+    if (lean) launch(composite_bwd_kernel<RAW, R, true>);                  \
+    else launch(composite_bwd_kernel<RAW, R, false>);                      \
+  } while (0)
   if (rounds <= 2) RN_BWD_CASE(2);
   else if (rounds <= 4) RN_BWD_CASE(4);
   else if (rounds <= 6) RN_BWD_CASE(6);
@@ -306,7 +334,7 @@ int rn_composite_bwd(const float* rgb, const float* sigma, const float* raw4, co
   RN_REQUIRE((raw4 != nullptr) != (rgb != nullptr && sigma != nullptr));
   RN_REQUIRE(raw4 ? (d_raw4 != nullptr) : (d_rgb != nullptr && d_sigma != nullptr));
   const int rounds = (S + 31) / 32;
-  const int grid = (int)(ceil_div(B, kCompWarps) < (int64_t)num_sms() * 4 ? ceil_div(B, kCompWarps) : (int64_t)num_sms() * 4);
+  const int grid = (int)(ceil_div(B, kCompWarps) < (int64_t)num_sms() * 8 ? ceil_div(B, kCompWarps) : (int64_t)num_sms() * 8);
   int rc;
   if (raw4)
     rc = launch_bwd<true>(rounds, dim3(grid), (cudaStream_t)stream, nullptr, nullptr, (const float4*)raw4, z, rd, noise, B, S,
