@@ -100,6 +100,11 @@ int rn_raygen_se3_bwd(const int64_t* image_idx, const float* pixel_uv, int64_t B
  * image = idx / (H*W), v = (idx % (H*W)) / W, u = idx % W; rgb gathered from images[N,H,W,3]. */
 int rn_pixel_gather(const int64_t* flat_idx /*[B]*/, int64_t B, int H, int W, const float* images /*or NULL*/,
                     int64_t* image_idx_out, float* pixel_uv_out, float* target_rgb_out /*or NULL*/, rn_stream_t stream);
+/* Same with the training images kept as uint8 [N,H,W,3] (a quarter of the fp32 table: 192 MB instead of 768 MB at
+ * 100 x 800^2).  Lossless for the reference's data: data.py:118-135 quantises every image to uint8 and divides by
+ * 255.0 in fp32, which is exactly what this gather does (rgb = float(k) / 255.0f, correctly rounded). */
+int rn_pixel_gather_u8(const int64_t* flat_idx /*[B]*/, int64_t B, int H, int W, const uint8_t* images_u8,
+                       int64_t* image_idx_out, float* pixel_uv_out, float* target_rgb_out, rn_stream_t stream);
 
 /* ---- sampling: rays.py:145-333 ---- */
 /* z = lower + (upper-lower)*t_rand over the base depths z_base (linspace built by the caller,

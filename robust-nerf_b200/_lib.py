@@ -44,6 +44,7 @@ _SIGS = {
     "rn_raygen_se3_bwd": (c_int, [_P, _P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P]),
     "rn_pixel_gather": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
+    "rn_pixel_gather_u8": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
     "rn_stratified_fwd": (c_int, [_P, _P, c_int64, _P, c_int, _P, _P, _P, _P]),
     "rn_points_fwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     "rn_points_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),

@@ -340,6 +340,22 @@ __global__ void pixel_gather_kernel(const int64_t* __restrict__ flat, int64_t B,
   }
 }
 
+// uint8 image table: rgb = k / 255.0f in fp32, the reference's own conversion (data.py:134-136)
+__global__ void pixel_gather_u8_kernel(const int64_t* __restrict__ flat, int64_t B, int H, int W,
+                                       const uint8_t* __restrict__ images, int64_t* __restrict__ img_out,
+                                       float* __restrict__ uv_out, float* __restrict__ rgb_out) {
+  const int64_t hw = (int64_t)H * W;
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = flat[b];
+    const int64_t im = f / hw, rem = f - im * hw;
+    const int64_t v = rem / W, u = rem - v * W;
+    img_out[b] = im;
+    uv_out[b * 2] = (float)u; uv_out[b * 2 + 1] = (float)v;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rgb_out[b * 3 + k] = __fdiv_rn((float)images[f * 3 + k], 255.0f);
+  }
+}
+
 }  // namespace rn
 
 using namespace rn;
@@ -433,6 +449,15 @@ int rn_pixel_gather(const int64_t* flat, int64_t B, int H, int W, const float* i
   if (B == 0) return RN_OK;
   RN_REQUIRE(flat && img_out && uv_out && B >= 0 && H > 0 && W > 0);
   pixel_gather_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(flat, B, H, W, images, img_out, uv_out, rgb_out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_pixel_gather_u8(const int64_t* flat, int64_t B, int H, int W, const uint8_t* images, int64_t* img_out, float* uv_out,
+                       float* rgb_out, rn_stream_t stream) {
+  if (B == 0) return RN_OK;
+  RN_REQUIRE(flat && images && img_out && uv_out && rgb_out && B >= 0 && H > 0 && W > 0);
+  pixel_gather_u8_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(flat, B, H, W, images, img_out, uv_out, rgb_out);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

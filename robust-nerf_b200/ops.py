@@ -148,11 +148,33 @@ def pixel_gather(flat_idx, H, W, images=None):
     img = torch.empty(B, device=flat.device, dtype=torch.int64)
     uv = torch.empty((B, 2), device=flat.device, dtype=torch.float32)
     rgb = None
+    if images is not None and images.dtype == torch.uint8:
+        # uint8 image table: rgb = k / 255 in fp32 inside the gather (exactly the reference's conversion, data.py:134-136)
+        images = require_cuda(images, "images", torch.uint8)
+        rgb = torch.empty((B, 3), device=flat.device, dtype=torch.float32)
+        call("rn_pixel_gather_u8", ptr(flat), B, int(H), int(W), ptr(images), ptr(img), ptr(uv), ptr(rgb), stream_ptr())
+        return img, uv, rgb
     if images is not None:
         images = _f32(images, "images")
         rgb = torch.empty((B, 3), device=flat.device, dtype=torch.float32)
     call("rn_pixel_gather", ptr(flat), B, int(H), int(W), ptr(images), ptr(img), ptr(uv), ptr(rgb), stream_ptr())
     return img, uv, rgb
+
+
+def quantize_images(images: torch.Tensor) -> torch.Tensor:
+    """fp32 images in [0,1] -> uint8, refusing anything that is not exactly k/255 (lossless by construction for data
+    loaded the reference's way, data.py:118-136)."""
+    q = torch.round(images * 255.0).clamp_(0, 255).to(torch.uint8)
+    if not torch.equal(dequantize_images(q), images.to(torch.float32)):
+        raise ValueError("images are not exact multiples of 1/255: uint8 storage would not be lossless")
+    return q
+
+
+def dequantize_images(q: torch.Tensor) -> torch.Tensor:
+    """uint8 -> fp32 k / 255 with a correctly rounded DIVISION, as numpy does in the reference (data.py:134-136) and as
+    the gather kernel does.  (torch's CUDA `tensor / python_scalar` multiplies by the reciprocal, which differs in the
+    last bit for some k; a tensor divisor takes the true-division path.)"""
+    return q.to(torch.float32) / torch.full((), 255.0, device=q.device, dtype=torch.float32)
 
 
 # --------------------------------------------------------------------------------------------

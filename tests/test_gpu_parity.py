@@ -785,6 +785,34 @@ def test_empty_and_ragged_inputs(rn, dev):
     assert pts.shape == (0, 8, 3) and z.shape == (0, 8)
 
 
+def test_uint8_image_table_is_lossless(rn, dev):
+    """training images kept as uint8, /255 inside the gather kernel.  Bit-exact against the
+    reference's fp32 table for images loaded its way (k/255 in fp32, data.py:134-136); non-k/255 images are refused."""
+    from robust_nerf_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(3)
+    N_, H, W = 5, 37, 53
+    u8 = torch.randint(0, 256, (N_, H, W, 3), device=dev, dtype=torch.uint8, generator=g)
+    f32 = torch.from_numpy(u8.cpu().numpy().astype(np.float32) / 255.0).to(dev)     # np.array(img, float32) / 255.0 (data.py:134-136)
+    assert torch.equal(ops.quantize_images(f32), u8)
+    idx = torch.randint(0, N_ * H * W, (4096,), device=dev, generator=g)
+    img_a, uv_a, rgb_a = ops.pixel_gather(idx, H, W, f32)
+    img_b, uv_b, rgb_b = ops.pixel_gather(idx, H, W, u8)
+    assert torch.equal(img_a, img_b) and torch.equal(uv_a, uv_b) and torch.equal(rgb_a, rgb_b)
+    assert torch.equal(rgb_b, f32.reshape(-1, 3)[idx])
+
+    class D:
+        pass
+    d = D(); d.images = f32; d.poses = rn.hemisphere_poses(N_, seed=2, device=dev); d.H, d.W, d.focal = H, W, 50.0
+    ds8, sm8 = rn.create_pixel_dataset(d, uint8_images=True)
+    ds32, sm32 = rn.create_pixel_dataset(d)
+    assert ds8.images.dtype == torch.uint8 and ds8.images.numel() * 4 == ds32.images.numel() * ds32.images.element_size()
+    assert torch.equal(ds8.target_rgb, ds32.target_rgb)
+    b8, b32 = sm8.batch_from_indices(idx), sm32.batch_from_indices(idx)
+    assert torch.equal(b8.target_rgb, b32.target_rgb) and torch.equal(b8.pixel_coords, b32.pixel_coords)
+    with pytest.raises(ValueError):
+        ops.quantize_images(torch.rand(2, 4, 4, 3, device=dev))
+
+
 def test_render_views_tile_sharded(rn, dev):
     """Tile-sharded test-view rendering (config 4): the union of the ranks' tiles equals the single-rank
     render, every ray is rendered exactly once, no collective involved."""
