@@ -142,21 +142,43 @@ def sample_along_rays(rays_o, rays_d, near, far, num_samples, perturb=True, lind
     return pts, z
 
 
+def _warp_scan(x: np.ndarray):
+    """Inclusive fp32 prefix sums over the last axis in the order a 32-lane warp scan produces them, and the total.
+
+    torch's own summation order is backend-dependent (pairwise / vectorised sum and a sequential cumsum on the CPU,
+    a parallel block scan on CUDA), so the oracle has to fix one; it fixes the order of the CUDA kernel
+    (csrc/sampling.cu: warp_build_cdf): with C = ceil(n / 32), lane l owns the contiguous chunk [l*C, (l+1)*C) and sums it
+    left to right; the 32 lane totals go through a Kogge-Stone scan (offsets 1, 2, 4, 8, 16: v[l] += v[l - o] for
+    l >= o, all lanes at once); element k = l*C + j gets offset[l] + local_prefix[j], offset[0] = 0.
+    """
+    x = np.asarray(x, dtype=F32)
+    n = x.shape[-1]
+    C = (n + 31) // 32
+    pad = np.zeros((*x.shape[:-1], 32 * C - n), dtype=F32)
+    xp = np.concatenate([x, pad], -1).reshape(*x.shape[:-1], 32, C)
+    local = np.empty_like(xp)
+    run = np.zeros(xp.shape[:-1], dtype=F32)
+    for j in range(C):
+        run = (run + xp[..., j]).astype(F32)
+        local[..., j] = run
+    v = run.copy()                                              # lane totals
+    for o in (1, 2, 4, 8, 16):
+        shifted = np.zeros_like(v)
+        shifted[..., o:] = v[..., :-o]
+        v = np.where(np.arange(32) >= o, (v + shifted).astype(F32), v).astype(F32)
+    excl = np.zeros_like(v)
+    excl[..., 1:] = v[..., :-1]
+    out = (excl[..., None] + local).astype(F32).reshape(*x.shape[:-1], 32 * C)[..., :n]
+    return out, v[..., 31].copy()
+
+
 def _seq_sum(x: np.ndarray) -> np.ndarray:
-    """Sequential left-to-right fp32 sum over the last axis (the kernel's order)."""
-    acc = x[..., 0].astype(F32).copy()
-    for k in range(1, x.shape[-1]):
-        acc = (acc + x[..., k]).astype(F32)
-    return acc
+    """Total of the last axis in the warp-scan order (name kept: it is the kernel's order)."""
+    return _warp_scan(x)[1]
 
 
 def _seq_cumsum(x: np.ndarray) -> np.ndarray:
-    out = np.empty_like(x, dtype=F32)
-    acc = np.zeros(x.shape[:-1], dtype=F32)
-    for k in range(x.shape[-1]):
-        acc = (acc + x[..., k]).astype(F32)
-        out[..., k] = acc
-    return out
+    return _warp_scan(x)[0]
 
 
 def sample_pdf(bins, weights, num_samples, det=False, u=None, return_inds=False):

@@ -7,7 +7,7 @@
 // sample_pdf / sample_hierarchical are warp-per-ray kernels: the ray's bins, cdf and merge buffer
 // live in shared memory, each lane inverts the cdf for Nf/32 draws with a binary search
 // (searchsorted right=True semantics), and the 32 lanes sort the merged depths with a bitonic
-// network.  The cdf is built with SEQUENTIAL fp32 adds (the order oracle/nerf_oracle.py defines) so
+// network.  The cdf is a warp scan in a fixed order that oracle/nerf_oracle.py restates, so
 // sample indices are bit-exact against the oracle; all interpolation arithmetic is unfused
 // (__fmul_rn/__fadd_rn) to reproduce the reference's separate mul/add roundings.
 //
@@ -80,25 +80,50 @@ __global__ void points_bwd_kernel(const float* __restrict__ g_pts, const float* 
 // ------------------------------------------------------------------------------------------
 // warp-level pieces of sample_pdf
 // ------------------------------------------------------------------------------------------
+// inclusive Kogge-Stone scan of one value per lane (the order oracle/nerf_oracle.py:_warp_scan restates)
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = __fadd_rn(v, n);
+  }
+  return v;
+}
+
 // s_w[0..nb-2] holds raw weights on entry; on exit s_cdf[0..nb-1] holds the cdf (s_cdf[0]=0).
+// Warp-scan cdf: lane l owns the contiguous chunk [l*C, (l+1)*C) (C = ceil(nw / 32)), sums it left to right, the lane
+// totals go through a Kogge-Stone scan, element k gets offset[lane] + local prefix.  The oracle sums in exactly this
+// order, so the searchsorted indices stay bit-exact; torch's own order is backend-dependent (pairwise sum + sequential
+// cumsum on the CPU, block scan on CUDA) and differs from any fixed order in <= 2e-3 of the draws
+// (tests/test_oracle_golden.py).  One lane adding all nb values sequentially was a third of the kernel's instructions.
 __device__ __forceinline__ void warp_build_cdf(float* s_w, float* s_cdf, int nb, int lane) {
   const int nw = nb - 1;
-  for (int k = lane; k < nw; k += 32) s_w[k] = __fadd_rn(s_w[k], 1e-5f);      // rays.py:243
-  __syncwarp();
-  if (lane == 0) {
-    float tot = s_w[0];
-    for (int k = 1; k < nw; ++k) tot = __fadd_rn(tot, s_w[k]);                // sequential sum (oracle order)
-    s_cdf[0] = tot;                                                           // stash
+  const int C = (nw + 31) >> 5;
+  const int k0 = lane * C;
+  float run = 0.f;
+  for (int j = 0; j < C; ++j) {
+    const int k = k0 + j;
+    if (k < nw) {
+      const float x = __fadd_rn(s_w[k], 1e-5f);                               // rays.py:243
+      s_w[k] = x;
+      run = __fadd_rn(run, x);
+    }
   }
-  __syncwarp();
-  const float tot = s_cdf[0];
-  __syncwarp();
-  for (int k = lane; k < nw; k += 32) s_w[k] = __fdiv_rn(s_w[k], tot);        // pdf, rays.py:246
-  __syncwarp();
-  if (lane == 0) {
-    float acc = 0.f;
-    s_cdf[0] = 0.f;
-    for (int k = 0; k < nw; ++k) { acc = __fadd_rn(acc, s_w[k]); s_cdf[k + 1] = acc; }  // sequential cumsum
+  const float tot = __shfl_sync(0xffffffffu, warp_scan_add(run, lane), 31);   // rays.py:246 denominator
+  run = 0.f;
+  for (int j = 0; j < C; ++j) {
+    const int k = k0 + j;
+    if (k < nw) {
+      run = __fadd_rn(run, __fdiv_rn(s_w[k], tot));                           // pdf, local prefix
+      s_w[k] = run;
+    }
+  }
+  const float incl = warp_scan_add(run, lane);
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) { excl = 0.f; s_cdf[0] = 0.f; }
+  for (int j = 0; j < C; ++j) {
+    const int k = k0 + j;
+    if (k < nw) s_cdf[k + 1] = __fadd_rn(excl, s_w[k]);                       // rays.py:247-248
   }
   __syncwarp();
 }
