@@ -129,68 +129,72 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return o;
 }
 
-// NG groups of 32 accumulator columns of one row: TMEM -> bias (+ReLU) -> bf16 -> in-place activation tile (+ mask, heads).
-// G-th group of the layer output = columns 32G..32G+31; bias_off / head_w_off are float offsets into the constants.
-// g0 = first group of this warp.  It stays a run-time value on purpose: all sixteen epilogue warps then execute ONE
-// instruction stream per layer type (a variant specialised per column quarter made the four warps of each scheduler run
-// four different code copies).
+// One 8-column chunk of a row: bias (+ReLU) -> bf16 -> 16 bytes of the in-place activation tile (+ mask bits, heads).
+// c = chunk index inside the layer output (columns 8c .. 8c+7).
+template <int HEADS, bool RELU, bool WMASK>
+__device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int c, uint8_t* s_tile, int row, const float* s_bias,
+                                                    int head_w_off, int n, uint32_t& outbits, float2& hh0, float2& hh1,
+                                                    float2& hh2) {
+  const int G = c >> 2, cc = c & 3;               // 32-column group and chunk inside it
+  const float4 bA = *reinterpret_cast<const float4*>(s_bias + c * 8);          // broadcast LDS.128 from the per-layer staging
+  const float4 bB = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
+  const float2 bsel[4] = {make_float2(bA.x, bA.y), make_float2(bA.z, bA.w), make_float2(bB.x, bB.y), make_float2(bB.z, bB.w)};
+  uint32_t packed[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const uint64_t r = fadd2(v[2 * e], v[2 * e + 1], bsel[e]);
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+    __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+    if (RELU) pk = __hmax2(pk, __float2bfloat162_rn(0.f));
+    packed[e] = *reinterpret_cast<uint32_t*>(&pk);
+    // after the ReLU both halves are +0 or positive: adding 0x7FFF sets bit 15 / 31 exactly for the non-zero ones
+    if (WMASK) outbits |= ((packed[e] + 0x7FFF7FFFu) & 0x80008000u) >> (cc * 4 + e);
+    if (HEADS > 0) {
+      // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation; even and odd columns accumulate in
+      // the two halves of a packed fp32 pair
+      const int w2 = (head_w_off >> 1) + c * 4 + e;
+      const float2 a = make_float2(__uint_as_float(packed[e] << 16), __uint_as_float(packed[e] & 0xFFFF0000u));
+      hh0 = ffma2(a, c_pair_consts2[w2], hh0);
+      if (HEADS == 3) {
+        hh1 = ffma2(a, c_pair_consts2[w2 + (n >> 1)], hh1);
+        hh2 = ffma2(a, c_pair_consts2[w2 + n], hh2);
+      }
+    }
+  }
+  uint8_t* box = s_tile + (G >> 1) * kChunkBytes + row * 128;
+  const int lchunk = (G & 1) * 4 + cc;
+  *reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+// NG groups of 32 accumulator columns of one row, starting at group g0: TMEM -> ... -> in-place activation tile.
+// A ROLLED loop over 8-column chunks (two per iteration, TMEM loads double-buffered): the fully unrolled version was
+// ~1,000 straight-line instructions per layer type and the epilogue warps spent 40 % of their stall samples waiting for
+// instruction fetch (stall_no_inst, profiles/r01_ncu_full_prof_fwd_pair.raw.csv); this body is ~90 instructions that
+// every warp re-executes out of the instruction cache.  g0 stays a run-time value so that all sixteen epilogue warps
+// share one instruction stream.
 template <int NG, int HEADS, bool RELU, bool WMASK, bool NOBIAS = false>
 __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int g0, const float* s_bias,
                                               int head_w_off, int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2,
                                               int dbg = 0) {
-  // every TMEM load of the item is issued before the first use: under a running MMA a tcgen05.ld takes several hundred
-  // cycles (the tensor core's accumulator traffic has priority), and a load -> wait -> math sequence per 32 columns exposed
-  // that latency once per group (profiles/r01_pair_experiments.md)
-  uint32_t v[NG][32];
-#pragma unroll
-  for (int g = 0; g < NG; ++g) tmem_ld_x32(t_addr + g * 32, v[g]);
-  tmem_ld_wait();
+  constexpr int NC = NG * 4;                      // 8-column chunks handled by this warp
+  const int c0 = g0 * 4;
   float2 hh0 = make_float2(0.f, 0.f), hh1 = make_float2(0.f, 0.f), hh2 = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    const int G = g0 + g;
-    uint8_t* box = s_tile + (G >> 1) * kChunkBytes + row * 128;
-    const int w2 = (head_w_off >> 1) + G * 16;         // float2 index of this group's first head-weight pair
-    uint32_t outbits = 0u;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int lchunk = (G & 1) * 4 + cc;
-      uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
-      uint32_t packed[4];
-      // the bias of these 8 columns: two broadcast LDS.128 from the per-layer staging buffer.  (Indexed constant loads of
-      // the 13 KB bias table were a third of the epilogue's stall samples, profiles/r01_pair_chain_ncu.md.)
-      const float4 bA = NOBIAS ? make_float4(0.5f, 0.25f, 0.5f, 0.25f) : *reinterpret_cast<const float4*>(s_bias + G * 32 + cc * 8);
-      const float4 bB = NOBIAS ? make_float4(0.5f, 0.25f, 0.5f, 0.25f) : *reinterpret_cast<const float4*>(s_bias + G * 32 + cc * 8 + 4);
-      const float2 bsel[4] = {make_float2(bA.x, bA.y), make_float2(bA.z, bA.w), make_float2(bB.x, bB.y), make_float2(bB.z, bB.w)};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = cc * 4 + e;                       // column pair within the group
-        const uint64_t r = fadd2(v[g][2 * i], v[g][2 * i + 1], bsel[e]);
-        float lo, hi;
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
-        __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-        if (RELU) pk = __hmax2(pk, __float2bfloat162_rn(0.f));
-        packed[e] = *reinterpret_cast<uint32_t*>(&pk);
-        // after the ReLU both halves are +0 or positive: adding 0x7FFF sets bit 15 / 31 exactly for the non-zero ones
-        if (WMASK) outbits |= ((packed[e] + 0x7FFF7FFFu) & 0x80008000u) >> i;
-        if (HEADS > 0) {
-          // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation; even and odd columns accumulate in
-          // the two halves of a packed fp32 pair
-          const float2 a = make_float2(__uint_as_float(packed[e] << 16), __uint_as_float(packed[e] & 0xFFFF0000u));
-          hh0 = ffma2(a, c_pair_consts2[w2 + i], hh0);
-          if (HEADS == 3) {
-            hh1 = ffma2(a, c_pair_consts2[w2 + (n >> 1) + i], hh1);
-            hh2 = ffma2(a, c_pair_consts2[w2 + n + i], hh2);
-          }
-        }
-      }
-#ifdef RN_EXPERIMENTS
-      if (dbg & 32) { if (packed[0] == 0x12345678u) *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]); }
-      else
-#endif
-      *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  uint32_t va[8], vb[8];
+  uint32_t outbits = 0u;
+  tmem_ld_x8(t_addr, va);
+#pragma unroll 1
+  for (int i = 0; i < NC; i += 2) {
+    tmem_ld_wait();
+    tmem_ld_x8(t_addr + (i + 1) * 8, vb);
+    pair_epilogue_chunk<HEADS, RELU, WMASK>(va, c0 + i, s_tile, row, s_bias, head_w_off, n, outbits, hh0, hh1, hh2);
+    tmem_ld_wait();
+    if (i + 2 < NC) tmem_ld_x8(t_addr + (i + 2) * 8, va);
+    pair_epilogue_chunk<HEADS, RELU, WMASK>(vb, c0 + i + 1, s_tile, row, s_bias, head_w_off, n, outbits, hh0, hh1, hh2);
+    if ((i & 3) == 2) {                           // a 32-column group is complete
+      if (i < 4) mb[0] = outbits; else mb[1] = outbits;
+      outbits = 0u;
     }
-    mb[g] = outbits;
   }
   if (HEADS > 0) { h0 = hh0.x + hh0.y; h1 = hh1.x + hh1.y; h2 = hh2.x + hh2.y; }
 }
