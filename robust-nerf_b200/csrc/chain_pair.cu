@@ -180,21 +180,26 @@ __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, 
   constexpr int NC = NG * 4;                      // 8-column chunks handled by this warp
   const int c0 = g0 * 4;
   float2 hh0 = make_float2(0.f, 0.f), hh1 = make_float2(0.f, 0.f), hh2 = make_float2(0.f, 0.f);
-  uint32_t va[8], vb[8];
+  uint32_t va[16], vb[16];
   uint32_t outbits = 0u;
-  tmem_ld_x8(t_addr, va);
+  auto two_chunks = [&](const uint32_t (&v)[16], int c) {
+    uint32_t lo8[8], hi8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { lo8[k] = v[k]; hi8[k] = v[8 + k]; }
+    pair_epilogue_chunk<HEADS, RELU, WMASK>(lo8, c, s_tile, row, s_bias, head_w_off, n, outbits, hh0, hh1, hh2);
+    pair_epilogue_chunk<HEADS, RELU, WMASK>(hi8, c + 1, s_tile, row, s_bias, head_w_off, n, outbits, hh0, hh1, hh2);
+  };
+  tmem_ld_x16(t_addr, va);
 #pragma unroll 1
-  for (int i = 0; i < NC; i += 2) {
+  for (int i = 0; i < NC; i += 4) {               // one 32-column group per iteration, two 16-column TMEM loads in flight
     tmem_ld_wait();
-    tmem_ld_x8(t_addr + (i + 1) * 8, vb);
-    pair_epilogue_chunk<HEADS, RELU, WMASK>(va, c0 + i, s_tile, row, s_bias, head_w_off, n, outbits, hh0, hh1, hh2);
+    tmem_ld_x16(t_addr + (i + 2) * 8, vb);
+    two_chunks(va, c0 + i);
     tmem_ld_wait();
-    if (i + 2 < NC) tmem_ld_x8(t_addr + (i + 2) * 8, va);
-    pair_epilogue_chunk<HEADS, RELU, WMASK>(vb, c0 + i + 1, s_tile, row, s_bias, head_w_off, n, outbits, hh0, hh1, hh2);
-    if ((i & 3) == 2) {                           // a 32-column group is complete
-      if (i < 4) mb[0] = outbits; else mb[1] = outbits;
-      outbits = 0u;
-    }
+    if (i + 4 < NC) tmem_ld_x16(t_addr + (i + 4) * 8, va);
+    two_chunks(vb, c0 + i + 2);
+    if (i < 4) mb[0] = outbits; else mb[1] = outbits;
+    outbits = 0u;
   }
   if (HEADS > 0) { h0 = hh0.x + hh0.y; h1 = hh1.x + hh1.y; h2 = hh2.x + hh2.y; }
 }
