@@ -13,7 +13,8 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTE
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librnerf_b200.so")
+# RN_B200_LIB: load another build of the same library (A/B timing of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("RN_B200_LIB") or os.path.join(_HERE, "librnerf_b200.so")
 
 NUM_PARAM_TENSORS = 24
 NUM_PARAMS = 595844

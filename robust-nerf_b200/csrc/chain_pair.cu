@@ -139,7 +139,7 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
   const float4 bA = *reinterpret_cast<const float4*>(s_bias + c * 8);          // broadcast LDS.128 from the per-layer staging
   const float4 bB = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
   const float2 bsel[4] = {make_float2(bA.x, bA.y), make_float2(bA.z, bA.w), make_float2(bB.x, bB.y), make_float2(bB.z, bB.w)};
-  uint32_t packed[4];
+  uint32_t packed[4], fl[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const uint64_t r = fadd2(v[2 * e], v[2 * e + 1], bsel[e]);
@@ -148,8 +148,9 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
     __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
     if (RELU) pk = __hmax2(pk, __float2bfloat162_rn(0.f));
     packed[e] = *reinterpret_cast<uint32_t*>(&pk);
-    // after the ReLU both halves are +0 or positive: adding 0x7FFF sets bit 15 / 31 exactly for the non-zero ones
-    if (WMASK) outbits |= ((packed[e] + 0x7FFF7FFFu) & 0x80008000u) >> (cc * 4 + e);
+    // after the ReLU both halves are +0 or positive bit patterns: an unsigned 16-bit min with 1 is the "> 0" flag of
+    // each half (bits 0 and 16), one instruction per pair
+    if (WMASK) fl[e] = __vminu2(packed[e], 0x00010001u);
     if (HEADS > 0) {
       // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation; even and odd columns accumulate in
       // the two halves of a packed fp32 pair
@@ -162,6 +163,8 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
       }
     }
   }
+  // the four pairs of this chunk are pairs 4cc .. 4cc+3 of the group: flags to bits 4cc + e and 16 + 4cc + e
+  if (WMASK) outbits |= (fl[0] + 2u * fl[1] + 4u * fl[2] + 8u * fl[3]) << (cc * 4);
   uint8_t* box = s_tile + (G >> 1) * kChunkBytes + row * 128;
   const int lchunk = (G & 1) * 4 + cc;
   *reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -693,9 +696,9 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
               uint32_t packed[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int pi = cc * 4 + e;                // column pair: flags at bits 15 - pi and 31 - pi of the word
+                const int pi = cc * 4 + e;                // column pair: flags at bits pi and 16 + pi of the word
                 __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(v[g][2 * pi]), __uint_as_float(v[g][2 * pi + 1]));
-                const uint32_t keep = ((word >> (15 - pi)) & 0x00010001u) * 0xFFFFu;
+                const uint32_t keep = ((word >> pi) & 0x00010001u) * 0xFFFFu;
                 packed[e] = *reinterpret_cast<uint32_t*>(&pk) & keep;
               }
               *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);

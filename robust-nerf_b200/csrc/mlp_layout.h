@@ -65,9 +65,9 @@ constexpr size_t kG_Total = kG_BRgb + 3;
 static_assert(kG_Total == 595844, "parameter count must match the reference (summary.json:46)");
 
 // ---- packed ReLU masks: one 32-bit word per 32 consecutive columns of a row ----
-// Column j = 2i + h (pair i = 0..15, half h) of the group sits at bit 15 - i (h = 0) or 31 - i (h = 1): the flags of a packed
-// bf16x2 word (bits 15 / 31 after adding 0x7FFF7FFF to the non-negative halves) drop into place with one shift by i.
-constexpr int relu_mask_bit(int j) { return (j & 1) ? 31 - (j >> 1) : 15 - (j >> 1); }
+// Column j = 2i + h (pair i = 0..15, half h) of the group sits at bit i (h = 0) or 16 + i (h = 1): the two flags of a
+// packed bf16x2 word -- min.u16x2(word, 0x00010001) of the non-negative halves -- drop into place with one shift by i.
+constexpr int relu_mask_bit(int j) { return (j & 1) ? 16 + (j >> 1) : (j >> 1); }
 
 // ---- activation workspace (bf16 elements per point) ----
 // training: XC[320] H0 H1 H2 H3 H5 H6 H7 (7 x 256) FD[320] HC[128] MB0..MB7 (packed masks) | backward: dHC[128] dFS[272] dA[256] dB[256]

@@ -441,12 +441,12 @@ _gemm_scratch = {}
 
 def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
     """bool/real [M,N] (N % 32 == 0) -> packed uint32-as-int32 [M, N/32]; column 32c + 2i + h of row m sits in word c at
-    bit 15 - i (h = 0) or 31 - i (h = 1)  (csrc/mlp_layout.h: relu_mask_bit; test helper, the kernels produce / consume
+    bit i (h = 0) or 16 + i (h = 1)  (csrc/mlp_layout.h: relu_mask_bit; test helper, the kernels produce / consume
     this layout)."""
     M, N = mask.shape
     b = (mask > 0).reshape(M, N // 32, 32).to(torch.int64)
     j = torch.arange(32, device=mask.device, dtype=torch.int64)
-    pos = torch.where(j % 2 == 1, 31 - j // 2, 15 - j // 2)
+    pos = torch.where(j % 2 == 1, 16 + j // 2, j // 2)
     w = (b << pos).sum(-1)
     return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
 
