@@ -106,6 +106,14 @@ int rn_pixel_gather(const int64_t* flat_idx /*[B]*/, int64_t B, int H, int W, co
 int rn_pixel_gather_u8(const int64_t* flat_idx /*[B]*/, int64_t B, int H, int W, const uint8_t* images_u8,
                        int64_t* image_idx_out, float* pixel_uv_out, float* target_rgb_out, rn_stream_t stream);
 
+/* ---- evaluation metrics: metrics.py:15-116 ---- */
+/* Per image of a batch pred/target [N,H,W,3] (fp32 in [0,1]): mean squared error (compute_mse; PSNR = 20 log10(max)
+ * - 10 log10(mse) is left to the caller) and the mean Gaussian-window SSIM (compute_ssim: 11 x 11 window, sigma 1.5,
+ * zero padding).  scratch: rn_image_metrics_scratch_bytes(N,H,W) bytes.  Deterministic (no atomics). */
+size_t rn_image_metrics_scratch_bytes(int N, int H, int W);
+int rn_image_metrics(const float* pred, const float* target, int N, int H, int W, float C1, float C2, float* scratch,
+                     float* mse_out /*[N]*/, float* ssim_out /*[N]*/, rn_stream_t stream);
+
 /* ---- sampling: rays.py:145-333 ---- */
 /* z = lower + (upper-lower)*t_rand over the base depths z_base (linspace built by the caller,
  * rays.py:185-195); t_rand NULL = no perturbation.  pts may be NULL. */

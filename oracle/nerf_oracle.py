@@ -717,3 +717,59 @@ def clip_and_adam(params_list, grads_list, state, lr=5e-4, max_norm=1.0, betas=(
             vhat = v / F32(1 - betas[1] ** t)
             ps[k] -= (F32(lr) * mhat / (np.sqrt(vhat) + F32(eps))).astype(F32)
     return tot
+
+
+# --------------------------------------------------------------------------------------
+# evaluation metrics: noisy_src/metrics.py:15-116
+# --------------------------------------------------------------------------------------
+def gaussian_window_2d(size: int = 11, sigma: float = 1.5) -> np.ndarray:
+    """metrics.py:85-89: g = exp(-x^2 / (2 sigma^2)), normalised, outer product (all fp32)."""
+    coords = (np.arange(size, dtype=F32) - F32(size // 2)).astype(F32)
+    g = np.exp(-(coords ** 2) / F32(2 * sigma ** 2)).astype(F32)
+    g = (g / g.sum(dtype=F32)).astype(F32)
+    return np.outer(g, g).astype(F32)
+
+
+def compute_mse(pred, target) -> float:
+    """metrics.py:44-46."""
+    d = _f32(pred) - _f32(target)
+    return float(np.mean((d * d).astype(F32), dtype=np.float64))
+
+
+def compute_psnr(pred, target, max_val: float = 1.0) -> float:
+    """metrics.py:15-41: 20 log10(max) - 10 log10(mse); inf for identical images."""
+    mse = compute_mse(pred, target)
+    if mse == 0:
+        return float("inf")
+    return float(20.0 * np.log10(max_val) - 10.0 * np.log10(mse))
+
+
+def _conv2d_same(x: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """Zero-padded 'same' cross-correlation of x (H, W) with w (k, k), as F.conv2d(padding=k//2) (metrics.py:98-110)."""
+    k = w.shape[0]
+    r = k // 2
+    H, W = x.shape
+    xp = np.zeros((H + 2 * r, W + 2 * r), dtype=np.float64)
+    xp[r:r + H, r:r + W] = x
+    out = np.zeros((H, W), dtype=np.float64)
+    for i in range(k):
+        for j in range(k):
+            out += np.float64(w[i, j]) * xp[i:i + H, j:j + W]
+    return out.astype(F32)
+
+
+def compute_ssim(pred, target, window_size: int = 11, C1: float = 0.01 ** 2, C2: float = 0.03 ** 2) -> float:
+    """metrics.py:49-116: per-channel Gaussian-window SSIM map of an (H, W, 3) image pair, mean over all pixels and channels."""
+    pred, target = _f32(pred), _f32(target)
+    w = gaussian_window_2d(window_size)
+    total = 0.0
+    for c in range(pred.shape[-1]):
+        p, t = pred[..., c], target[..., c]
+        mu_p, mu_t = _conv2d_same(p, w), _conv2d_same(t, w)
+        mu_pp, mu_tt, mu_pt = mu_p * mu_p, mu_t * mu_t, mu_p * mu_t
+        s_pp = _conv2d_same(p * p, w) - mu_pp
+        s_tt = _conv2d_same(t * t, w) - mu_tt
+        s_pt = _conv2d_same(p * t, w) - mu_pt
+        ssim_map = ((2 * mu_pt + F32(C1)) * (2 * s_pt + F32(C2))) / ((mu_pp + mu_tt + F32(C1)) * (s_pp + s_tt + F32(C2)))
+        total += float(np.sum(ssim_map, dtype=np.float64))
+    return total / pred.size

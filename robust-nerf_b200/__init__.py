@@ -13,6 +13,7 @@ from .data_pose_opt import PixelBatch, PixelDataset, PixelSampler, create_pixel_
 from .train import (train_step, train_step_with_poses, render_image, render_image_with_pose, compute_psnr,
                     Trainer, render_views_sharded)
 from .synthetic import BlenderData, make_scene, lego_poses, hemisphere_poses, add_noise_to_poses
+from .metrics import image_metrics, compute_ssim, compute_mse
 
 __all__ = [
     "NeRFConfig", "ModelConfig", "RenderConfig", "DataConfig", "TrainConfig", "PoseOptConfig",
@@ -21,4 +22,5 @@ __all__ = [
     "CameraPoseParameters", "PixelBatch", "PixelDataset", "PixelSampler", "create_pixel_dataset",
     "train_step", "train_step_with_poses", "render_image", "render_image_with_pose", "compute_psnr", "Trainer",
     "render_views_sharded", "BlenderData", "make_scene", "lego_poses", "hemisphere_poses", "add_noise_to_poses",
+    "image_metrics", "compute_ssim", "compute_mse",
 ]

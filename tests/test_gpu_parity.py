@@ -813,6 +813,35 @@ def test_uint8_image_table_is_lossless(rn, dev):
         ops.quantize_images(torch.rand(2, 4, 4, 3, device=dev))
 
 
+def test_image_metrics_batched(rn, dev):
+    """Batched PSNR / SSIM kernel against the oracle restatement of noisy_src/metrics.py and
+    the reference's own values (tests/golden/metrics.npz); tile-boundary sizes, batch == singles, identical images."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
+    for tag in ("small", "tile", "tiny"):
+        pred, target = T(g[f"{tag}_pred"], dev), T(g[f"{tag}_target"], dev)
+        m = rn.image_metrics(pred, target)
+        np.testing.assert_allclose(N(m["mse"]), g[f"{tag}_mse"], rtol=2e-6)
+        np.testing.assert_allclose(N(m["psnr"]), g[f"{tag}_psnr"], atol=2e-5)
+        np.testing.assert_allclose(N(m["ssim"]), g[f"{tag}_ssim"], atol=2e-6)
+        for i in range(pred.shape[0]):                                   # reference-signature single-image calls
+            assert abs(float(rn.compute_ssim(pred[i], target[i])) - float(m["ssim"][i])) == 0.0
+            assert abs(float(rn.compute_psnr(pred[i], target[i])) - float(m["psnr"][i])) == 0.0
+    rng = np.random.default_rng(5)
+    for (n, h, w) in ((1, 1, 1), (2, 31, 33), (1, 32, 32), (2, 65, 40), (1, 100, 100)):
+        t = rng.uniform(0, 1, (n, h, w, 3)).astype(np.float32)
+        p = np.clip(t + rng.normal(0, 0.1, t.shape), 0, 1).astype(np.float32)
+        m = rn.image_metrics(T(p, dev), T(t, dev))
+        for i in range(n):
+            assert abs(float(m["ssim"][i]) - O.compute_ssim(p[i], t[i])) < 2e-6
+            assert abs(float(m["psnr"][i]) - O.compute_psnr(p[i], t[i])) < 2e-5
+    same = T(rng.uniform(0, 1, (2, 40, 50, 3)).astype(np.float32), dev)
+    m = rn.image_metrics(same, same)
+    assert torch.isinf(m["psnr"]).all() and (m["mse"] == 0).all() and (m["ssim"] - 1).abs().max().item() < 1e-6
+    e = rn.image_metrics(torch.zeros(0, 8, 8, 3, device=dev), torch.zeros(0, 8, 8, 3, device=dev))
+    assert e["psnr"].shape == (0,)
+
+
 def test_render_views_tile_sharded(rn, dev):
     """Tile-sharded test-view rendering (config 4): the union of the ranks' tiles equals the single-rank
     render, every ray is rendered exactly once, no collective involved."""

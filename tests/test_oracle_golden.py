@@ -230,3 +230,17 @@ def test_pose_error_known_answers():
     e = O.compute_pose_errors(P, gt)
     np.testing.assert_allclose([e["rotation_error_mean"], e["translation_error_mean"]],
                                gp["pose_errors"][[0, 3]], rtol=1e-4)
+
+
+def test_metrics_oracle_against_reference():
+    """compute_psnr / compute_mse / compute_ssim (noisy_src/metrics.py:15-116) restated in the
+    oracle, against values produced by the unmodified reference (tests/golden/make_golden_metrics.py)."""
+    g = load_golden("metrics")
+    for tag in ("small", "tile", "tiny"):
+        for i in range(len(g[f"{tag}_psnr"])):
+            p, t = g[f"{tag}_pred"][i], g[f"{tag}_target"][i]
+            assert abs(O.compute_mse(p, t) - g[f"{tag}_mse"][i]) <= 1e-6 * g[f"{tag}_mse"][i]
+            assert abs(O.compute_psnr(p, t) - g[f"{tag}_psnr"][i]) <= 5e-6
+            assert abs(O.compute_ssim(p, t) - g[f"{tag}_ssim"][i]) <= 1e-6
+    same = g["tiny_target"][0]
+    assert O.compute_psnr(same, same) == float("inf") and abs(O.compute_ssim(same, same) - 1.0) < 1e-6
