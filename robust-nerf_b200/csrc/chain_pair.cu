@@ -145,9 +145,13 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
     const uint64_t r = fadd2(v[2 * e], v[2 * e + 1], bsel[e]);
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
-    __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-    if (RELU) pk = __hmax2(pk, __float2bfloat162_rn(0.f));
-    packed[e] = *reinterpret_cast<uint32_t*>(&pk);
+    if (RELU) {
+      // convert and ReLU in one instruction (F2FP.RELU): round(max(x, 0)) == max(round(x), 0)
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e]) : "f"(hi), "f"(lo));
+    } else {
+      __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+      packed[e] = *reinterpret_cast<uint32_t*>(&pk);
+    }
     // after the ReLU both halves are +0 or positive bit patterns: an unsigned 16-bit min with 1 is the "> 0" flag of
     // each half (bits 0 and 16), one instruction per pair
     if (WMASK) fl[e] = __vminu2(packed[e], 0x00010001u);
