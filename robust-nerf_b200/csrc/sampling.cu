@@ -24,20 +24,35 @@ __global__ void stratified_kernel(const float* __restrict__ ro, const float* __r
                                   const float* __restrict__ zb, int Nc, const float* __restrict__ t_rand,
                                   float* __restrict__ z_out, float* __restrict__ pts) {
   const int64_t n = B * Nc;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / Nc;
-    const int s = (int)(i - b * Nc);
-    float z = __ldg(zb + s);
-    if (t_rand) {
-      const float lower = (s == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, __ldg(zb + s - 1)));
-      const float upper = (s == Nc - 1) ? z : __fmul_rn(0.5f, __fadd_rn(__ldg(zb + s + 1), z));
-      z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldcs(t_rand + i)));
-    }
-    z_out[i] = z;
-    if (pts) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // four samples per thread and iteration, their loads issued first (the kernel is latency-bound:
+  // profiles/r01_ncu_full_hbm_kernels.raw.csv, 20 long-scoreboard stall cycles per issued instruction)
+  constexpr int kU = 4;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += kU * stride) {
+    float tr[kU];
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
-        pts[i * 3 + k] = __fadd_rn(__ldg(ro + b * 3 + k), __fmul_rn(__ldg(rd + b * 3 + k), z));
+    for (int u = 0; u < kU; ++u) {
+      const int64_t i = i0 + u * stride;
+      tr[u] = (t_rand && i < n) ? __ldcs(t_rand + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n) break;
+      const int64_t b = i / Nc;
+      const int s = (int)(i - b * Nc);
+      float z = __ldg(zb + s);
+      if (t_rand) {
+        const float lower = (s == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, __ldg(zb + s - 1)));
+        const float upper = (s == Nc - 1) ? z : __fmul_rn(0.5f, __fadd_rn(__ldg(zb + s + 1), z));
+        z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr[u]));
+      }
+      z_out[i] = z;
+      if (pts) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          pts[i * 3 + k] = __fadd_rn(__ldg(ro + b * 3 + k), __fmul_rn(__ldg(rd + b * 3 + k), z));
+      }
     }
   }
 }
