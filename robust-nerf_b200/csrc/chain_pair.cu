@@ -62,7 +62,7 @@ struct PairLayer {
 };
 // measurement knobs, compiled in only with -DRN_EXPERIMENTS (results are WRONG when any bit is set):
 // bit 0: no weight loads   bit 1: no TMA stores   bit 2: no side-chunk loads   bit 3: epilogue reads TMEM but skips the math
-// bit 4: epilogue does not even read TMEM
+// bit 4: epilogue does not even read TMEM   bit 7: no fence.proxy.async after the epilogue's shared-memory writes
 #ifdef RN_EXPERIMENTS
 extern int g_chain_dbg;
 #define RN_PDBG(p, bit) ((p).dbg & (bit))
@@ -180,10 +180,9 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
 // instruction fetch (stall_no_inst, profiles/r01_ncu_full_prof_fwd_pair.raw.csv); this body is ~90 instructions that
 // every warp re-executes out of the instruction cache.  g0 stays a run-time value so that all sixteen epilogue warps
 // share one instruction stream.
-template <int NG, int HEADS, bool RELU, bool WMASK, bool NOBIAS = false>
+template <int NG, int HEADS, bool RELU, bool WMASK>
 __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int g0, const float* s_bias,
-                                              int head_w_off, int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2,
-                                              int dbg = 0) {
+                                              int head_w_off, int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2) {
   constexpr int NC = NG * 4;                      // 8-column chunks handled by this warp
   const int c0 = g0 * 4;
   float2 hh0 = make_float2(0.f, 0.f), hh1 = make_float2(0.f, 0.f), hh2 = make_float2(0.f, 0.f);
@@ -400,14 +399,11 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
           }
           else {
             if (L.n == 256) {
-              if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);
-#ifdef RN_EXPERIMENTS
-              else if (L.relu && (p.dbg & 64)) pair_epilogue<2, 0, true, TRAIN, true>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);
-#endif
-              else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);
-              else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2, p.dbg);
+              if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2);
+              else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2);
+              else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2);
             } else {
-              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, s_bias, L.head_w_off, 128, mb, h0, h1, h2, p.dbg);
+              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, s_bias, L.head_w_off, 128, mb, h0, h1, h2);
             }
           }
           RN_TL(tl, 600 + l * 10 + slot);                  // math done

@@ -20,8 +20,7 @@ names = {0: "all on", 1: "no B (weight) loads", 2: "no TMA stores", 4: "no A loa
          3: "no B loads, no stores", 7: "no loads, no stores", 15: "MMA + barriers only", 10: "no stores, no epilogue math",
          11: "no B, no stores, no epilogue", 31: "MMA only (no TMEM reads either)"}
 pair_names = {0: "all on", 1: "no weight loads", 4: "no side-chunk loads", 8: "no epilogue math", 16: "no epilogue (no TMEM reads)",
-              5: "no loads", 13: "no loads, no epilogue math", 21: "MMA + barriers only", 32: "no smem writes in the epilogue",
-              64: "bias from registers (no constant loads)", 96: "no smem writes, no constant loads"}
+              5: "no loads", 13: "no loads, no epilogue math", 21: "MMA + barriers only"}
 import ctypes
 def timed(fn, n=3):
     """kernel-only milliseconds of the GEMM launches (CUDA events around each launch, rn_prof_*), per call"""
