@@ -44,7 +44,8 @@ def test_sass_uses_blackwell_tensor_path(rn):
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
         assert mnemonic in sass, mnemonic
     assert "UTCHMMA.2CTA" in sass          # the chain kernels issue cta_group::2 MMAs (M = 256 per CTA pair)
-    assert "FADD2" in sass and "HMNMX2" in sass     # packed two-column epilogue arithmetic
+    # packed two-column epilogue arithmetic: bias add, convert+ReLU, mask flags
+    assert "FADD2" in sass and "F2FP.RELU" in sass and "VIMNMX.U16x2" in sass
     assert "HMMA.16816" not in sass        # no legacy mma.sync path
 
 
