@@ -327,7 +327,7 @@ class Trainer:
         graph.replay()
         return loss
 
-    def step_pixels(self, pixel_batch, sampler, optimize_poses: bool = True, optimise: bool = True) -> torch.Tensor:
+    def _step_pixels_body(self, pixel_batch, sampler, optimize_poses: bool, optimise: bool, advance: bool):
         cam = self.camera_params
         self._zero_grad()
         rays_o, rays_d = sampler.get_rays_for_batch_fused(pixel_batch, cam)
@@ -342,8 +342,46 @@ class Trainer:
         loss = self._backward(out, pixel_batch.target_rgb, reg)
         self._allreduce()
         if optimise:
-            self._advance_schedule(optimize_poses)
+            if advance:
+                self._advance_schedule(optimize_poses)
             self._optimise(separate_clip=True, optimize_poses=optimize_poses)
+        return loss
+
+    def step_pixels(self, pixel_batch, sampler, optimize_poses: bool = True, optimise: bool = True) -> torch.Tensor:
+        return self._step_pixels_body(pixel_batch, sampler, optimize_poses, optimise, advance=True)
+
+    def step_pixels_graphed(self, pixel_batch, sampler, optimize_poses: bool = True) -> torch.Tensor:
+        """step_pixels (joint pose optimisation, train_pose_opt.py:290-411) replayed from a CUDA graph, captured on first
+        use per (batch size, optimize_poses).  Same contract as step_rays_graphed: inputs are copied into static
+        buffers, the optimiser schedule is uploaded outside the graph, the returned loss tensor is static."""
+        from .data_pose_opt import PixelBatch
+        key = ("pixels", int(pixel_batch.image_indices.shape[0]), bool(optimize_poses))
+        g = self._graphs.get(key)
+        if g is None:
+            static = PixelBatch(image_indices=pixel_batch.image_indices.clone(), pixel_coords=pixel_batch.pixel_coords.clone(),
+                                target_rgb=pixel_batch.target_rgb.clone())
+            saved = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq)]
+            self.hyper.zero_()                       # lr = 0 during warm-up/capture passes
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._step_pixels_body(static, sampler, optimize_poses, True, advance=False)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self._step_pixels_body(static, sampler, optimize_poses, True, advance=False)
+            for t, sv in zip((self.flat, self.exp_avg, self.exp_avg_sq), saved):
+                t.copy_(sv)
+            for m in self.nets:
+                m._packed.key = None
+            g = self._graphs[key] = (graph, static, loss)
+        graph, static, loss = g
+        static.image_indices.copy_(pixel_batch.image_indices, non_blocking=True)
+        static.pixel_coords.copy_(pixel_batch.pixel_coords, non_blocking=True)
+        static.target_rgb.copy_(pixel_batch.target_rgb, non_blocking=True)
+        self._advance_schedule(optimize_poses)
+        graph.replay()
         return loss
 
 

@@ -115,6 +115,16 @@ def main():
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / 10
     out["pose_opt_step"] = {"ms": t * 1e3, "rays_per_s": 4096 / t}
+    for i in range(5):
+        tr.step_pixels_graphed(batches[i % 4], sampler)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(20):
+        tr.step_pixels_graphed(batches[i % 4], sampler)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / 20
+    out["pose_opt_step_graphed"] = {"ms": t * 1e3, "rays_per_s": 4096 / t}
     print(json.dumps(out))
 
 
