@@ -259,6 +259,9 @@ class Composite(torch.autograd.Function):
              float(t_min), ptr(rgb_map), ptr(depth), ptr(acc), ptr(w), stream_ptr())
         ctx.save_for_backward(*(t for t in (raw4, rgb, sigma, z, rd, noise) if t is not None))
         ctx.meta = (raw_mode, noise is not None, bool(white))
+        # unused outputs (depth, acc, weights in training) arrive as None in backward instead of zero tensors: no fill
+        # launches, and the backward kernel takes its lean variant
+        ctx.set_materialize_grads(False)
         return rgb_map, depth, acc, w
 
     @staticmethod
