@@ -755,7 +755,7 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   int rc = check_arch();
   if (rc != RN_OK) return rc;
   RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kPairMaxLayers && M > 0 && in && (in_cols == 128 || in_cols == 256));
-  static BwdParams p;
+  static thread_local BwdParams p;
   double flops = 0.0;
   if ((rc = make_tmap(&p.tmIn, in, in_cols, M, ld_in, 128)) != RN_OK) return rc;
   if ((rc = make_tmap(&p.tmAux, aux ? aux : in, aux ? aux_cols : in_cols, M, aux ? ld_aux : ld_in, 128)) != RN_OK) return rc;
@@ -806,7 +806,7 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
   int rc = check_arch();
   if (rc != RN_OK) return rc;
   RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kPairMaxLayers && M > 0 && consts && raw && x_enc && d_enc);
-  static PairParams p;
+  static thread_local PairParams p;     // ~4 KB of tensor maps: built on the host, passed by value as a kernel parameter
   double flops = 0.0;
   if ((rc = make_tmap(&p.tmAux[0], x_enc, 64, M, ld_x, 128)) != RN_OK) return rc;
   if ((rc = make_tmap(&p.tmAux[1], d_enc, 64, M, ld_d, 128)) != RN_OK) return rc;

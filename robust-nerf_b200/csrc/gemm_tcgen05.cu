@@ -1048,7 +1048,7 @@ int mlp_chain_forward(const ChainLayerHost* layers, int n_layers, int64_t M, con
   int rc = check_arch();
   if (rc != RN_OK) return rc;
   RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kChainMaxLayers && M > 0 && consts && raw);
-  static ChainParams p;            // ~5 KB of tensor maps: built on the host, passed by value as a kernel parameter
+  static thread_local ChainParams p;   // ~5 KB of tensor maps: built on the host, passed by value as a kernel parameter
   double flops = 0.0;
   for (int l = 0; l < n_layers; ++l) {
     const ChainLayerHost& h = layers[l];
