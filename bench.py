@@ -311,13 +311,22 @@ def run_gpu(args):
         algo_flops_per_step = TRAIN_FLOP_PER_RAY * RAYS_PER_GPU
         achieved = algo_flops_per_step / (gemm_ms_per_step * 1e-3) / 1e12 if gemm_ms_per_step > 0 else None
         n_gemm = ln3[0] + ln3[1] + ln3[2]
-        traffic = None
+        traffic, hbm_view = None, None
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch")
+                # second view of the same launches: the present data flow (activations and their gradients written
+                # once and read once by the weight-gradient GEMMs) is HBM-heavy; DRAM bytes from the committed ncu pass
+                # over the live GEMM time of this run
+                step_bytes = tj.get("dram_bytes_per_step")
+                if step_bytes and gemm_ms_per_step > 0:
+                    gbs = step_bytes / (gemm_ms_per_step * 1e-3) / 1e9
+                    hbm_view = {"dram_bytes_per_step": step_bytes, "achieved": gbs, "peak": peaks["gbs"], "unit": "GB/s",
+                                "frac": gbs / peaks["gbs"], "source": "profiles/gemm_traffic.json (ncu) / live GEMM time"}
             except Exception:
-                traffic = None
+                traffic, hbm_view = None, None
         per_mode = {}
         for i, nm in enumerate(("nt_forward", "nn_dgrad", "tn_wgrad")):
             if ln3[i]:
@@ -348,7 +357,7 @@ def run_gpu(args):
                          "algorithmic_flops_per_step": algo_flops_per_step, "gemm_launches_per_step": n_gemm / K_,
                          "gemm_ms_per_step": gemm_ms_per_step, "gemm_share_of_step": gemm_ms_per_step / eager_ms_per_step,
                          "measured_in": "eager pass of the same K steps (CUDA events around every GEMM launch on its stream)",
-                         "per_mode": per_mode},
+                         "per_mode": per_mode, "hbm_view": hbm_view},
             "cpu_baseline": None if cpu_rate is None else {
                 "value": cpu_rate, "unit": "rays/s", "cores": cores, "kind": "port",
                 "sample": f"256-ray slice of the same training step, 2 timed steps after 1 warm-up ({cpu_t:.1f} s/step), numpy oracle port"},

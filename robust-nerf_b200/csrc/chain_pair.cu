@@ -73,6 +73,7 @@ extern int g_chain_dbg;
 // timeline of cluster 0 (scripts/pair_timeline.py): role r of CTA rank c appends (tag, clock64, globaltimer) triples
 constexpr int kTlRoles = 4, kTlEntries = 2048;
 long long* g_pair_timeline = nullptr;        // [2 ranks][kTlRoles][kTlEntries][3]
+long long* g_pair_timeline_bwd = nullptr;    // same, data-gradient chain
 struct Tl {
   long long* base; int n;
   __device__ __forceinline__ void init(long long* buf, int rank, int role, bool on) {
@@ -498,6 +499,7 @@ struct BwdLayer {
   const uint32_t* mask_in;     // packed ReLU mask of the layer OUTPUT rows [M][8], or null
 };
 struct BwdParams {
+  long long* timeline;          // RN_EXPERIMENTS only (scripts/pair_timeline.py bwd)
   CUtensorMap tmB[kPairMaxLayers], tmD[kPairMaxLayers], tmIn, tmAux;
   BwdLayer L[kPairMaxLayers];
   int n_layers, n_ptiles;
@@ -613,6 +615,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
       const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_b), 8192);
       int s = 0, s_mark = 0; uint32_t ph = 0, ph_mark = 0;
       uint32_t it0 = 0, it1 = 0, aux_n0 = 0, aux_n1 = 0, in_n0 = 0, in_n1 = 0;
+      RN_TL_DECL(tl, 0, lane == 0);
       for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
         const int tiles_here = min(2, p.n_ptiles - grp * 2);
         for (int l = 0; l < p.n_layers; ++l) {
@@ -620,7 +623,9 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
           const int k_chunks = L.k_chunks;
           for (int slot = 0; slot < tiles_here; ++slot) {
             const uint32_t i = slot ? it1++ : it0++;
+            RN_TL(tl, 100 + l * 10 + slot);
             if (i > 0) mbar_wait(&act_ready[slot], (i - 1) & 1u);             // accumulator drained (and input written)
+            RN_TL(tl, 300 + l * 10 + slot);
             if (L.act_load_chunks) {
               const uint32_t j = slot ? in_n1++ : in_n0++;
               mbar_wait(&act_full[slot], j & 1u);
@@ -635,6 +640,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
             s_mark = s; ph_mark = ph;
             for (int kc = 0; kc < k_chunks; ++kc) {
               if (!(shared && slot == 1)) mbar_wait(&full_b[s], ph);
+              RN_TL(tl, 1000 + l * 100 + slot * 10 + kc);
               tcgen05_fence_after();
               if (elect_one()) {
                 const int src = L.a_src[kc];
@@ -666,6 +672,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
     const int row = q * 32 + lane;
     const uint32_t act_ready_leader = mapa_u32(smem_u32(act_ready), 0);
     uint32_t it0 = 0, it1 = 0;
+    RN_TL_DECL(tl, (warp == 2 ? 1 : 2), lane == 0 && (warp == 2 || warp == 17));
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
       for (int l = 0; l < p.n_layers; ++l) {
@@ -675,8 +682,11 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
           const int64_t gr = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128 + row;
           uint2 mw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
           if (mask_in && gr < p.m_rows) mw = __ldg(reinterpret_cast<const uint2*>(mask_in + gr * 8 + cq * 2));
+          RN_TL(tl, 100 + l * 10 + slot);
           mbar_wait(&tmem_full[slot], i & 1u);
+          RN_TL(tl, 300 + l * 10 + slot);
           if (i > 0) mbar_wait(&store_done[slot], (i - 1) & 1u);
+          RN_TL(tl, 500 + l * 10 + slot);
           tcgen05_fence_after();
           uint8_t* s_tile = s_act + slot * kActBytes;
           const uint32_t t_addr = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16) + cq * 64;
@@ -704,6 +714,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
               *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
           }
+          RN_TL(tl, 600 + l * 10 + slot);
           tcgen05_fence_before();
           fence_proxy_async_smem();
           __syncwarp();
@@ -711,6 +722,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
             mbar_arrive_cluster(act_ready_leader + slot * 8);
             mbar_arrive(&staged[slot]);
           }
+          RN_TL(tl, 700 + l * 10 + slot);
         }
       }
     }
@@ -718,6 +730,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
     // ---------------- store warp: every layer's data gradient goes to global for the weight-gradient GEMMs ----------------
     if (lane == 0) {
       uint32_t it0 = 0, it1 = 0;
+      RN_TL_DECL(tl, 3, true);
       for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
         const int tiles_here = min(2, p.n_ptiles - grp * 2);
         for (int l = 0; l < p.n_layers; ++l) {
@@ -725,10 +738,12 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
             const uint32_t i = slot ? it1++ : it0++;
             const int row0 = ((grp * 2 + slot) * 2 + (int)rank) * 128;
             mbar_wait(&staged[slot], i & 1u);
+            RN_TL(tl, 3300 + l * 10 + slot);
             for (int c = 0; c < 4; ++c)
               tma_store_2d(&p.tmD[l], s_act + slot * kActBytes + c * kChunkBytes, c * 64, row0);
             tma_store_commit();
             tma_store_wait_read0();
+            RN_TL(tl, 3700 + l * 10 + slot);
             mbar_arrive(&store_done[slot]);
             if (l == p.n_layers - 1) mbar_arrive(&act_free[slot]);
           }
@@ -781,6 +796,11 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
   p.m_rows = M;
+#ifdef RN_EXPERIMENTS
+  p.timeline = g_pair_timeline_bwd;
+#else
+  p.timeline = nullptr;
+#endif
   static bool configured = false;
   if (!configured) {
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
@@ -867,5 +887,6 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
 
 #ifdef RN_EXPERIMENTS
 extern "C" int rn_pair_timeline(long long* device_buffer) { rn::g_pair_timeline = device_buffer; return 0; }
+extern "C" int rn_pair_timeline_bwd(long long* device_buffer) { rn::g_pair_timeline_bwd = device_buffer; return 0; }
 extern "C" int rn_pair_timeline_dims(int* roles, int* entries) { *roles = rn::kTlRoles; *entries = rn::kTlEntries; return 0; }
 #endif
