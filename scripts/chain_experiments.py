@@ -36,7 +36,7 @@ def timed(fn, n=3):
     return ms3[0] / n
 lib.rn_set_flag(0, 2)
 with torch.no_grad():
-    for dbg in sorted(pair_names):
+    for dbg in ([] if os.environ.get("RN_TRAIN_ONLY") == "1" else sorted(pair_names)):
         lib.rn_set_flag(1, dbg)
         ms = timed(lambda: fine.forward_raw(pts, dirs, 192))
         key = f"pair chain (inference) {pair_names[dbg]}"
@@ -46,7 +46,8 @@ lib.rn_set_flag(1, 0)
 # training-mode forward (stores + masks), smaller M to fit the activation workspace
 Mt = 16384 * 192
 pts_t, dirs_t = pts[:Mt].clone().requires_grad_(True), dirs[:16384]
-for dbg, nm in ((0, "all on"), (2, "no TMA stores"), (8, "no epilogue math"), (10, "no stores, no epilogue math")):
+for dbg, nm in ((0, "all on"), (1, "no weight loads"), (2, "no TMA stores"), (3, "no weight loads, no stores"),
+                (8, "no epilogue math"), (10, "no stores, no epilogue math")):
     lib.rn_set_flag(1, dbg)
     ms = timed(lambda: fine.forward_raw(pts_t, dirs_t, 192))
     key = f"pair chain (training fwd, {Mt} pts) {nm}"
