@@ -21,6 +21,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 if os.environ.get("RN_EXPERIMENTS") == "1":      # measurement-only knobs (scripts/chain_experiments.py); never shipped
     FLAGS.append("-DRN_EXPERIMENTS")
+FLAGS += os.environ.get("RN_EXTRA_FLAGS", "").split()      # variant builds for A/B timing (scripts/ab.sh)
 
 
 def _digest():
