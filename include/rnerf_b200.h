@@ -114,6 +114,20 @@ size_t rn_image_metrics_scratch_bytes(int N, int H, int W);
 int rn_image_metrics(const float* pred, const float* target, int N, int H, int W, float C1, float C2, float* scratch,
                      float* mse_out /*[N]*/, float* ssim_out /*[N]*/, rn_stream_t stream);
 
+/* ---- pose-noise initialisation and pose-error tracking: noise.py:71-268, train_pose_opt.py:232-271
+ *       ---- */
+/* noisy_out[i] = add_noise_to_pose(poses[i]) for n camera-to-world matrices [n,4,4], given the raw standard-normal
+ * draws of the reference's generator calls: g_angle [n] and g_axis [n,3] (random_rotation_matrix: angle = g * std_rad
+ * about the normalised axis, Rodrigues, left-multiplied onto R; both NULL = no rotation noise) and g_trans [n,3]
+ * (random_translation; NULL = none).  Translation std = |camera position| * trans_pct / 100 when trans_pct > 0
+ * (NoiseConfig.get_translation_std), else trans_std_abs.  info_out [n,2] (may be NULL): actual_rotation_deg,
+ * actual_translation_norm of add_noise_to_pose's noise_info. */
+int rn_pose_noise(const float* poses, int n, const float* g_angle, const float* g_axis, const float* g_trans,
+                  float rot_std_rad, float trans_std_abs, double trans_pct, float* noisy_out, float* info_out,
+                  rn_stream_t stream);
+/* err_out[i] = {rotation_error_deg, translation_error} of compute_pose_error(gt_poses[i], cur_poses[i]) (noise.py:237-268). */
+int rn_pose_errors(const float* gt_poses, const float* cur_poses, int n, float* err_out /*[n,2]*/, rn_stream_t stream);
+
 /* ---- sampling: rays.py:145-333 ---- */
 /* z = lower + (upper-lower)*t_rand over the base depths z_base (linspace built by the caller,
  * rays.py:185-195); t_rand NULL = no perturbation.  pts may be NULL. */

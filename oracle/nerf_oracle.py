@@ -681,6 +681,44 @@ def compute_pose_error(pose_gt, pose_est):
             "translation_error": float(np.sqrt((dt * dt).sum()))}
 
 
+def add_noise_to_poses(poses, g_angle, g_axis, g_trans, rotation_noise_deg=0.0, translation_noise=0.0,
+                       translation_noise_pct=0.0):
+    """noisy_src/noise.py:71-234 (random_rotation_matrix, random_translation, add_noise_to_pose, add_noise_to_poses) given
+    the raw standard-normal draws of the reference's generator calls (per pose randn(1), randn(3) for the rotation,
+    randn(3) for the translation; None = that noise is off).  fp32 throughout, sums in index order.
+    Returns (noisy poses [n,4,4], info [n,2] = actual_rotation_deg, actual_translation_norm)."""
+    poses = _f32(poses)
+    n = poses.shape[0]
+    out, info = poses.copy(), np.zeros((n, 2), F32)
+    std_rad = F32(rotation_noise_deg * np.pi / 180.0)
+    for i in range(n):
+        if g_angle is not None:
+            a = F32(F32(g_angle[i]) * std_rad)
+            ax = _f32(g_axis[i])
+            ax = (ax / np.sqrt(F32(F32(ax[0] * ax[0] + ax[1] * ax[1]) + ax[2] * ax[2]))).astype(F32)
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]], F32)
+            KK = np.zeros((3, 3), F32)
+            for r in range(3):
+                for c in range(3):
+                    KK[r, c] = F32(F32(K[r, 0] * K[0, c] + K[r, 1] * K[1, c]) + K[r, 2] * K[2, c])
+            R = ((np.eye(3, dtype=F32) + np.sin(a).astype(F32) * K).astype(F32) + F32(F32(1.0) - np.cos(a).astype(F32)) * KK).astype(F32)
+            Ro = poses[i, :3, :3]
+            for r in range(3):
+                for c in range(3):
+                    out[i, r, c] = F32(F32(R[r, 0] * Ro[0, c] + R[r, 1] * Ro[1, c]) + R[r, 2] * Ro[2, c])
+            tr = F32(F32(R[0, 0] + R[1, 1]) + R[2, 2])
+            ang = np.arccos(np.clip(F32(tr - F32(1.0)) / F32(2.0), F32(-1.0), F32(1.0))).astype(F32)
+            info[i, 0] = F32(F32(ang * F32(180.0)) / F32(np.pi))
+        if g_trans is not None:
+            t = poses[i, :3, 3]
+            dist = np.sqrt(F32(F32(t[0] * t[0] + t[1] * t[1]) + t[2] * t[2])).astype(F32)
+            std = F32(float(dist) * (translation_noise_pct / 100.0)) if translation_noise_pct > 0 else F32(translation_noise)
+            d = (_f32(g_trans[i]) * std).astype(F32)
+            out[i, :3, 3] = (t + d).astype(F32)
+            info[i, 1] = np.sqrt(F32(F32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]))
+    return out, info
+
+
 def compute_pose_errors(poses, gt_poses):
     """noisy_src/train_pose_opt.py:232-271."""
     r, t = zip(*[(e["rotation_error_deg"], e["translation_error"])

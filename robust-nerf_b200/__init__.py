@@ -14,6 +14,8 @@ from .train import (train_step, train_step_with_poses, render_image, render_imag
                     Trainer, render_views_sharded)
 from .synthetic import BlenderData, make_scene, lego_poses, hemisphere_poses, add_noise_to_poses
 from .metrics import image_metrics, compute_ssim, compute_mse
+from .noise import NoiseConfig, set_noise_seed, draw_pose_noise, compute_pose_error, compute_pose_errors_batch
+from . import noise
 
 __all__ = [
     "NeRFConfig", "ModelConfig", "RenderConfig", "DataConfig", "TrainConfig", "PoseOptConfig",
@@ -23,4 +25,5 @@ __all__ = [
     "train_step", "train_step_with_poses", "render_image", "render_image_with_pose", "compute_psnr", "Trainer",
     "render_views_sharded", "BlenderData", "make_scene", "lego_poses", "hemisphere_poses", "add_noise_to_poses",
     "image_metrics", "compute_ssim", "compute_mse",
+    "NoiseConfig", "set_noise_seed", "draw_pose_noise", "compute_pose_error", "compute_pose_errors_batch", "noise",
 ]

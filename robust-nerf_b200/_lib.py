@@ -47,6 +47,8 @@ _SIGS = {
     "rn_pixel_gather": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
     "rn_image_metrics_scratch_bytes": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "rn_image_metrics": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float, _P, _P, _P, _P]),
+    "rn_pose_noise": (c_int, [_P, c_int, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_double, _P, _P, _P]),
+    "rn_pose_errors": (c_int, [_P, _P, c_int, _P, _P]),
     "rn_pixel_gather_u8": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
     "rn_stratified_fwd": (c_int, [_P, _P, c_int64, _P, c_int, _P, _P, _P, _P]),
     "rn_points_fwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),

@@ -4,6 +4,7 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -51,17 +52,15 @@ class CameraPoseParameters(nn.Module):
     def compute_pose_errors(self, ground_truth_poses: torch.Tensor, indices: Optional[torch.Tensor] = None
                             ) -> Dict[str, float]:
         """Geodesic rotation error (deg) and translation L2 statistics (train_pose_opt.py:232-271,
-        noise.py:237-268), batched on the device: one host sync instead of 200."""
+        noise.py:237-268): one launch over all poses (`rn_pose_errors`) and one host copy instead of 200
+        `.item()` synchronisations; the statistics are numpy float64 over the per-pose values, as in the reference."""
+        from .noise import compute_pose_errors_batch
         cur = self.get_poses(indices)
         gt = ground_truth_poses.to(cur.device)
         if indices is not None:
             gt = gt[indices]
-        Rd = torch.matmul(gt[:, :3, :3].transpose(-1, -2), cur[:, :3, :3])
-        tr = Rd[:, 0, 0] + Rd[:, 1, 1] + Rd[:, 2, 2]
-        rot = torch.acos(torch.clamp((tr - 1) / 2, -1, 1)) * (180.0 / torch.pi)
-        tra = torch.norm(gt[:, :3, 3] - cur[:, :3, 3], dim=-1)
-        stats = torch.stack([rot.double().mean(), rot.double().std(unbiased=False), rot.double().max(),
-                             tra.double().mean(), tra.double().std(unbiased=False), tra.double().max()]).tolist()
-        keys = ("rotation_error_mean", "rotation_error_std", "rotation_error_max",
-                "translation_error_mean", "translation_error_std", "translation_error_max")
-        return dict(zip(keys, stats))
+        err = compute_pose_errors_batch(gt, cur).cpu().numpy().astype(np.float64)
+        rot, tra = err[:, 0], err[:, 1]
+        return {"rotation_error_mean": float(np.mean(rot)), "rotation_error_std": float(np.std(rot)),
+                "rotation_error_max": float(np.max(rot)), "translation_error_mean": float(np.mean(tra)),
+                "translation_error_std": float(np.std(tra)), "translation_error_max": float(np.max(tra))}

@@ -55,26 +55,10 @@ def hemisphere_poses(n: int, radius: float = 4.0311, seed: int = 1, device="cpu"
 
 def add_noise_to_poses(poses: torch.Tensor, rotation_noise_deg: float = 0.0, translation_noise_pct: float = 0.0,
                        seed: Optional[int] = None) -> torch.Tensor:
-    """Pose perturbation with the semantics of noisy_src/noise.py:71-234: per pose, a Gaussian angle
-    (std in degrees) about a uniformly random axis, left-multiplied onto R; Gaussian translation with
-    std = pct% of the camera distance.  Draw order (randn(1), randn(3), randn(3) per pose on the CPU
-    generator) follows the reference so the same seed gives the same noisy initialisation."""
-    if seed is not None:
-        torch.manual_seed(seed)
-        np.random.seed(seed)
-    P = poses.detach().cpu().clone()
-    for i in range(P.shape[0]):
-        dist = float(torch.norm(P[i, :3, 3]))
-        if rotation_noise_deg > 0:
-            ang = torch.randn(1) * (rotation_noise_deg * np.pi / 180.0)
-            ax = torch.randn(3)
-            ax = ax / torch.norm(ax)
-            K = torch.tensor([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
-            Rn = torch.eye(3) + torch.sin(ang) * K + (1 - torch.cos(ang)) * (K @ K)
-            P[i, :3, :3] = Rn @ P[i, :3, :3]
-        if translation_noise_pct > 0:
-            P[i, :3, 3] = P[i, :3, 3] + torch.randn(3) * (dist * translation_noise_pct / 100.0)
-    return P.to(poses.device)
+    """Noisy initial poses for a synthetic scene: shorthand for `noise.add_noise_to_poses` (noisy_src/noise.py:194-234
+    semantics, CUDA arithmetic, the reference's draw order on the CPU generator) that returns only the poses."""
+    from .noise import NoiseConfig, add_noise_to_poses as _add
+    return _add(poses, NoiseConfig(rotation_noise_deg, 0.0, translation_noise_pct, seed))[0]
 
 
 def make_scene(H: int = 800, W: int = 800, n_views: int = 100, seed: int = 0, device="cuda",

@@ -884,3 +884,42 @@ def test_render_views_tile_sharded(rn, dev):
     img = rn.render_image_with_pose(nc, nf, poses[0], H, W, focal, cfg, chunk_size=700)
     assert img["rgb"].shape == (H, W, 3) and img["depth"].shape == (H, W)
     assert (img["rgb"].reshape(-1, 3) - full["rgb"][0]).abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
+def test_pose_noise_and_pose_errors_against_reference_and_oracle(rn, dev):
+    """SURVEY section 8f row 4 through the C ABI (rn_pose_noise, rn_pose_errors): noisy poses / noise_info /
+    per-pose errors against the unmodified reference's (tests/golden/noise.npz; noisy_src/noise.py:138-268) and the
+    numpy restatement on the same draws; CPU and CUDA input poses, the empty batch, a single pair."""
+    g = load_golden("noise")
+    poses = g["poses"]
+    for tag in ("rot5_pct5", "rot2_abs", "pct3", "rot1p5", "clean"):
+        rot, tabs, pct, seed = g[f"{tag}_cfg"]
+        cfg = rn.NoiseConfig(float(rot), float(tabs), float(pct), seed=int(seed))
+        for src in (torch.from_numpy(poses), T(poses, dev)):
+            noisy, infos = rn.noise.add_noise_to_poses(src, cfg)
+            assert noisy.device == src.device and len(infos) == len(poses)
+            close(N(noisy), g[f"{tag}_noisy"], rtol=0, atol=1e-6)
+            info = np.array([[d.get("actual_rotation_deg", 0.0), d.get("actual_translation_norm", 0.0)] for d in infos])
+            close(info[:, 0], g[f"{tag}_info"][:, 0], rtol=1e-4, atol=5e-3)
+            close(info[:, 1], g[f"{tag}_info"][:, 1], rtol=1e-5, atol=1e-6)
+            assert ("actual_rotation_deg" in infos[0]) == (rot > 0)
+            assert "actual_translation_norm" not in infos[7] or tabs > 0      # the camera at the origin under % noise
+        ga, gx, gt_ = rn.draw_pose_noise(torch.from_numpy(poses), cfg)
+        o_noisy, o_info = O.add_noise_to_poses(poses, None if ga is None else ga.numpy(), None if gx is None else gx.numpy(),
+                                               None if gt_ is None else gt_.numpy(), float(rot), float(tabs), float(pct))
+        close(N(noisy), o_noisy, rtol=0, atol=5e-7)
+        close(info[:, 1], o_info[:, 1], rtol=1e-6, atol=1e-7)
+        err = N(rn.compute_pose_errors_batch(T(poses, dev), T(g[f"{tag}_noisy"], dev)))
+        # acos near 1 turns one ulp of the trace into ~0.03 degrees
+        close(err[:, 0], g[f"{tag}_err"][:, 0], rtol=1e-4, atol=0.06)
+        close(err[:, 1], g[f"{tag}_err"][:, 1], rtol=1e-5, atol=1e-6)
+    one = rn.compute_pose_error(torch.from_numpy(poses[3]), torch.from_numpy(g["rot5_pct5_noisy"][3]))
+    np.testing.assert_allclose([one["rotation_error_deg"], one["translation_error"]], g["rot5_pct5_err"][3], rtol=1e-4, atol=1e-5)
+    empty, infos = rn.noise.add_noise_to_poses(torch.zeros(0, 4, 4, device=dev), rn.NoiseConfig(5.0, 0.0, 5.0, seed=1))
+    assert empty.shape == (0, 4, 4) and infos == []
+    assert rn.compute_pose_errors_batch(torch.zeros(0, 4, 4, device=dev), torch.zeros(0, 4, 4, device=dev)).shape == (0, 2)
+    with pytest.raises(ValueError):
+        rn.compute_pose_errors_batch(torch.zeros(2, 4, 4, device=dev), torch.zeros(3, 4, 4, device=dev))
+    # the shorthand used for synthetic scenes is the same path
+    close(N(rn.add_noise_to_poses(torch.from_numpy(poses), 5.0, 5.0, seed=42)), g["rot5_pct5_noisy"], rtol=0, atol=1e-6)

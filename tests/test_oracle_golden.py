@@ -244,3 +244,4 @@ def test_metrics_oracle_against_reference():
             assert abs(O.compute_ssim(p, t) - g[f"{tag}_ssim"][i]) <= 1e-6
     same = g["tiny_target"][0]
     assert O.compute_psnr(same, same) == float("inf") and abs(O.compute_ssim(same, same) - 1.0) < 1e-6
+
