@@ -44,20 +44,32 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clock / throttle-reason sampling.  The sampler is started before the warm-up (nvidia-smi needs ~100 ms
+    to produce its first line, as long as a whole 20-step timed region) and the samples are then filtered to the
+    wall-clock windows of the timed regions (`mark()` ... `mark()`)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/rn_clocks_{os.getpid()}.csv"
+        self.windows, self._open = [], None
 
     def start(self):
         try:
             self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
                                           "-i", str(self.gpu)], stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Open / close a timed-region window (call right before the first and right after the last synchronised step)."""
+        now = time.time()
+        if self._open is None:
+            self._open = now
+        else:
+            self.windows.append((self._open, now))
+            self._open = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -69,20 +81,28 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.fh.close()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if any(a - 0.005 <= r[0] <= b + 0.005 for a, b in self.windows)]
+        used = inside if inside else rows
+        reasons = set()
+        for r in used:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if used:
+            out = {"sm_mhz": statistics.median([r[1] for r in used]), "sm_max_mhz": max(r[2] for r in used),
+                   "reasons": sorted(reasons), "samples": len(used),
+                   "window": "timed regions (value + e2e)" if inside else "whole run (no sample fell inside a timed region)"}
         try:
             os.remove(self.path)
         except OSError:
@@ -234,19 +254,20 @@ def run_gpu(args):
     eager_ms_per_step = reduce_max(e0.elapsed_time(e1)) / K_
 
     # ---- device-resident timing (value): the same step, replayed from a CUDA graph unless --no-graph ----
-    for i in range(W_):
-        step_fn(*dev_batches[i % POOL])
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for i in range(W_):
+        step_fn(*dev_batches[i % POOL])
+    barrier()
+    clocks.mark()
     e0.record()
     for i in range(K_):
         loss = step_fn(*dev_batches[i % POOL])
     e1.record()
     barrier()
+    clocks.mark()
     t_ms = reduce_max(e0.elapsed_time(e1))
-    clock_info = clocks.stop() if rank == 0 else None
     ms_per_step = t_ms / K_
     value = world * RAYS_PER_GPU * K_ / (t_ms * 1e-3)
     loss_val = float(loss.item())
@@ -280,10 +301,13 @@ def run_gpu(args):
 
     e2e_loop(3)
     barrier()
+    clocks.mark()
     e0.record()
     e2e_loop(K_)
     e1.record()
     barrier()
+    clocks.mark()
+    clock_info = clocks.stop() if rank == 0 else None
     t_e2e = reduce_max(e0.elapsed_time(e1))
     e2e_value = world * RAYS_PER_GPU * K_ / (t_e2e * 1e-3)
 
