@@ -17,6 +17,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// 256-bit global stores (sm_100: STG.E.ENL2.256): sixteen bf16 from sixteen floats, or zeros
+__device__ __forceinline__ void stg256_bf16x16(__nv_bfloat16* p, const float* f) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])),
+                 "r"(pack_bf16(f[6], f[7])), "r"(pack_bf16(f[8], f[9])), "r"(pack_bf16(f[10], f[11])),
+                 "r"(pack_bf16(f[12], f[13])), "r"(pack_bf16(f[14], f[15]))
+               : "memory");
+}
+__device__ __forceinline__ void stg256_zero(__nv_bfloat16* p) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(p), "r"(0u) : "memory");
+}
+
 // feat[0..3*(1+2L)) for one 3-vector, reference order: x, then per frequency sin(xyz), cos(xyz)
 template <int L>
 __device__ __forceinline__ void encode3(const float x[3], float* feat) {
@@ -43,11 +55,10 @@ encode_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, int
     const float x[3] = {__ldcs(pts + m * 3), __ldcs(pts + m * 3 + 1), __ldcs(pts + m * 3 + 2)};
     encode3<kPosFreqs>(x, feat);
     feat[63] = 0.f;
-    uint4* dst = reinterpret_cast<uint4*>(XC + m * ldx);
+    // one full 32-byte sector per store instruction (rows are 32-byte aligned: ld is a multiple of 16 elements)
+    __nv_bfloat16* dst = XC + m * ldx;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      dst[i] = make_uint4(pack_bf16(feat[8 * i], feat[8 * i + 1]), pack_bf16(feat[8 * i + 2], feat[8 * i + 3]),
-                          pack_bf16(feat[8 * i + 4], feat[8 * i + 5]), pack_bf16(feat[8 * i + 6], feat[8 * i + 7]));
+    for (int i = 0; i < 4; ++i) stg256_bf16x16(dst + 16 * i, feat + 16 * i);
     if (FD) {
       const int64_t r = m / group;
       const float d[3] = {__ldg(dirs + r * 3), __ldg(dirs + r * 3 + 1), __ldg(dirs + r * 3 + 2)};
@@ -55,13 +66,11 @@ encode_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, int
       encode3<kDirFreqs>(d, df);
 #pragma unroll
       for (int i = 27; i < 32; ++i) df[i] = 0.f;
-      uint4* dd = reinterpret_cast<uint4*>(FD + m * ldf + 256);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        dd[i] = make_uint4(pack_bf16(df[8 * i], df[8 * i + 1]), pack_bf16(df[8 * i + 2], df[8 * i + 3]),
-                           pack_bf16(df[8 * i + 4], df[8 * i + 5]), pack_bf16(df[8 * i + 6], df[8 * i + 7]));
-#pragma unroll
-      for (int i = 4; i < 8; ++i) dd[i] = make_uint4(0, 0, 0, 0);
+      __nv_bfloat16* dd = FD + m * ldf + 256;
+      stg256_bf16x16(dd, df);
+      stg256_bf16x16(dd + 16, df + 16);
+      stg256_zero(dd + 32);
+      stg256_zero(dd + 48);
     }
   }
 }
