@@ -15,8 +15,12 @@ against the reference's only recorded known-answer data
 Each function cites the reference file:line it follows (paths relative to the
 reference repo root).  Arithmetic is float32 end to end, like the reference.
 Summation-order contract for the inverse-CDF sampler (`sample_pdf`): the weight sum and
-the cumulative sum are SEQUENTIAL fp32 left-to-right adds -- this is the order the CUDA
-kernel implements, so sample indices are bit-exact between the two.
+the cumulative sum follow a fixed 32-lane scan order (`_warp_scan`: contiguous chunk per
+lane summed left to right, Kogge-Stone over the lane totals) -- the order the CUDA kernel
+implements (`warp_build_cdf`), so sample indices are bit-exact between the two.
+Golden vectors of the later rows: `tests/golden/make_golden_metrics.py` (metrics.py) and
+`tests/golden/make_golden_noise.py` (noise.py), checked in `tests/test_oracle_golden.py` /
+`tests/test_host_cpu.py`.
 """
 from __future__ import annotations
 
