@@ -923,3 +923,53 @@ def test_pose_noise_and_pose_errors_against_reference_and_oracle(rn, dev):
         rn.compute_pose_errors_batch(torch.zeros(2, 4, 4, device=dev), torch.zeros(3, 4, 4, device=dev))
     # the shorthand used for synthetic scenes is the same path
     close(N(rn.add_noise_to_poses(torch.from_numpy(poses), 5.0, 5.0, seed=42)), g["rot5_pct5_noisy"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_full_size_step_properties(rn, dev):
+    """BASELINE configs[1] at its full size (4096-ray batch, 64+128 samples: 1,048,576 MLP points), checked through
+    properties that do not need the oracle to run a million points: (i) the step is bit-reproducible (no float atomics:
+    same seed -> identical loss and identical gradient buffer); (ii) with deterministic sampling the loss is a mean
+    over rays, so the full batch's loss / gradient equal the average of its two halves' (only the split-K summation
+    order of the weight-gradient GEMMs differs); (iii) one optimiser step lowers the loss on the same batch."""
+    data, ds, sampler, pb = _scene_batch(rn, dev, 4096, seed=77)
+    with torch.no_grad():
+        ro, rd = sampler.get_rays_for_batch(pb, data.poses)
+    tgt = pb.target_rgb
+    mc, mf = _two_nets(rn, dev)
+    # (ii) same stratified offsets and inverse-CDF draws for a ray whether it is rendered in the full batch or in a half
+    # (training mode draws u at random even with perturb off, rendering.py:213, so the draws are passed explicitly)
+    g = torch.Generator(device=dev).manual_seed(3)
+    t_rand = torch.rand(4096, 64, device=dev, generator=g)
+    u = torch.rand(4096, 128, device=dev, generator=g)
+    params = list(mc.parameters()) + list(mf.parameters())
+
+    def loss_and_grad(sl):
+        for p_ in params:
+            p_.grad = None
+        out = rn.render_rays(mc, mf, ro[sl].contiguous(), rd[sl].contiguous(), rn.RenderConfig(), is_train=True,
+                             t_rand=t_rand[sl].contiguous(), u=u[sl].contiguous())
+        loss = torch.nn.functional.mse_loss(out["rgb_coarse"], tgt[sl]) + torch.nn.functional.mse_loss(out["rgb_fine"], tgt[sl])
+        loss.backward()
+        return float(loss.detach()), torch.cat([p_.grad.reshape(-1) for p_ in params]).clone()
+
+    full_loss, g_full = loss_and_grad(slice(0, 4096))
+    halves = [loss_and_grad(slice(0, 2048)), loss_and_grad(slice(2048, 4096))]
+    np.testing.assert_allclose(full_loss, 0.5 * (halves[0][0] + halves[1][0]), rtol=2e-6)
+    g_avg = 0.5 * (halves[0][1] + halves[1][1])
+    rel = ((g_full - g_avg).double().norm() / g_full.double().norm()).item()
+    assert rel < 1e-5, rel
+    tr = rn.Trainer(mc, mf, rn.RenderConfig(), lr=5e-4)
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(9)
+        loss = tr.step_rays(ro, rd, tgt, optimise=False)
+        runs.append((float(loss), tr.gflat.clone()))
+    assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1])
+    assert torch.isfinite(runs[0][1]).all() and runs[0][1].abs().max().item() > 0
+    # (iii) it trains
+    torch.manual_seed(9)
+    l0 = float(tr.step_rays(ro, rd, tgt))
+    torch.manual_seed(9)
+    l1 = float(tr.step_rays(ro, rd, tgt, optimise=False))
+    assert l1 < l0, (l0, l1)
