@@ -209,3 +209,25 @@ def test_pose_noise_oracle_against_reference(rn):
     assert str(rn.NoiseConfig(5.0, 0.0, 5.0)) == "rot5.0deg_trans5.0pct" and str(rn.NoiseConfig()) == "clean"
     assert rn.NoiseConfig(0.0, 0.1).has_noise and not rn.NoiseConfig().has_noise
     assert rn.NoiseConfig(0, 0.2, 0).get_translation_std(4.0) == 0.2 and rn.NoiseConfig(0, 0.2, 5.0).get_translation_std(4.0) == 0.2
+
+
+def test_committed_bench_line_has_every_contract_key():
+    """The bench line committed under profiles/ (produced by `python bench.py` on a B200) carries every key of the
+    measurement contract: headline, e2e with per-step copy sizes, clocks, launch count, roofline, CPU baseline."""
+    import json
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_1gpu_final.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["unit"] == "rays/s" and line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["data"] == "synthetic" and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert abs(line["value"] - 4096 / (line["ms_per_step"] * 1e-3)) / line["value"] < 1e-6
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] == 4096 * 9 * 4 and e["d2h_bytes_per_step"] == 4 and 0 < e["value"] <= line["value"] * 1.02
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    c = line["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert line["gpu_launches"] > 0 and line["clocks"]["sm_mhz"] and not set(line["clocks"]["reasons"]) & {
+        "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
