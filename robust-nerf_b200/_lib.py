@@ -116,8 +116,13 @@ def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tenso
         raise RuntimeError(f"{name} is on {t.device}: the B200 path has no CPU fallback, move it to a CUDA device")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"{name} lives on {t.device} but the current CUDA device is {torch.cuda.current_device()}: "
+                           "kernels launch on the current device's stream (use torch.cuda.device(...) / set_device)")
     return t.contiguous()
 
 
 def call(name: str, *args) -> None:
+    """Invoke a C-ABI entry point.  The kernels launch on the CURRENT device's stream (`stream_ptr()`), and every
+    wrapper validates its tensors with `require_cuda`, which refuses tensors that live on another device."""
     check(getattr(lib(), name)(*args), name)

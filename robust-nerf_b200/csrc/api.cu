@@ -9,16 +9,15 @@ int g_last_cuda_error = 0;
 unsigned long long g_launch_count = 0;
 
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      return kNumSMsDefault;
+  static int cached[kMaxDevices] = {0};
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMsDefault;
+  int& c = cached[dev & (kMaxDevices - 1)];
+  if (c == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) c = n;
+    else return kNumSMsDefault;
   }
-  return cached;
+  return c;
 }
 
 constexpr int kMaxGroups = 8;

@@ -103,14 +103,13 @@ struct PairParams {
   float* raw;
 };
 
-// Biases and fp32 head weights of the network being evaluated (layout::kF32Elems floats), copied device-to-device on the
-// launching stream before each launch.  Every lane of an epilogue warp needs the SAME bias values: read through the
-// constant cache they cost no LSU/L1 cycles (a uniform LDG.128 per 4 columns made the load/store unit -- shared with the
-// tensor core's operand reads -- the bottleneck of the epilogue, profiles/r01_pair_experiments.md).
-__constant__ float2 c_pair_consts2[1664 + 128];   // + slack: the bias staging copies 256 floats from any bias offset
-#define c_pair_consts (reinterpret_cast<const float*>(c_pair_consts2))
-static_assert(layout::kF32Elems <= 3328, "constant staging buffer too small");
-
+// Biases and fp32 head weights of the network being evaluated come straight from the fp32 section of the packed-weight
+// buffer (`PairParams::consts`, layout::kF32Elems floats): there is NO process-global per-launch state, so forwards of
+// different networks may overlap on different streams or threads (the earlier __constant__ staging copy
+// raced).  Every lane of an epilogue warp needs the SAME values: the per-layer bias is staged once per layer into shared
+// memory (a uniform LDG.128 per 4 columns made the load/store unit -- shared with the tensor core's operand reads -- the
+// bottleneck of the epilogue, profiles/r01_pair_experiments.md); the head weights (two of ten layers) are warp-uniform
+// read-only loads that hit L1.
 __device__ __forceinline__ uint64_t fadd2(uint32_t a_lo, uint32_t a_hi, float2 b) {
   uint64_t a, bb, r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a_lo), "r"(a_hi));
@@ -134,8 +133,8 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 // c = chunk index inside the layer output (columns 8c .. 8c+7).
 template <int HEADS, bool RELU, bool WMASK>
 __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int c, uint8_t* s_tile, int row, const float* s_bias,
-                                                    int head_w_off, int n, uint32_t& outbits, float2& hh0, float2& hh1,
-                                                    float2& hh2) {
+                                                    const float2* __restrict__ consts2, int head_w2_off, int n, uint32_t& outbits,
+                                                    float2& hh0, float2& hh1, float2& hh2) {
   const int G = c >> 2, cc = c & 3;               // 32-column group and chunk inside it
   const float4 bA = *reinterpret_cast<const float4*>(s_bias + c * 8);          // broadcast LDS.128 from the per-layer staging
   const float4 bB = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
@@ -159,12 +158,12 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
     if (HEADS > 0) {
       // fused head (model.py:181,194): fp32 dot with the bf16-rounded activation; even and odd columns accumulate in
       // the two halves of a packed fp32 pair
-      const int w2 = (head_w_off >> 1) + c * 4 + e;
+      const int w2 = head_w2_off + c * 4 + e;
       const float2 a = make_float2(__uint_as_float(packed[e] << 16), __uint_as_float(packed[e] & 0xFFFF0000u));
-      hh0 = ffma2(a, c_pair_consts2[w2], hh0);
+      hh0 = ffma2(a, __ldg(consts2 + w2), hh0);
       if (HEADS == 3) {
-        hh1 = ffma2(a, c_pair_consts2[w2 + (n >> 1)], hh1);
-        hh2 = ffma2(a, c_pair_consts2[w2 + n], hh2);
+        hh1 = ffma2(a, __ldg(consts2 + w2 + (n >> 1)), hh1);
+        hh2 = ffma2(a, __ldg(consts2 + w2 + n), hh2);
       }
     }
   }
@@ -183,7 +182,8 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
 // share one instruction stream.
 template <int NG, int HEADS, bool RELU, bool WMASK>
 __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int g0, const float* s_bias,
-                                              int head_w_off, int n, uint32_t (&mb)[2], float& h0, float& h1, float& h2) {
+                                              const float2* __restrict__ consts2, int head_w2_off, int n, uint32_t (&mb)[2],
+                                              float& h0, float& h1, float& h2) {
   constexpr int NC = NG * 4;                      // 8-column chunks handled by this warp
   const int c0 = g0 * 4;
   float2 hh0 = make_float2(0.f, 0.f), hh1 = make_float2(0.f, 0.f), hh2 = make_float2(0.f, 0.f);
@@ -193,8 +193,8 @@ __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, 
     uint32_t lo8[8], hi8[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { lo8[k] = v[k]; hi8[k] = v[8 + k]; }
-    pair_epilogue_chunk<HEADS, RELU, WMASK>(lo8, c, s_tile, row, s_bias, head_w_off, n, outbits, hh0, hh1, hh2);
-    pair_epilogue_chunk<HEADS, RELU, WMASK>(hi8, c + 1, s_tile, row, s_bias, head_w_off, n, outbits, hh0, hh1, hh2);
+    pair_epilogue_chunk<HEADS, RELU, WMASK>(lo8, c, s_tile, row, s_bias, consts2, head_w2_off, n, outbits, hh0, hh1, hh2);
+    pair_epilogue_chunk<HEADS, RELU, WMASK>(hi8, c + 1, s_tile, row, s_bias, consts2, head_w2_off, n, outbits, hh0, hh1, hh2);
   };
   tmem_ld_x16(t_addr, va);
 #pragma unroll 1
@@ -377,7 +377,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
         // stage this layer's bias: every epilogue warp has finished the previous layer (first barrier), 256 threads copy
         // one value each out of the constant table, and the copies are visible to all (second barrier)
         named_bar_sync(5, 512);
-        if (threadIdx.x - 64 < 256) s_bias[threadIdx.x - 64] = c_pair_consts[L.bias_off + (threadIdx.x - 64)];
+        if (threadIdx.x - 64 < 256) s_bias[threadIdx.x - 64] = __ldg(p.consts + L.bias_off + (threadIdx.x - 64));
         named_bar_sync(5, 512);
         for (int slot = 0; slot < tiles_here; ++slot) {
           const uint32_t i = slot ? it1++ : it0++;
@@ -400,11 +400,11 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
           }
           else {
             if (L.n == 256) {
-              if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2);
-              else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2);
-              else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, s_bias, L.head_w_off, 256, mb, h0, h1, h2);
+              if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, reinterpret_cast<const float2*>(p.consts), L.head_w_off >> 1, 256, mb, h0, h1, h2);
+              else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, reinterpret_cast<const float2*>(p.consts), L.head_w_off >> 1, 256, mb, h0, h1, h2);
+              else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, s_bias, reinterpret_cast<const float2*>(p.consts), L.head_w_off >> 1, 256, mb, h0, h1, h2);
             } else {
-              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, s_bias, L.head_w_off, 128, mb, h0, h1, h2);
+              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, s_bias, reinterpret_cast<const float2*>(p.consts), L.head_w_off >> 1, 128, mb, h0, h1, h2);
             }
           }
           RN_TL(tl, 600 + l * 10 + slot);                  // math done
@@ -435,7 +435,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
               named_bar_sync(1 + q, 128);
             }
             if (cq == 0 && row_ok) {
-              const float* hb = c_pair_consts + L.head_b_off;
+              const float* hb = p.consts + L.head_b_off;
               float* o = p.raw + gr * 4 + L.head_col;
               o[0] = h0 + s_hx[row] + hb[0];
               if (nh == 3) { o[1] = h1 + s_hx[128 + row] + hb[1]; o[2] = h2 + s_hx[256 + row] + hb[2]; }
@@ -801,11 +801,9 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
 #else
   p.timeline = nullptr;
 #endif
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured))
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
-    configured = true;
-  }
   const int n_groups = (p.n_ptiles + 1) / 2;
   const int max_clusters = num_sms() / 2;
   const int grid = 2 * (n_groups < max_clusters ? n_groups : max_clusters);
@@ -863,13 +861,11 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
   p.m_rows = M; p.consts = consts; p.raw = raw;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
-    configured = true;
   }
-  RN_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pair_consts2, consts, layout::kF32Elems * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
   const int n_groups = (p.n_ptiles + 1) / 2;
   const int max_clusters = num_sms() / 2;
   const int grid = 2 * (n_groups < max_clusters ? n_groups : max_clusters);

@@ -33,7 +33,19 @@ inline int cuda_fail(cudaError_t e) {
   } while (0)
 
 constexpr int kNumSMsDefault = 148;
-int num_sms();
+int num_sms();        // of the CURRENT device (cached per device)
+constexpr int kMaxDevices = 64;
+// One-time per-DEVICE setup (cudaFuncSetAttribute and friends are per device): true the first time it is called with
+// this mask while a given device is current.  Hosts call the library from one thread per device or from one thread
+// switching devices; the mask is a plain word because the setup it guards is idempotent.
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & (kMaxDevices - 1));
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

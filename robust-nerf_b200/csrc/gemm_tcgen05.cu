@@ -545,12 +545,10 @@ template <int BN, int MODE, int HEADS = 0, bool WMASK = false>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const GemmArgs& args, int grid,
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN, MODE>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured))
     RN_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, MODE, HEADS, WMASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
-    configured = true;
-  }
   int slot;
   prof_begin(MODE, st, &slot);
   gemm_kernel<BN, MODE, HEADS, WMASK><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tA, tB, tD, args);
@@ -560,14 +558,15 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 }
 
 int check_arch() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return RN_ERR_CUDA;
+  static int cached[kMaxDevices];            // 0 = unknown, 1 = ok, 2 = unsupported (per device)
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return RN_ERR_CUDA;
+  int& c = cached[dev & (kMaxDevices - 1)];
+  if (c == 0) {
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return RN_ERR_CUDA;
-    cached = (major == 10) ? RN_OK : RN_ERR_UNSUPPORTED_ARCH;
+    c = (major == 10) ? 1 : 2;
   }
-  return cached;
+  return c == 1 ? RN_OK : RN_ERR_UNSUPPORTED_ARCH;
 }
 
 // D[M,N] = act(A[M,K] B[N,K]^T + bias)        (forward layer)
@@ -1071,13 +1070,12 @@ int mlp_chain_forward(const ChainLayerHost* layers, int n_layers, int64_t M, con
   p.n_layers = n_layers;
   p.m_tiles = (int)ceil_div(M, kBlockM);
   p.m_rows = M; p.consts = consts; p.raw = raw;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fwd_kernel<true, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fwd_kernel<false, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fwd_kernel<true, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fwd_kernel<false, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    configured = true;
   }
   const int n_groups = (int)ceil_div(p.m_tiles, kChainG);
   const int grid = n_groups < num_sms() ? n_groups : num_sms();

@@ -16,10 +16,12 @@ namespace rn {
 
 constexpr int kWin = 11, kHalo = 5, kTile = 32, kPatch = kTile + 2 * kHalo;     // 42
 constexpr int kMetThreads = 256;
-__constant__ float c_ssim_window[kWin * kWin];
+// 11x11 Gaussian window, passed by value as a kernel parameter (parameters live in the constant bank): no process-global
+// __constant__ symbol, so no per-device first-use copy and nothing illegal under stream capture
+struct SsimWindow { float w[kWin * kWin]; };
 
 __global__ void __launch_bounds__(kMetThreads)
-image_metrics_tile_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, float C1, float C2,
+image_metrics_tile_kernel(const __grid_constant__ SsimWindow win, const float* __restrict__ pred, const float* __restrict__ target, int H, int W, float C1, float C2,
                           float* __restrict__ partial /*[N][tiles][2]*/) {
   extern __shared__ float smem[];
   float* s_p = smem;                                   // [42][42][3]
@@ -51,7 +53,7 @@ image_metrics_tile_kernel(const float* __restrict__ pred, const float* __restric
         const float* rt = s_t + ((oy + i) * kPatch + ox) * 3 + c;
 #pragma unroll
         for (int j = 0; j < kWin; ++j) {
-          const float w = c_ssim_window[i * kWin + j];
+          const float w = win.w[i * kWin + j];
           const float a = rp[j * 3], b = rt[j * 3];
           mp = fmaf(w, a, mp); mt = fmaf(w, b, mt);
           pp = fmaf(w, a * a, pp); tt = fmaf(w, b * b, tt); pt = fmaf(w, a * b, pt);
@@ -103,20 +105,18 @@ int rn_image_metrics(const float* pred, const float* target, int N, int H, int W
                      float* mse_out, float* ssim_out, rn_stream_t stream) {
   if (N == 0) return RN_OK;
   RN_REQUIRE(pred && target && scratch && mse_out && ssim_out && N > 0 && H > 0 && W > 0);
-  static bool window_set = false;
-  if (!window_set) {
-    // metrics.py:85-89: g = exp(-x^2 / (2 * 1.5^2)), g /= sum(g), window = outer(g, g), all in fp32
-    float g[kWin], s = 0.f, w2[kWin * kWin];
+  // metrics.py:85-89: g = exp(-x^2 / (2 * 1.5^2)), g /= sum(g), window = outer(g, g), all in fp32
+  SsimWindow win;
+  {
+    float g[kWin], s = 0.f;
     for (int i = 0; i < kWin; ++i) { const float x = (float)(i - kWin / 2); g[i] = expf(-(x * x) / (2.f * 1.5f * 1.5f)); s += g[i]; }
     for (int i = 0; i < kWin; ++i) g[i] /= s;
-    for (int i = 0; i < kWin; ++i) for (int j = 0; j < kWin; ++j) w2[i * kWin + j] = g[i] * g[j];
-    RN_CUDA_CHECK(cudaMemcpyToSymbol(c_ssim_window, w2, sizeof(w2)));
-    window_set = true;
+    for (int i = 0; i < kWin; ++i) for (int j = 0; j < kWin; ++j) win.w[i * kWin + j] = g[i] * g[j];
   }
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, N);
   const size_t smem = (size_t)2 * kPatch * kPatch * 3 * sizeof(float);
-  image_metrics_tile_kernel<<<grid, kMetThreads, smem, st>>>(pred, target, H, W, C1, C2, scratch);
+  image_metrics_tile_kernel<<<grid, kMetThreads, smem, st>>>(win, pred, target, H, W, C1, C2, scratch);
   RN_LAUNCH_CHECK();
   image_metrics_reduce_kernel<<<N, 32, 0, st>>>(scratch, N, (int)(grid.x * grid.y), 1.0f / ((float)H * (float)W * 3.0f), mse_out, ssim_out);
   RN_LAUNCH_CHECK();

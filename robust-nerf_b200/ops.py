@@ -307,10 +307,12 @@ class PackedWeights:
     def __init__(self):
         self.buf: Optional[torch.Tensor] = None
         self.key = None
-        # Optional flat fp32 gradient sink (RN_NUM_PARAMS floats).  When set (Trainer), the backward
-        # kernels write this network's parameter gradients straight into it (overwrite, one MLP call per
-        # net and step) and autograd receives None for the parameters -- no 48 accumulate launches.
+        # Optional flat fp32 gradient sink (RN_NUM_PARAMS floats).  While set (only inside a Trainer step, see
+        # Trainer._sinks), the backward kernels write this network's parameter gradients straight into it and autograd
+        # receives None for the parameters -- no 48 accumulate launches.  The first backward through the net after
+        # the sink was armed overwrites, any further one (chunked rendering, gradient accumulation) adds.
         self.grad_sink: Optional[torch.Tensor] = None
+        self.sink_dirty = False
 
     def get(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
         key = tuple((p.data_ptr(), p._version) for p in params)
@@ -378,13 +380,17 @@ class NeRFMLP(torch.autograd.Function):
         pts, dirs = ctx.saved_tensors
         g_raw = _f32(g_raw, "g_raw")
         sink = ctx.cache.grad_sink
-        flat = sink if sink is not None else _empty((L.NUM_PARAMS,), pts)
+        accumulate = sink is not None and ctx.cache.sink_dirty
+        flat = sink if (sink is not None and not accumulate) else _empty((L.NUM_PARAMS,), pts)
         g_pts = _empty((M, 3), pts) if ctx.needs_input_grad[0] else None
         g_dirs = _empty((M // group, 3), pts) if ctx.needs_input_grad[1] else None
         call("rn_mlp_bwd", ptr(ctx.packed), ptr(pts), ptr(dirs), M, group, ptr(ctx.ws), ptr(g_raw), ptr(flat), ptr(g_pts),
              ptr(g_dirs), stream_ptr())
         ctx.ws = None
         if sink is not None:
+            if accumulate:
+                sink.add_(flat)
+            ctx.cache.sink_dirty = True
             return (g_pts, g_dirs, None, None, None) + (None,) * L.NUM_PARAM_TENSORS
         grads = split_flat_grads(flat)
         grads = [g if ctx.needs_input_grad[n_in + i] else None for i, g in enumerate(grads)]

@@ -202,24 +202,45 @@ class Trainer:
         self.exp_avg_sq = torch.zeros(total, device=dev)
         off = 0
         self.net_offsets = [0]
+        self._sink_slices: List[torch.Tensor] = []
         for m, ps in zip(nets, self.net_params):
             start = off
             off = _flatten_into(ps, self.flat, self.gflat, off)
             self.net_offsets.append(off)
-            m._packed.grad_sink = self.gflat[start:off]      # backward kernels write gradients here directly
+            self._sink_slices.append(self.gflat[start:off])  # armed as the net's gradient sink only inside a Trainer step
         off = _flatten_into(self.pose_params, self.flat, self.gflat, off)
         self.norms = torch.zeros(2 * (8 + 8 * 64), device=dev)    # two rn_clip_adam_step scratch areas
         # [lr, 1-b1^t, sqrt(1-b2^t)] for the nets and for the poses: read by the Adam kernel from device memory so
         # a captured CUDA graph can be replayed while the schedule advances
-        self.hyper_host = torch.zeros(512, 6).pin_memory()      # ring: the host may run many steps ahead of the device
+        # Pinned ring of schedule rows: the async H2D copy of step t reads slot t % RING; the slot is rewritten at step
+        # t + RING, so each slot carries an event recorded after its copy and the host waits on it before reuse (a host
+        # that runs more than RING replays ahead of the device would otherwise corrupt an in-flight step's LR).
+        self.hyper_host = torch.zeros(self.RING, 6).pin_memory()
+        self._hyper_events: List[Optional[torch.cuda.Event]] = [None] * self.RING
         self.hyper = torch.zeros(6, device=dev)
         self._graphs = {}
         self.iteration = 0
         self.pose_steps = 0
         self.nets = nets
 
+    RING = 512
+
     # -- pieces --------------------------------------------------------------------------------
+    def _arm_sinks(self, on: bool):
+        """Point the nets' backward kernels at the flat gradient buffer for the duration of a Trainer step only:
+        outside it the models behave like ordinary modules (p.grad filled by autograd), so the reference-style
+        train_step / train_step_with_poses on the same models keep working."""
+        for m, sl in zip(self.nets, self._sink_slices):
+            m._packed.grad_sink = sl if on else None
+            m._packed.sink_dirty = False
+
+    def _neutral_hyper(self):
+        """lr = 0 with unit bias corrections: warm-up / capture passes leave the parameters untouched (all-zero rows
+        would divide 0 by 0 in the Adam kernel and push NaN weights through the whole pipeline)."""
+        self.hyper.copy_(torch.tensor([0.0, 1.0, 1.0, 0.0, 1.0, 1.0], device=self.hyper.device))
+
     def _zero_grad(self):
+        self._check_aliasing()
         if self.n_pose:
             self.gflat[self.n_net:].zero_()                  # net gradients are overwritten by the kernels
         off = 0
@@ -246,8 +267,13 @@ class Trainer:
         buffer the Adam kernel reads, outside any captured graph."""
         self.iteration += 1
         t = self.iteration
-        h = self.hyper_host[t % 512]
-        h[3:] = self.hyper_host[(t - 1) % 512][3:]
+        ev = self._hyper_events[t % self.RING]
+        if ev is not None:
+            ev.synchronize()                                  # the copy issued RING steps ago has read this slot
+        h = self.hyper_host[t % self.RING]
+        h[3:] = self.hyper_host[(t - 1) % self.RING][3:]
+        if t == 1:
+            h[3:] = torch.tensor([0.0, 1.0, 1.0])
         h[0] = self.lr * (0.1 ** ((t - 1) / self.lr_decay_steps))
         h[1] = 1.0 - self.betas[0] ** t
         h[2] = (1.0 - self.betas[1] ** t) ** 0.5
@@ -258,6 +284,9 @@ class Trainer:
             h[4] = 1.0 - self.betas[0] ** tp
             h[5] = (1.0 - self.betas[1] ** tp) ** 0.5
         self.hyper.copy_(h, non_blocking=True)
+        ev = self._hyper_events[t % self.RING] or torch.cuda.Event()
+        ev.record()
+        self._hyper_events[t % self.RING] = ev
 
     def _optimise(self, separate_clip: bool, optimize_poses: bool):
         if separate_clip and len(self.nets) == 2:
@@ -277,11 +306,85 @@ class Trainer:
         loss.backward()
         return loss.detach()
 
+    # -- checkpointing (train.py:248-271, train_pose_opt.py:563-597: optimizer.state_dict() travels with the model) ------
+    def _adam_state(self, params: Sequence[nn.Parameter], lo: int, base_lr: float, steps: int) -> dict:
+        state, off = {}, lo
+        if steps > 0:
+            for i, p in enumerate(params):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(steps)),
+                            "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+                off += n
+        group = {"lr": base_lr * (0.1 ** (steps / self.lr_decay_steps)), "betas": tuple(self.betas), "eps": self.eps,
+                 "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "decoupled_weight_decay": False, "initial_lr": base_lr,
+                 "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def state_dict(self) -> dict:
+        """Optimiser state in `torch.optim.Adam.state_dict()` format (per-parameter `step`, `exp_avg`, `exp_avg_sq`, in
+        the reference's parameter order: coarse net then fine net; rotation then translation deltas), so a reference
+        checkpoint's `optimizer_state_dict` loads here and ours loads into `torch.optim.Adam`.  The models and the camera
+        parameters are saved through their own `state_dict()` as in the reference."""
+        net_params = [p for ps in self.net_params for p in ps]
+        out = {"optimizer_nerf": self._adam_state(net_params, 0, self.lr, self.iteration), "iteration": self.iteration,
+               "pose_steps": self.pose_steps}
+        if self.n_pose:
+            out["optimizer_poses"] = self._adam_state(self.pose_params, self.n_net, self.pose_lr, self.pose_steps)
+        return out
+
+    def _load_adam_state(self, sd: dict, params: Sequence[nn.Parameter], lo: int) -> int:
+        off, steps = lo, 0
+        for i, p in enumerate(params):
+            n = p.numel()
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is None:
+                self.exp_avg[off:off + n].zero_(); self.exp_avg_sq[off:off + n].zero_()
+            else:
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {i} has shape {tuple(st['exp_avg'].shape)}, parameter has {tuple(p.shape)}")
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps = max(steps, int(float(st["step"])))
+            off += n
+        return steps
+
+    def load_state_dict(self, sd: dict) -> None:
+        """Accepts `Trainer.state_dict()` or a dict holding `torch.optim.Adam.state_dict()`s under the same keys."""
+        net_params = [p for ps in self.net_params for p in ps]
+        steps = self._load_adam_state(sd["optimizer_nerf"], net_params, 0)
+        self.iteration = int(sd.get("iteration", steps))
+        if self.n_pose and "optimizer_poses" in sd:
+            psteps = self._load_adam_state(sd["optimizer_poses"], self.pose_params, self.n_net)
+            self.pose_steps = int(sd.get("pose_steps", psteps))
+        # schedule rows are rebuilt from the step counters on the next _advance_schedule; the pose row must survive a
+        # clean-mode step, so seed the previous slot with it
+        h = self.hyper_host[self.iteration % self.RING]
+        tp = max(self.pose_steps, 1)
+        h[3] = self.pose_lr * (0.1 ** ((tp - 1) / self.lr_decay_steps))
+        h[4] = 1.0 - self.betas[0] ** tp
+        h[5] = (1.0 - self.betas[1] ** tp) ** 0.5
+        self._check_aliasing()
+
+    def _check_aliasing(self):
+        """Parameters must still be views of the flat buffer (model.to(), p.data = ... after construction detaches them)."""
+        off = 0
+        for p in [q for ps in self.net_params for q in ps] + self.pose_params:
+            if p.data_ptr() != self.flat.data_ptr() + 4 * off:
+                raise RuntimeError("a parameter no longer aliases the Trainer's flat buffer (was the model moved or "
+                                   "re-assigned after the Trainer was built?); rebuild the Trainer")
+            off += p.numel()
+
     # -- public steps -----------------------------------------------------------------------------
     def _step_rays_body(self, rays_o, rays_d, target, optimise):
         self._zero_grad()
-        out = render_rays(self.model_coarse, self.model_fine, rays_o, rays_d, self.cfg, is_train=True)
-        loss = self._backward(out, target)
+        self._arm_sinks(True)
+        try:
+            out = render_rays(self.model_coarse, self.model_fine, rays_o, rays_d, self.cfg, is_train=True)
+            loss = self._backward(out, target)
+        finally:
+            self._arm_sinks(False)
         self._allreduce()
         if optimise:
             self._optimise(separate_clip=False, optimize_poses=False)
@@ -305,7 +408,7 @@ class Trainer:
                 s_.copy_(x)
             # keep parameters / optimiser state untouched by warm-up and capture
             saved = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq)]
-            self.hyper.zero_()                       # lr = 0 during warm-up/capture passes
+            self._neutral_hyper()                    # lr = 0, unit bias corrections during warm-up/capture passes
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -330,16 +433,20 @@ class Trainer:
     def _step_pixels_body(self, pixel_batch, sampler, optimize_poses: bool, optimise: bool, advance: bool):
         cam = self.camera_params
         self._zero_grad()
-        rays_o, rays_d = sampler.get_rays_for_batch_fused(pixel_batch, cam)
-        out = render_rays(self.model_coarse, self.model_fine, rays_o, rays_d, self.cfg, is_train=True)
-        reg = None
-        if optimize_poses and (self.rot_reg > 0 or self.trans_reg > 0):
-            reg = 0.0
-            if self.rot_reg > 0 and cam.learn_rotation:
-                reg = reg + self.rot_reg * torch.mean(cam.rotation_deltas ** 2)
-            if self.trans_reg > 0 and cam.learn_translation:
-                reg = reg + self.trans_reg * torch.mean(cam.translation_deltas ** 2)
-        loss = self._backward(out, pixel_batch.target_rgb, reg)
+        self._arm_sinks(True)
+        try:
+            rays_o, rays_d = sampler.get_rays_for_batch_fused(pixel_batch, cam)
+            out = render_rays(self.model_coarse, self.model_fine, rays_o, rays_d, self.cfg, is_train=True)
+            reg = None
+            if optimize_poses and (self.rot_reg > 0 or self.trans_reg > 0):
+                reg = 0.0
+                if self.rot_reg > 0 and cam.learn_rotation:
+                    reg = reg + self.rot_reg * torch.mean(cam.rotation_deltas ** 2)
+                if self.trans_reg > 0 and cam.learn_translation:
+                    reg = reg + self.trans_reg * torch.mean(cam.translation_deltas ** 2)
+            loss = self._backward(out, pixel_batch.target_rgb, reg)
+        finally:
+            self._arm_sinks(False)
         self._allreduce()
         if optimise:
             if advance:
@@ -361,7 +468,7 @@ class Trainer:
             static = PixelBatch(image_indices=pixel_batch.image_indices.clone(), pixel_coords=pixel_batch.pixel_coords.clone(),
                                 target_rgb=pixel_batch.target_rgb.clone())
             saved = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq)]
-            self.hyper.zero_()                       # lr = 0 during warm-up/capture passes
+            self._neutral_hyper()                    # lr = 0, unit bias corrections during warm-up/capture passes
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -388,10 +495,11 @@ class Trainer:
 @torch.no_grad()
 def render_views_sharded(model_coarse: NeRF, model_fine: Optional[NeRF], poses: torch.Tensor, H: int, W: int, focal: float,
                          render_config: RenderConfig, tile_rays: int = 32768, rank: int = 0, world: int = 1,
-                         out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                         out: Optional[torch.Tensor] = None, view_offset: int = 0) -> Dict[str, torch.Tensor]:
     """Test-view rendering sharded by ray tile: global tile t = view * tiles_per_view + k goes to rank
     t % world; no collective.  Returns this rank's tiles written into a (n_views, H*W, 3) buffer
-    (zeros elsewhere) and the number of rays this rank rendered."""
+    (zeros elsewhere) and the number of rays this rank rendered.  `view_offset`: index of poses[0] in the whole job
+    (callers that render a long test set a few views at a time keep the global round-robin)."""
     n_views = poses.shape[0]
     npix = H * W
     tiles_per_view = (npix + tile_rays - 1) // tile_rays
@@ -400,7 +508,7 @@ def render_views_sharded(model_coarse: NeRF, model_fine: Optional[NeRF], poses: 
         out = torch.zeros(n_views, npix, 3, device=poses.device)
     done = 0
     for v in range(n_views):
-        mine = tiles_for_rank(v, tiles_per_view, rank, world)
+        mine = tiles_for_rank(v + view_offset, tiles_per_view, rank, world)
         if not mine:
             continue
         for k in mine:
