@@ -321,36 +321,49 @@ def _sigmoid(x):
     return (F32(1.0) / (F32(1.0) + np.exp(-x))).astype(F32)
 
 
+# Which rounding points of the CUDA path `emulate_bf16` restates.  All on = the kernels as built.  The ablation in
+# scripts/grad_rounding_ablation.py switches groups off to measure where the distance to the fp32 reference comes from:
+# "w" weights, "act" stored activations, "enc" positional-encoding features (forward operands); "dh" back-propagated
+# activation gradients, "dxe" the three 64-wide encoding-gradient outputs, "bw" weights as read by the data-gradient GEMMs.
+BF16_POINTS = {"w": True, "act": True, "enc": True, "dh": True, "dxe": True, "bw": True}
+
+
+def _rounders(emulate: bool):
+    ident = (lambda a: a)
+    return {k: (bf16_round if (emulate and on) else ident) for k, on in BF16_POINTS.items()}
+
+
 def nerf_forward(params: Dict[str, np.ndarray], x, d, cfg: Optional[ModelConfig] = None,
                  keep_cache: bool = False, emulate_bf16: bool = False):
     """noisy_src/model.py:145-196.  Returns rgb (N,3), sigma (N,1)[, cache]."""
     cfg = cfg or ModelConfig()
-    r = bf16_round if emulate_bf16 else (lambda a: a)
+    rr = _rounders(emulate_bf16)
+    rW, rA, rE = rr["w"], rr["act"], rr["enc"]
     x = _f32(x)
-    x_enc = r(positional_encoding(x, cfg.pos_freqs))
+    x_enc = rE(positional_encoding(x, cfg.pos_freqs))
     h = x_enc
     cache = {"x": x, "x_enc": x_enc, "ins": [], "pre": [], "emulate": emulate_bf16}
     for i in range(cfg.num_hidden_layers):
-        W, b = r(params[f"pts_linears.{i}.weight"]), params[f"pts_linears.{i}.bias"]
+        W, b = rW(params[f"pts_linears.{i}.weight"]), params[f"pts_linears.{i}.bias"]
         cache["ins"].append(h)
         pre = (h @ W.T + b).astype(F32)
-        h = r(np.maximum(pre, F32(0.0)))
+        h = rA(np.maximum(pre, F32(0.0)))
         cache["pre"].append(h if emulate_bf16 else pre)   # mask = stored activation > 0
         if i in cfg.skips:
             h = np.concatenate([x_enc, h], -1)
     sig_pre = (h @ params["sigma_linear.weight"].T + params["sigma_linear.bias"]).astype(F32)
     sigma = np.maximum(sig_pre, F32(0.0))
-    feats = r((h @ r(params["feature_linear.weight"]).T + params["feature_linear.bias"]).astype(F32))
+    feats = rA((h @ rW(params["feature_linear.weight"]).T + params["feature_linear.bias"]).astype(F32))
     if cfg.use_view_dirs:
         if d is None:
             raise ValueError("reference crashes for d=None with use_view_dirs (model.py:187-193)")
         d = _f32(d)
-        d_enc = r(positional_encoding(d, cfg.dir_freqs))
+        d_enc = rE(positional_encoding(d, cfg.dir_freqs))
         hc_in = np.concatenate([feats, d_enc], -1)
     else:
         d_enc, hc_in = None, feats
-    hc_pre = (hc_in @ r(params["dir_linear.weight"]).T + params["dir_linear.bias"]).astype(F32)
-    hc = r(np.maximum(hc_pre, F32(0.0)))
+    hc_pre = (hc_in @ rW(params["dir_linear.weight"]).T + params["dir_linear.bias"]).astype(F32)
+    hc = rA(np.maximum(hc_pre, F32(0.0)))
     rgb_pre = (hc @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]).astype(F32)
     rgb = _sigmoid(rgb_pre)
     if keep_cache:
@@ -363,41 +376,43 @@ def nerf_backward(params, cache, g_rgb, g_sigma, cfg: Optional[ModelConfig] = No
                   need_input_grad: bool = False):
     """Manual backward of nerf_forward.  Returns (param grads dict, dx, dd)."""
     cfg = cfg or ModelConfig()
-    r = bf16_round if cache.get("emulate") else (lambda a: a)
+    rr = _rounders(bool(cache.get("emulate")))
+    rh, rx, rw = rr["dh"], rr["dxe"], rr["bw"]
     g = {}
     rgb = cache["rgb"]
     g_rgb_pre = (_f32(g_rgb) * rgb * (F32(1.0) - rgb)).astype(F32)
     g["rgb_linear.weight"] = (g_rgb_pre.T @ cache["hc"]).astype(F32)
     g["rgb_linear.bias"] = g_rgb_pre.sum(0).astype(F32)
     g_hc = (g_rgb_pre @ params["rgb_linear.weight"]).astype(F32)
-    g_hc_pre = r((g_hc * (cache["hc_pre"] > 0)).astype(F32))
+    g_hc_pre = rh((g_hc * (cache["hc_pre"] > 0)).astype(F32))
     g["dir_linear.weight"] = (g_hc_pre.T @ cache["hc_in"]).astype(F32)
     g["dir_linear.bias"] = g_hc_pre.sum(0).astype(F32)
-    g_hc_in = r((g_hc_pre @ r(params["dir_linear.weight"])).astype(F32))
     H = cfg.hidden_dim
+    g_hc_in = (g_hc_pre @ rw(params["dir_linear.weight"])).astype(F32)
+    g_hc_in = np.concatenate([rh(g_hc_in[:, :H]), rx(g_hc_in[:, H:])], -1)
     g_feats = g_hc_in[:, :H]
     g_d_enc = g_hc_in[:, H:] if cfg.use_view_dirs else None
     h_last = cache["h_last"]
     g["feature_linear.weight"] = (g_feats.T @ h_last).astype(F32)
     g["feature_linear.bias"] = g_feats.sum(0).astype(F32)
-    g_sig_pre = r((_f32(g_sigma).reshape(-1, 1) * (cache["sig_pre"] > 0)).astype(F32))
+    g_sig_pre = rh((_f32(g_sigma).reshape(-1, 1) * (cache["sig_pre"] > 0)).astype(F32))
     g["sigma_linear.weight"] = (g_sig_pre.T @ h_last).astype(F32)
     g["sigma_linear.bias"] = g_sig_pre.sum(0).astype(F32)
-    g_h = (g_feats @ r(params["feature_linear.weight"]) + g_sig_pre @ r(params["sigma_linear.weight"])).astype(F32)
+    g_h = (g_feats @ rw(params["feature_linear.weight"]) + g_sig_pre @ rw(params["sigma_linear.weight"])).astype(F32)
     pos_dim = cache["x_enc"].shape[-1]
     g_x_enc = np.zeros_like(cache["x_enc"])
     for i in reversed(range(cfg.num_hidden_layers)):
         if i in cfg.skips:
-            g_x_enc += r(g_h[:, :pos_dim])
+            g_x_enc += rx(g_h[:, :pos_dim])
             g_h = g_h[:, pos_dim:]
-        g_pre = r((g_h * (cache["pre"][i] > 0)).astype(F32))
+        g_pre = rh((g_h * (cache["pre"][i] > 0)).astype(F32))
         g[f"pts_linears.{i}.weight"] = (g_pre.T @ cache["ins"][i]).astype(F32)
         g[f"pts_linears.{i}.bias"] = g_pre.sum(0).astype(F32)
         if i > 0 or need_input_grad:
-            g_h = (g_pre @ r(params[f"pts_linears.{i}.weight"])).astype(F32)
+            g_h = (g_pre @ rw(params[f"pts_linears.{i}.weight"])).astype(F32)
     dx = dd = None
     if need_input_grad:
-        g_x_enc += r(g_h)
+        g_x_enc += rx(g_h)
         dx = positional_encoding_backward(cache["x"], cfg.pos_freqs, g_x_enc)
         if cfg.use_view_dirs:
             dd = positional_encoding_backward(cache["d"], cfg.dir_freqs, g_d_enc)

@@ -27,6 +27,7 @@
 #include "gemm.h"
 #include "mlp_layout.h"
 #include <cuda_bf16.h>
+#include <mutex>
 
 namespace rn {
 
@@ -99,17 +100,26 @@ struct PairParams {
   PairLayer L[kPairMaxLayers];
   int n_layers, n_ptiles;      // pair tiles of 256 rows
   int64_t m_rows;
-  const float* consts;
+  int const_slot;              // which slot of c_pair_consts2 holds this network's fp32 section
   float* raw;
 };
 
-// Biases and fp32 head weights of the network being evaluated come straight from the fp32 section of the packed-weight
-// buffer (`PairParams::consts`, layout::kF32Elems floats): there is NO process-global per-launch state, so forwards of
-// different networks may overlap on different streams or threads (the earlier __constant__ staging copy
-// raced).  Every lane of an epilogue warp needs the SAME values: the per-layer bias is staged once per layer into shared
-// memory (a uniform LDG.128 per 4 columns made the load/store unit -- shared with the tensor core's operand reads -- the
-// bottleneck of the epilogue, profiles/r01_pair_experiments.md); the head weights (two of ten layers) are warp-uniform
-// read-only loads that hit L1.
+// Biases and fp32 head weights of the network being evaluated (layout::kF32Elems floats), copied device-to-device on the
+// launching stream before each launch.  Every lane of an epilogue warp needs the SAME values: read through the
+// constant cache they cost no LSU/L1 cycles (a uniform LDG.128 per 4 columns made the load/store unit -- shared with the
+// tensor core's operand reads -- the bottleneck of the epilogue, profiles/r01_pair_experiments.md; reading the head
+// weights with warp-uniform __ldg instead cost +10 % of the training forward, profiles/r02_ab_consts.md).
+//
+// The staging area is NOT one global: it is kConstSlots slots keyed by the packed-weight buffer (acquire_const_slot
+// below), so forwards of different networks -- coarse and fine overlapped on two streams, an evaluation render beside a
+// training step, several host threads -- never share a slot, and two launches of the SAME network write identical
+// bytes.  A fifth distinct network evicts the least recently used slot after a device synchronisation.
+constexpr int kConstSlots = 4;
+constexpr int kConstSlotFloat2 = 1664 + 128;      // + slack: the bias staging copies 256 floats from any bias offset
+__constant__ float2 c_pair_consts2[kConstSlots][kConstSlotFloat2];
+static_assert(layout::kF32Elems <= 2 * 1664, "constant staging slot too small");
+static_assert(sizeof(float2) * kConstSlots * kConstSlotFloat2 <= 60 * 1024, "constant bank exceeded");
+
 __device__ __forceinline__ uint64_t fadd2(uint32_t a_lo, uint32_t a_hi, float2 b) {
   uint64_t a, bb, r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a_lo), "r"(a_hi));
@@ -133,7 +143,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 // c = chunk index inside the layer output (columns 8c .. 8c+7).
 template <int HEADS, bool RELU, bool WMASK>
 __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int c, uint8_t* s_tile, int row, const float* s_bias,
-                                                    const float2* __restrict__ consts2, int head_w2_off, int n, uint32_t& outbits,
+                                                    const float2* consts2, int head_w2_off, int n, uint32_t& outbits,
                                                     float2& hh0, float2& hh1, float2& hh2) {
   const int G = c >> 2, cc = c & 3;               // 32-column group and chunk inside it
   const float4 bA = *reinterpret_cast<const float4*>(s_bias + c * 8);          // broadcast LDS.128 from the per-layer staging
@@ -160,10 +170,10 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
       // the two halves of a packed fp32 pair
       const int w2 = head_w2_off + c * 4 + e;
       const float2 a = make_float2(__uint_as_float(packed[e] << 16), __uint_as_float(packed[e] & 0xFFFF0000u));
-      hh0 = ffma2(a, __ldg(consts2 + w2), hh0);
+      hh0 = ffma2(a, consts2[w2], hh0);
       if (HEADS == 3) {
-        hh1 = ffma2(a, __ldg(consts2 + w2 + (n >> 1)), hh1);
-        hh2 = ffma2(a, __ldg(consts2 + w2 + n), hh2);
+        hh1 = ffma2(a, consts2[w2 + (n >> 1)], hh1);
+        hh2 = ffma2(a, consts2[w2 + n], hh2);
       }
     }
   }
@@ -182,7 +192,7 @@ __device__ __forceinline__ void pair_epilogue_chunk(const uint32_t (&v)[8], int 
 // share one instruction stream.
 template <int NG, int HEADS, bool RELU, bool WMASK>
 __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, int row, int g0, const float* s_bias,
-                                              const float2* __restrict__ consts2, int head_w2_off, int n, uint32_t (&mb)[2],
+                                              const float2* consts2, int head_w2_off, int n, uint32_t (&mb)[2],
                                               float& h0, float& h1, float& h2) {
   constexpr int NC = NG * 4;                      // 8-column chunks handled by this warp
   const int c0 = g0 * 4;
@@ -370,14 +380,16 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     const uint32_t act_ready_leader = mapa_u32(smem_u32(act_ready), 0);
     uint32_t it0 = 0, it1 = 0;
     RN_TL_DECL(tl, (warp == 2 ? 1 : 2), lane == 0 && (warp == 2 || warp == 17));
+    const float2* consts2 = c_pair_consts2[p.const_slot];
+    const float* consts1 = reinterpret_cast<const float*>(consts2);
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
       for (int l = 0; l < p.n_layers; ++l) {
         const PairLayer L = p.L[l];
         // stage this layer's bias: every epilogue warp has finished the previous layer (first barrier), 256 threads copy
-        // one value each out of the constant table, and the copies are visible to all (second barrier)
+        // one value each out of the constant slot, and the copies are visible to all (second barrier)
         named_bar_sync(5, 512);
-        if (threadIdx.x - 64 < 256) s_bias[threadIdx.x - 64] = __ldg(p.consts + L.bias_off + (threadIdx.x - 64));
+        if (threadIdx.x - 64 < 256) s_bias[threadIdx.x - 64] = consts1[L.bias_off + (threadIdx.x - 64)];
         named_bar_sync(5, 512);
         for (int slot = 0; slot < tiles_here; ++slot) {
           const uint32_t i = slot ? it1++ : it0++;
@@ -400,11 +412,11 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
           }
           else {
             if (L.n == 256) {
-              if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, reinterpret_cast<const float2*>(p.consts), L.head_w_off >> 1, 256, mb, h0, h1, h2);
-              else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, reinterpret_cast<const float2*>(p.consts), L.head_w_off >> 1, 256, mb, h0, h1, h2);
-              else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, s_bias, reinterpret_cast<const float2*>(p.consts), L.head_w_off >> 1, 256, mb, h0, h1, h2);
+              if (L.heads == 1) pair_epilogue<2, 1, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, consts2, L.head_w_off >> 1, 256, mb, h0, h1, h2);
+              else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, consts2, L.head_w_off >> 1, 256, mb, h0, h1, h2);
+              else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, s_bias, consts2, L.head_w_off >> 1, 256, mb, h0, h1, h2);
             } else {
-              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, s_bias, reinterpret_cast<const float2*>(p.consts), L.head_w_off >> 1, 128, mb, h0, h1, h2);
+              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, s_bias, consts2, L.head_w_off >> 1, 128, mb, h0, h1, h2);
             }
           }
           RN_TL(tl, 600 + l * 10 + slot);                  // math done
@@ -435,7 +447,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
               named_bar_sync(1 + q, 128);
             }
             if (cq == 0 && row_ok) {
-              const float* hb = p.consts + L.head_b_off;
+              const float* hb = consts1 + L.head_b_off;
               float* o = p.raw + gr * 4 + L.head_col;
               o[0] = h0 + s_hx[row] + hb[0];
               if (nh == 3) { o[1] = h1 + s_hx[128 + row] + hb[1]; o[2] = h2 + s_hx[256 + row] + hb[2]; }
@@ -816,6 +828,44 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   return RN_OK;
 }
 
+// Constant-slot table, per device: slot <-> packed-weight buffer (key = address of its fp32 section).
+struct ConstSlots {
+  const void* key[kConstSlots] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long last_use[kConstSlots] = {0, 0, 0, 0};
+  unsigned long long tick = 0;
+};
+static ConstSlots g_const_slots[kMaxDevices];
+static std::mutex g_const_mu;
+
+// Returns the slot of `consts`, uploading its current contents on `st` (stream-ordered before the launch that follows).
+static int acquire_const_slot(const float* consts, cudaStream_t st, int* slot_out) {
+  int dev = 0;
+  RN_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_const_mu);
+  ConstSlots& t = g_const_slots[dev & (kMaxDevices - 1)];
+  int slot = -1, lru = 0;
+  for (int i = 0; i < kConstSlots; ++i) {
+    if (t.key[i] == consts) slot = i;
+    if (t.last_use[i] < t.last_use[lru]) lru = i;
+  }
+  if (slot < 0) {
+    slot = lru;
+    if (t.key[slot] != nullptr) {
+      // eviction: a kernel of the previous owner may still be reading the slot on another stream
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      RN_CUDA_CHECK(cudaStreamIsCapturing(st, &cs));
+      if (cs != cudaStreamCaptureStatusNone) return RN_ERR_INVALID_ARG;   // > kConstSlots distinct networks inside one capture
+      RN_CUDA_CHECK(cudaDeviceSynchronize());
+    }
+    t.key[slot] = consts;
+  }
+  t.last_use[slot] = ++t.tick;
+  RN_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pair_consts2, consts, layout::kF32Elems * sizeof(float),
+                                        (size_t)slot * kConstSlotFloat2 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+  *slot_out = slot;
+  return RN_OK;
+}
+
 // Host launcher.  layers[l] uses the ChainLayerHost description of the per-layer chain (gemm.h); the pair kernel derives
 // where each K chunk of A lives: activation chunks for the part produced by the previous layer, the side buffer for
 // x_enc (first chunk of layers 0 and 5) and d_enc (last chunk of the view layer).
@@ -860,7 +910,8 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
 #endif
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
-  p.m_rows = M; p.consts = consts; p.raw = raw;
+  p.m_rows = M; p.raw = raw;
+  if ((rc = acquire_const_slot(consts, st, &p.const_slot)) != RN_OK) return rc;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) {
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
