@@ -18,6 +18,9 @@
 namespace rn {
 
 constexpr int kCompWarps = 8;
+#ifndef RN_COMP_BWD12_BLOCKS
+#define RN_COMP_BWD12_BLOCKS 2      // resident CTAs asked of the 7..12-round training backward (A/B knob, scripts/ab_hbm.sh)
+#endif
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
@@ -248,6 +251,102 @@ composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
   }
 }
 
+// The training configuration of the backward (gradient from rgb_map only: no noise, no depth / weight gradients in, no
+// ray-direction gradient out) as its own kernel, built to keep more rays in flight per SM (the general kernel holds ten
+// per-round register arrays; at S = 384 that is 151 registers and ONE resident CTA):
+//   * per round only alpha, the three colours and the masked interval length stay in registers (5 arrays); dL/dw is
+//     re-evaluated from the colours, the incoming transmittance is re-scanned from alpha in the reverse sweep with the
+//     round's carry parked in lane r of one register -- same operations in the same order, so the values are those of
+//     the forward sweep bit for bit;
+//   * FULL = the ray fills MAXR rounds exactly (64, 128, 192, 384 samples: every benchmark configuration): no `valid`
+//     predicates and no run-time trip counts, so the unrolled rounds are straight-line code and the scans / exponentials
+//     of different rounds interleave (the dependent SHFL chains of one round at a time left the schedulers idle).
+template <bool RAW, int MAXR, bool FULL>
+__global__ void __launch_bounds__(kCompWarps * 32, MAXR <= 4 ? 4 : (MAXR <= 6 ? 3 : (MAXR <= 12 ? RN_COMP_BWD12_BLOCKS : 1)))
+composite_bwd_lean_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma, const float4* __restrict__ raw4,
+                          const float* __restrict__ z, const float* __restrict__ rd, int64_t B, int S, int white,
+                          const float* __restrict__ g_map, float* __restrict__ d_rgb, float* __restrict__ d_sigma,
+                          float4* __restrict__ d_raw4) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = blockIdx.x * (int64_t)kCompWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  const int rounds = FULL ? MAXR : ((S + 31) >> 5);
+  for (int64_t b = warp; b < B; b += nwarps) {
+    const float nrm = ray_norm(rd, b);
+    const int64_t base = b * S;
+    const float gm0 = g_map[b * 3], gm1 = g_map[b * 3 + 1], gm2 = g_map[b * 3 + 2];
+    const float gconst = -(white ? (gm0 + gm1 + gm2) : 0.f);
+    float al[MAXR], c0[MAXR], c1[MAXR], c2[MAXR], ds[MAXR];
+    // ---- phase 0: issue every global load of the ray before any dependent math (sigma parks in al) ----
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      c0[r] = c1[r] = c2[r] = 0.f; al[r] = 0.f; ds[r] = 0.f;
+      const int s = r * 32 + lane;
+      if (FULL || (r < rounds && s < S)) {
+        const Fetched f = fetch_sample<RAW>(rgb, sigma, raw4, z, nullptr, base, s, S);
+        c0[r] = f.a; c1[r] = f.b; c2[r] = f.c; al[r] = f.sig;
+        ds[r] = (s == S - 1) ? 1e10f : __fsub_rn(f.zn, f.z);        // interval length dz (rendering.py:67-72)
+      }
+    }
+    float carry = 1.0f, parked = 1.0f;
+    // ---- forward sweep: alpha per sample, carried transmittance per round ----
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      if (FULL || r < rounds) {
+        const int s = r * 32 + lane;
+        const bool valid = FULL || s < S;
+        float t = 1.f;
+        if (valid) {
+          if (RAW) { c0[r] = sigmoidf_acc(c0[r]); c1[r] = sigmoidf_acc(c1[r]); c2[r] = sigmoidf_acc(c2[r]); }
+          const float sg = al[r];
+          const float dist = __fmul_rn(ds[r], nrm);                                                // rendering.py:75
+          al[r] = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(sg, 0.f), dist)));
+          t = __fadd_rn(__fsub_rn(1.0f, al[r]), 1e-10f);
+          ds[r] = (sg > 0.f) ? dist : 0.f;                // d relu(sigma) folded in: sigma itself is not needed again
+        }
+        if (lane == r) parked = carry;                    // transmittance entering round r
+        const float incl = warp_scan_mul(t, lane);
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    // ---- reverse sweep: R_s = sum_{k>s} G_k w_k ; dL/dalpha = G T - R / t ----
+    float suffix = 0.f;
+#pragma unroll
+    for (int r = MAXR - 1; r >= 0; --r) {
+      if (FULL || r < rounds) {
+        const int s = r * 32 + lane;
+        const bool valid = FULL || s < S;
+        const float t = valid ? __fadd_rn(__fsub_rn(1.0f, al[r]), 1e-10f) : 1.f;
+        const float incl_t = warp_scan_mul(t, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl_t, 1);
+        if (lane == 0) excl = 1.0f;
+        const float Tn = __shfl_sync(0xffffffffu, parked, r) * excl;
+        const float G = gm0 * c0[r] + gm1 * c1[r] + gm2 * c2[r] + gconst;
+        const float w = al[r] * Tn;
+        const float gw = valid ? G * w : 0.f;
+        const float incl = warp_suffix_sum(gw, lane);
+        const float R = suffix + (incl - gw);
+        suffix += __shfl_sync(0xffffffffu, incl, 0);
+        if (valid) {
+          const float d_alpha = G * Tn - R / t;
+          const float one_m = 1.0f - al[r];
+          const float dsig = d_alpha * ds[r] * one_m;
+          const float g0 = w * gm0, g1 = w * gm1, g2 = w * gm2;
+          if (RAW) {
+            float4 o;
+            o.x = g0 * c0[r] * (1.0f - c0[r]); o.y = g1 * c1[r] * (1.0f - c1[r]); o.z = g2 * c2[r] * (1.0f - c2[r]);
+            o.w = dsig;
+            __stcs(d_raw4 + base + s, o);
+          } else {
+            __stcs(d_rgb + (base + s) * 3, g0); __stcs(d_rgb + (base + s) * 3 + 1, g1); __stcs(d_rgb + (base + s) * 3 + 2, g2);
+            __stcs(d_sigma + base + s, dsig);
+          }
+        }
+      }
+    }
+  }
+}
+
 // train.py:89-99: loss += mean((rgb_map-target)^2); g = 2*(rgb_map-target)/(3B)*scale. One CTA,
 // fixed reduction order (deterministic); B*3 elements is tiny (12,288 at B=4096).
 __global__ void __launch_bounds__(1024)
@@ -286,9 +385,17 @@ static int launch_bwd(int rounds, dim3 grid, cudaStream_t st, const float* rgb, 
     kern<<<(unsigned)g, kCompWarps * 32, 0, st>>>(rgb, sigma, raw4, z, rd, noise, B, S, white, g_map, g_depth, g_acc, g_w, d_rgb,
                                                   d_sigma, d_raw4, d_rd);
   };
+  auto launch_lean = [&](auto kern) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCompWarps * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int64_t g = (int64_t)num_sms() * per_sm;
+    if (g > grid.x || grid.x <= 2 * g) g = grid.x;
+    kern<<<(unsigned)g, kCompWarps * 32, 0, st>>>(rgb, sigma, raw4, z, rd, B, S, white, g_map, d_rgb, d_sigma, d_raw4);
+  };
 #define RN_BWD_CASE(R)                                                     \
   do {                                                                     \
-    if (lean) launch(composite_bwd_kernel<RAW, R, true>);                  \
+    if (lean && S == (R) * 32) launch_lean(composite_bwd_lean_kernel<RAW, R, true>);   \
+    else if (lean) launch_lean(composite_bwd_lean_kernel<RAW, R, false>);  \
     else launch(composite_bwd_kernel<RAW, R, false>);                      \
   } while (0)
   if (rounds <= 2) RN_BWD_CASE(2);

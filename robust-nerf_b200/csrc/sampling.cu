@@ -177,6 +177,9 @@ __device__ __forceinline__ void warp_bitonic_sort(float* s, int P, int lane) {
 }
 
 constexpr int kWarpsPerCta = 8;
+// floats of shared memory per warp of sample_hierarchical_kernel: z, bins, w, cdf [Nc each]; u, samples [NS each];
+// merged depths [Nc + Nf]; bucket starts [NS + 1] ints; two uint16 index arrays [NS each] (= NS floats); + padding
+__host__ __device__ constexpr int hier_smem_floats(int Nc, int NS, int Nf) { return 4 * Nc + 2 * NS + (Nc + Nf) + (NS + 1) + NS + 3; }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, int64_t B, int nb,
@@ -237,9 +240,21 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[E], int lane) 
   }
 }
 
-// sample_hierarchical, fast path (Nf <= 32*E <= 256): samples are inverted and sorted in registers
-// (shuffle bitonic network), then merged with the already sorted coarse depths by rank: a coarse
-// depth lands at i + #{samples < z_i}, a sample at j + #{coarse <= s_j} (binary searches in smem).
+// sample_hierarchical, fast path (Nf <= 32*E <= 256).  Work per ray is kept near the byte count instead of the
+// 2 x 256 binary searches + 36-stage bitonic network of the first version (0.18 of the HBM roofline at 128 + 256 samples,
+// 69 % issue-bound: profiles/r01_ncu_full_hbm_kernels.raw.csv):
+//   1. the draws u are put in ascending order FIRST: deterministic draws (linspace) already are -- one vote; random draws
+//      are uniform by construction (torch.rand), so a counting sort into Nf buckets by floor(u * Nf) leaves ~1 draw per
+//      bucket and the within-bucket rank is a handful of compares (any other distribution stays correct, only slower);
+//   2. with ascending u the searchsorted index is non-decreasing: each lane inverts E CONSECUTIVE draws, the first by
+//      binary search, the rest by stepping from the previous index (same predicate #{cdf <= u}, so the indices are the
+//      ones torch.searchsorted(right=True) returns);
+//   3. a sample of bin `ind` lies between the mid-points around z[ind], so its rank among the coarse depths is ind or
+//      ind + 1: one or two compares instead of a binary search (a short local walk keeps it exact in every rounding case);
+//   4. the samples come out ascending except for 1-ulp inversions at bin borders (fl(b + t (a - b)) may exceed a):
+//      checked with a vote, and only then sorted (register bitonic network, the previous version's hot loop);
+//   5. the coarse depths find their slots by binary search over the ascending samples (Nc / 32 searches per lane).
+// Values are those of sort(cat(z, samples)) bit for bit; `inds_out` (tests) is scattered back through the sort permutation.
 template <int E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict__ rd,
@@ -249,51 +264,150 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nb = Nc - 1, Nt = Nc + Nf;
-  constexpr int NS = 32 * E;
-  float* s_z = smem + (size_t)w * (5 * Nc + NS + Nf);
+  constexpr int NS = 32 * E;                 // padded draw count = bucket count
+  float* s_z = smem + (size_t)w * hier_smem_floats(Nc, NS, Nf);
   float* s_bins = s_z + Nc;
   float* s_w = s_bins + Nc;
   float* s_cdf = s_w + Nc;
-  float* s_smp = s_cdf + Nc;                 // [NS] sorted samples
+  float* s_u = s_cdf + Nc;                   // [NS] draws, ascending
+  float* s_smp = s_u + NS;                   // [NS] samples, ascending (scratch of the counting sort before that)
   float* s_out = s_smp + NS;                 // [Nc + Nf] merged depths
+  int* s_cnt = reinterpret_cast<int*>(s_out + Nt);                       // [NS + 1] bucket counts -> starts
+  unsigned short* s_id = reinterpret_cast<unsigned short*>(s_cnt + NS + 1);    // [NS] original index of the sorted draw
+  unsigned short* s_id2 = s_id + NS;                                     // [NS] scratch
   for (int64_t b = blockIdx.x * (int64_t)kWarpsPerCta + w; b < B; b += (int64_t)gridDim.x * kWarpsPerCta) {
     for (int k = lane; k < Nc; k += 32) s_z[k] = __ldcs(zc + b * Nc + k);
     for (int k = lane; k < Nc - 2; k += 32) s_w[k] = __ldcs(weights + b * Nc + k + 1);   // interior weights, rays.py:321
-    __syncwarp();
-    for (int k = lane; k < nb; k += 32) s_bins[k] = __fmul_rn(0.5f, __fadd_rn(s_z[k + 1], s_z[k]));   // rays.py:316
-    __syncwarp();
-    warp_build_cdf(s_w, s_cdf, nb, lane);
-    float v[E];
+    float ur[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const int j = e * 32 + lane;            // coalesced over u / inds
-      v[e] = CUDART_INF_F;
-      if (j < Nf) {
-        int ind;
-        v[e] = invert_cdf(s_cdf, s_bins, nb, __ldg(u + b * u_stride + j), ind);
-        if (inds_out) inds_out[b * Nf + j] = ind;
+      const int j = e * 32 + lane;            // coalesced over u
+      ur[e] = (j < Nf) ? __ldg(u + b * u_stride + j) : CUDART_INF_F;
+      s_u[j] = ur[e];
+      s_id[j] = (unsigned short)j;
+    }
+    __syncwarp();
+    for (int k = lane; k < nb; k += 32) s_bins[k] = __fmul_rn(0.5f, __fadd_rn(s_z[k + 1], s_z[k]));   // rays.py:316
+    // ---- 1. ascending draws ----
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int j = e * 32 + lane;
+      if (j + 1 < Nf) ok = ok && (ur[e] <= s_u[j + 1]);
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+      for (int k = lane; k <= NS; k += 32) s_cnt[k] = 0;
+      __syncwarp();
+      int bk[E], arr[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int j = e * 32 + lane;
+        const float x = ur[e];
+        int k = (x >= 1.0f) ? NS - 1 : ((x > 0.0f) ? (int)(x * (float)NS) : 0);
+        bk[e] = k < NS - 1 ? k : NS - 1;
+        arr[e] = (j < Nf) ? atomicAdd(&s_cnt[bk[e]], 1) : 0;
+      }
+      __syncwarp();
+      // exclusive scan of the NS bucket counts: lane l owns buckets [l*E, (l+1)*E)
+      int cnt[E], tot = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) { cnt[e] = s_cnt[lane * E + e]; tot += cnt[e]; }
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+      int run = incl - tot;
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < E; ++e) { s_cnt[lane * E + e] = run; run += cnt[e]; }
+      if (lane == 31) s_cnt[NS] = run;
+      __syncwarp();
+      // scatter into bucket order (arrival order inside a bucket), then rank inside the bucket by (value, slot)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int j = e * 32 + lane;
+        if (j < Nf) { const int pos = s_cnt[bk[e]] + arr[e]; s_smp[pos] = ur[e]; s_id2[pos] = (unsigned short)j; }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int j = e * 32 + lane;
+        if (j < Nf) {
+          const int b0 = s_cnt[bk[e]], b1 = s_cnt[bk[e] + 1], pos = b0 + arr[e];
+          const float x = ur[e];
+          int rank = 0;
+          for (int q = b0; q < b1; ++q) { const float y = s_smp[q]; rank += (y < x || (y == x && q < pos)) ? 1 : 0; }
+          s_u[b0 + rank] = x;
+          s_id[b0 + rank] = (unsigned short)j;
+        }
       }
     }
-    warp_bitonic_sort_regs<E>(v, lane);
+    __syncwarp();
+    warp_build_cdf(s_w, s_cdf, nb, lane);
+    // ---- 2. inversion of E consecutive ascending draws per lane ----
+    float v[E];
+    int cind[E];                              // searchsorted index of each draw: the starting guess of its rank among z
+    int ind = 0;
+    bool have = false;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int j = lane * E + e;
+      v[e] = CUDART_INF_F;
+      cind[e] = 0;
+      if (j < Nf) {
+        const float x = s_u[j];
+        if (!have) {
+          int lo = 0, hi = nb;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cdf[mid] <= x) lo = mid + 1; else hi = mid; }
+          ind = lo;
+          have = true;
+        } else if (ind < nb && s_cdf[ind] <= x) {
+          ++ind;
+          if (ind < nb && s_cdf[ind] <= x) {           // more than one bin ahead: finish with a binary search
+            int lo = ind + 1, hi = nb;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cdf[mid] <= x) lo = mid + 1; else hi = mid; }
+            ind = lo;
+          }
+        }
+        const int below = max(ind - 1, 0), above = min(ind, nb - 1);
+        const float cb = s_cdf[below], ca = s_cdf[above], bb = s_bins[below], ba = s_bins[above];
+        float denom = __fsub_rn(ca, cb);
+        if (denom < 1e-5f) denom = 1.0f;
+        const float t = __fdiv_rn(__fsub_rn(x, cb), denom);
+        v[e] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                 // rays.py:259-277
+        cind[e] = ind;
+        if (inds_out) inds_out[b * Nf + s_id[j]] = ind;
+      }
+    }
+    // ---- 4. ascending?  (1-ulp inversions at bin borders are possible; sort only then) ----
+    {
+      bool asc = true;
+#pragma unroll
+      for (int e = 0; e + 1 < E; ++e) asc = asc && (v[e] <= v[e + 1]);
+      const float nxt = __shfl_down_sync(0xffffffffu, v[0], 1);
+      if (lane < 31) asc = asc && (v[E - 1] <= nxt);
+      if (!__all_sync(0xffffffffu, asc)) warp_bitonic_sort_regs<E>(v, lane);
+    }
 #pragma unroll
     for (int e = 0; e < E; ++e) s_smp[lane * E + e] = v[e];
     __syncwarp();
-    // rank merge (rays.py:328: sort of the concatenation, values only)
-    for (int i = lane; i < Nc; i += 32) {
-      const float zi = s_z[i];
-      int lo = 0, hi = Nf;                    // #{samples < zi}
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_smp[mid] < zi) lo = mid + 1; else hi = mid; }
-      s_out[i + lo] = zi;
-    }
+    // ---- 3. rank merge (rays.py:328: sort of the concatenation, values only) ----
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int j = lane * E + e;
       if (j < Nf) {
         const float sj = v[e];
-        int lo = 0, hi = Nc;                  // #{coarse <= sj}
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_z[mid] <= sj) lo = mid + 1; else hi = mid; }
-        s_out[j + lo] = sj;
+        // #{coarse <= sj}: the sample's bin puts it next to z[ind]; walk from there (0-2 steps)
+        int c = min(cind[e], Nc);
+        while (c < Nc && s_z[c] <= sj) ++c;
+        while (c > 0 && s_z[c - 1] > sj) --c;
+        s_out[j + c] = sj;
       }
+    }
+    for (int i = lane; i < Nc; i += 32) {
+      const float zi = s_z[i];
+      int lo = 0, hi = Nf;                    // #{samples < zi}
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_smp[mid] < zi) lo = mid + 1; else hi = mid; }
+      s_out[i + lo] = zi;
     }
     __syncwarp();
     for (int k = lane; k < Nt; k += 32) z_all[b * Nt + k] = s_out[k];
@@ -301,9 +415,9 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
       const float o0 = ro[b * 3], o1 = ro[b * 3 + 1], o2 = ro[b * 3 + 2];
       const float d0 = rd[b * 3], d1 = rd[b * 3 + 1], d2 = rd[b * 3 + 2];
       for (int e = lane; e < 3 * Nt; e += 32) {     // 3*Nt contiguous floats per ray: coalesced stores
-        const int s = e / 3, k = e - 3 * s;
+        const int sidx = e / 3, k = e - 3 * sidx;
         const float o = k == 0 ? o0 : (k == 1 ? o1 : o2), d = k == 0 ? d0 : (k == 1 ? d1 : d2);
-        pts[(b * Nt) * 3 + e] = __fadd_rn(o, __fmul_rn(d, s_out[s]));
+        pts[(b * Nt) * 3 + e] = __fadd_rn(o, __fmul_rn(d, s_out[sidx]));
       }
     }
     __syncwarp();
@@ -355,7 +469,7 @@ sample_hierarchical_generic_kernel(const float* __restrict__ ro, const float* __
 template <int E>
 static int launch_hier(const float* ro, const float* rd, const float* zc, const float* weights, int64_t B, int Nc,
                        const float* u, int64_t u_stride, int Nf, float* z_all, float* pts, int64_t* inds_out, cudaStream_t st) {
-  const size_t smem = (size_t)kWarpsPerCta * (5 * Nc + 32 * E + Nf) * sizeof(float);
+  const size_t smem = (size_t)kWarpsPerCta * hier_smem_floats(Nc, 32 * E, Nf) * sizeof(float);
   if (smem > 200 * 1024) return RN_ERR_INVALID_ARG;
   if (smem > 48 * 1024)
     RN_CUDA_CHECK(cudaFuncSetAttribute(sample_hierarchical_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -303,6 +303,36 @@ def test_sample_hierarchical(rn, dev, Nc, Nf, B):
         assert (np.abs(N(zf) - g["hier_z_rand"]) > 2e-5 + 1e-5 * np.abs(g["hier_z_rand"])).mean() < 2e-3
 
 
+@pytest.mark.parametrize("kind", ["descending", "all_equal", "clustered", "ties_and_edges", "sorted_random"])
+def test_sample_hierarchical_any_draw_distribution(rn, dev, kind):
+    """The resampling kernel orders the draws with a counting sort tuned for uniform u; every other distribution of
+    caller-supplied draws (`u=`) must give the same bits as the oracle, indices included."""
+    from robust_nerf_b200 import ops
+    rng = np.random.default_rng(17)
+    B, Nc, Nf = 37, 64, 128
+    ro = rng.standard_normal((B, 3)).astype(np.float32)
+    rd = rng.standard_normal((B, 3)).astype(np.float32)
+    z = np.sort(rng.uniform(2, 6, (B, Nc)).astype(np.float32), -1)
+    z[3, 10:14] = z[3, 10]                                    # duplicate coarse depths
+    w = (rng.uniform(0, 1, (B, Nc)) ** 6).astype(np.float32)
+    w[1] = 0; w[2] = 0; w[2, 30] = 7.0                        # uniform pdf; single spike (flat cdf, denom < 1e-5 branch)
+    if kind == "descending":
+        u = np.sort(rng.uniform(0, 1, (B, Nf)).astype(np.float32), -1)[:, ::-1].copy()
+    elif kind == "all_equal":
+        u = np.full((B, Nf), 0.3125, np.float32)
+    elif kind == "clustered":
+        u = (0.5 + 1e-4 * rng.standard_normal((B, Nf))).astype(np.float32)
+    elif kind == "ties_and_edges":
+        u = rng.choice(np.array([0.0, 1.0, 0.25, 0.5, 0.99999994, 1e-8], np.float32), (B, Nf))
+    else:
+        u = np.sort(rng.uniform(0, 1, (B, Nf)).astype(np.float32), -1)
+    pts_ref, z_ref, i_ref = O.sample_hierarchical(ro, rd, z, w, Nf, det=False, u=u, return_inds=True)
+    z_all, pts, inds = ops.sample_hierarchical(T(ro, dev), T(rd, dev), T(z, dev), T(w, dev), T(u, dev), return_inds=True)
+    assert np.array_equal(inds.cpu().numpy(), i_ref)
+    assert np.array_equal(z_all.cpu().numpy(), z_ref)
+    close(N(pts), pts_ref, atol=2e-6)
+
+
 # ------------------------------------------------------------------------------------------------
 # compositing
 # ------------------------------------------------------------------------------------------------
