@@ -275,6 +275,8 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
   int* s_cnt = reinterpret_cast<int*>(s_out + Nt);                       // [NS + 1] bucket counts -> starts
   unsigned short* s_id = reinterpret_cast<unsigned short*>(s_cnt + NS + 1);    // [NS] original index of the sorted draw
   unsigned short* s_id2 = s_id + NS;                                     // [NS] scratch
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(z_all) | reinterpret_cast<uintptr_t>(pts) |
+                        (uintptr_t)__cvta_generic_to_shared(s_out)) & 15) == 0;
   for (int64_t b = blockIdx.x * (int64_t)kWarpsPerCta + w; b < B; b += (int64_t)gridDim.x * kWarpsPerCta) {
     for (int k = lane; k < Nc; k += 32) s_z[k] = __ldcs(zc + b * Nc + k);
     for (int k = lane; k < Nc - 2; k += 32) s_w[k] = __ldcs(weights + b * Nc + k + 1);   // interior weights, rays.py:321
@@ -360,13 +362,8 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
           while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cdf[mid] <= x) lo = mid + 1; else hi = mid; }
           ind = lo;
           have = true;
-        } else if (ind < nb && s_cdf[ind] <= x) {
-          ++ind;
-          if (ind < nb && s_cdf[ind] <= x) {           // more than one bin ahead: finish with a binary search
-            int lo = ind + 1, hi = nb;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cdf[mid] <= x) lo = mid + 1; else hi = mid; }
-            ind = lo;
-          }
+        } else {
+          while (ind < nb && s_cdf[ind] <= x) ++ind;   // ascending draws: a step or two from the previous index
         }
         const int below = max(ind - 1, 0), above = min(ind, nb - 1);
         const float cb = s_cdf[below], ca = s_cdf[above], bb = s_bins[below], ba = s_bins[above];
@@ -410,14 +407,35 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
       s_out[i + lo] = zi;
     }
     __syncwarp();
-    for (int k = lane; k < Nt; k += 32) z_all[b * Nt + k] = s_out[k];
-    if (pts) {
-      const float o0 = ro[b * 3], o1 = ro[b * 3 + 1], o2 = ro[b * 3 + 2];
-      const float d0 = rd[b * 3], d1 = rd[b * 3 + 1], d2 = rd[b * 3 + 2];
-      for (int e = lane; e < 3 * Nt; e += 32) {     // 3*Nt contiguous floats per ray: coalesced stores
-        const int sidx = e / 3, k = e - 3 * sidx;
-        const float o = k == 0 ? o0 : (k == 1 ? o1 : o2), d = k == 0 ? d0 : (k == 1 ? d1 : d2);
-        pts[(b * Nt) * 3 + e] = __fadd_rn(o, __fmul_rn(d, s_out[sidx]));
+    float* zrow = z_all + b * Nt;
+    float* prow = pts ? pts + b * Nt * 3 : nullptr;
+    if ((Nt & 3) == 0 && vec_ok) {
+      // four depths per lane and step: one 16-byte store of depths, three of points (12 consecutive floats)
+      const float o0 = pts ? ro[b * 3] : 0.f, o1 = pts ? ro[b * 3 + 1] : 0.f, o2 = pts ? ro[b * 3 + 2] : 0.f;
+      const float d0 = pts ? rd[b * 3] : 0.f, d1 = pts ? rd[b * 3 + 1] : 0.f, d2 = pts ? rd[b * 3 + 2] : 0.f;
+      for (int g = lane; g < (Nt >> 2); g += 32) {
+        const float4 zq = *reinterpret_cast<const float4*>(s_out + 4 * g);
+        __stcs(reinterpret_cast<float4*>(zrow) + g, zq);
+        if (pts) {
+          float4* pq = reinterpret_cast<float4*>(prow) + 3 * g;
+          __stcs(pq, make_float4(__fadd_rn(o0, __fmul_rn(d0, zq.x)), __fadd_rn(o1, __fmul_rn(d1, zq.x)),
+                                 __fadd_rn(o2, __fmul_rn(d2, zq.x)), __fadd_rn(o0, __fmul_rn(d0, zq.y))));
+          __stcs(pq + 1, make_float4(__fadd_rn(o1, __fmul_rn(d1, zq.y)), __fadd_rn(o2, __fmul_rn(d2, zq.y)),
+                                     __fadd_rn(o0, __fmul_rn(d0, zq.z)), __fadd_rn(o1, __fmul_rn(d1, zq.z))));
+          __stcs(pq + 2, make_float4(__fadd_rn(o2, __fmul_rn(d2, zq.z)), __fadd_rn(o0, __fmul_rn(d0, zq.w)),
+                                     __fadd_rn(o1, __fmul_rn(d1, zq.w)), __fadd_rn(o2, __fmul_rn(d2, zq.w))));
+        }
+      }
+    } else {
+      for (int k = lane; k < Nt; k += 32) zrow[k] = s_out[k];
+      if (pts) {
+        const float o0 = ro[b * 3], o1 = ro[b * 3 + 1], o2 = ro[b * 3 + 2];
+        const float d0 = rd[b * 3], d1 = rd[b * 3 + 1], d2 = rd[b * 3 + 2];
+        for (int e = lane; e < 3 * Nt; e += 32) {     // 3*Nt contiguous floats per ray: coalesced stores
+          const int sidx = e / 3, k = e - 3 * sidx;
+          const float o = k == 0 ? o0 : (k == 1 ? o1 : o2), d = k == 0 ? d0 : (k == 1 ? d1 : d2);
+          prow[e] = __fadd_rn(o, __fmul_rn(d, s_out[sidx]));
+        }
       }
     }
     __syncwarp();

@@ -340,28 +340,57 @@ def test_convergence_300_steps_vs_fp32_restatement(rn, dev):
     assert dev_ours <= max(0.1, 2.0 * dev_tf32), (dev_ours, dev_tf32)                        # single checkpoints: within the noise scale
 
 
-def test_pose_refinement_on_known_scene(rn, dev):
-    """The quantity pose gradients exist for: moving noisy cameras against a known scene.  Both networks are FIXED at the
-    teacher's weights (lr = 0), the cameras start 1 deg / 1 % off with omega seeded N(0, 1e-3) (live rotation branch,
-    quirk 11), and only (omega, delta_t) are optimised (pose clip 0.1, Adam at 1e-3, train_pose_opt.py:398-409 semantics).
-    With no chaotic network training in the loop the two trajectories are comparable point by point."""
-    steps, B, H, W = 200, 2048, 800, 800
+def _blob_scene_targets(ro, rd, n=256):
+    """Analytic learnable scene: three coloured Gaussian density blobs inside the lego cameras' view volume, rendered with
+    the reference's compositing formula (oracle/torch_ref.py::raw2outputs) on n uniform depths in [2, 6]."""
+    dev = ro.device
+    centers = torch.tensor([[0.7, 0.0, 0.2], [-0.5, 0.5, -0.1], [0.0, -0.7, 0.4]], device=dev)
+    cols = torch.tensor([[1.0, 0.15, 0.15], [0.15, 1.0, 0.15], [0.15, 0.15, 1.0]], device=dev)
+    z = torch.linspace(2.0, 6.0, n, device=dev).expand(ro.shape[0], n)
+    pts = ro[:, None, :] + rd[:, None, :] * z[..., None]
+    d2 = ((pts[:, :, None, :] - centers) ** 2).sum(-1)
+    dens = 25.0 * torch.exp(-d2 / (2 * 0.4 ** 2))
+    sigma = dens.sum(-1, keepdim=True)
+    rgb = (dens[..., None] * cols).sum(-2) / (sigma + 1e-6)
+    return TR.raw2outputs(rgb, sigma, z, rd, None, True)["rgb_map"]
+
+
+def test_pose_refinement_on_learned_scene(rn, dev):
+    """The quantity pose gradients exist for.  A scene is first LEARNED (our Trainer, true cameras, 600 steps on an
+    analytic three-blob density field), then the cameras are perturbed by 2 deg / 2 %, omega is seeded N(0, 1e-3) (live
+    rotation branch, quirk 11) and ONLY the poses are optimised (networks frozen: lr = 0; pose clip 0.1, Adam,
+    train_pose_opt.py:398-409 semantics) -- once with our kernels, once with the fp32 restatement, same batches and
+    draws.  Both must pull the cameras back, and ours must end where fp32 ends."""
+    H = W = 800
     focal = TR.lego_focal(W)
-    wc, wf = O.make_weights(21, sharpen=True), O.make_weights(22, sharpen=True)
-    tc, tf = TR.to_params(wc, dev, False), TR.to_params(wf, dev, False)
     gt = rn.lego_poses(dev)
-    noisy = rn.add_noise_to_poses(gt, 1.0, 1.0, seed=42)
     dirs = TR.get_ray_directions(H, W, focal, device=dev)
+    torch.manual_seed(42)
+    nc, nf = rn.create_nerf(rn.ModelConfig())
+    nc, nf = nc.to(dev), nf.to(dev)
+    pre = rn.Trainer(nc, nf, rn.RenderConfig(), lr=5e-4)
+    for it in range(600):
+        ro, rd, _, _ = _scene_rays(rn, dev, 4096, 20000 + it)
+        with torch.no_grad():
+            tgt = _blob_scene_targets(ro, rd)
+        torch.manual_seed(it)
+        loss = pre.step_rays(ro, rd, tgt)
+    psnr_scene = _psnr(float(loss) / 2)
+    wc, wf = _weights_of(nc), _weights_of(nf)
+    del pre
+    # fresh modules on the learned weights (the pre-training Trainer's flat buffers are gone)
     nc, nf = _net_from(rn, wc, dev), _net_from(rn, wf, dev)
     pc, pf = TR.to_params(wc, dev), TR.to_params(wf, dev)
+    noisy = rn.add_noise_to_poses(gt, 2.0, 2.0, seed=42)
     cam = rn.CameraPoseParameters(noisy).to(dev)
     g = torch.Generator(device=dev).manual_seed(1)
     with torch.no_grad():
         cam.rotation_deltas.copy_(torch.randn(100, 3, device=dev, generator=g) * 1e-3)
     rot = cam.rotation_deltas.detach().clone().requires_grad_(True)
     trans = cam.translation_deltas.detach().clone().requires_grad_(True)
-    ours = rn.Trainer(nc, nf, rn.RenderConfig(), lr=0.0, camera_params=cam, pose_lr=1e-3)
-    ref = TR.RefTrainer(pc, pf, lr=0.0, initial_poses=noisy, rot=rot, trans=trans, pose_lr=1e-3)
+    steps, B, pose_lr = 300, 2048, 1e-3
+    ours = rn.Trainer(nc, nf, rn.RenderConfig(), lr=0.0, camera_params=cam, pose_lr=pose_lr)
+    ref = TR.RefTrainer(pc, pf, lr=0.0, initial_poses=noisy, rot=rot, trans=trans, pose_lr=pose_lr)
 
     class _Sampler:
         def get_rays_for_batch_fused(self, pb, cp):
@@ -380,30 +409,28 @@ def test_pose_refinement_on_known_scene(rn, dev):
         _, _, img, uv = _scene_rays(rn, dev, B, 9000 + it)
         with torch.no_grad():
             ro_gt, rd_gt = TR.rays_from_pixels(img, uv, gt, dirs)
-        tgt = _teacher_targets(tc, tf, ro_gt.contiguous(), rd_gt.contiguous())
+            tgt = _blob_scene_targets(ro_gt.contiguous(), rd_gt.contiguous())
         torch.manual_seed(it)
         ours.step_pixels(PixelBatch(img, uv, tgt), _Sampler(), optimize_poses=True)
         torch.manual_seed(it)
         ref.step_pixels(img, uv, tgt, dirs, optimize_poses=True)
-        if (it + 1) % 25 == 0:
+        if (it + 1) % 50 == 0:
             with torch.no_grad():
                 traj.append((it + 1, *errs(cam.get_all_poses()), *errs(TR.get_poses(noisy, rot, trans))))
-    print(f"\n[pose refinement, known scene] initial pose error: rot {e0[0]:.4f} deg, trans {e0[1]:.5f}")
+    d_rot = float((cam.rotation_deltas.detach() - rot.detach()).norm() / rot.detach().norm())
+    d_tr = float((cam.translation_deltas.detach() - trans.detach()).norm() / trans.detach().norm().clamp_min(1e-12))
+    print(f"\n[pose refinement, learned scene] scene PSNR after pre-training {psnr_scene:.2f} dB; initial pose error: rot {e0[0]:.4f} deg, "
+          f"trans {e0[1]:.5f}")
     print("  step   ours: rot deg, trans      fp32 restatement: rot deg, trans")
     for s_, a, b, c, d in traj:
         print(f"  {s_:4d}  {a:8.4f} {b:8.5f}   {c:8.4f} {d:8.5f}")
-    d_rot = float((cam.rotation_deltas.detach() - rot.detach()).norm() / rot.detach().norm())
-    d_tr = float((cam.translation_deltas.detach() - trans.detach()).norm() / trans.detach().norm().clamp_min(1e-12))
     print(f"  parameter space after {steps} steps: |omega_ours - omega_fp32| / |omega_fp32| = {d_rot:.3f}, "
           f"|dt_ours - dt_fp32| / |dt_fp32| = {d_tr:.3f}")
-    _report("pose_refinement_known_scene", {"steps": steps, "rays_per_step": B, "initial_err": e0, "trajectory": traj,
-                                            "rel_diff_omega": d_rot, "rel_diff_delta_t": d_tr})
-    # Measured on a B200: on this random-teacher scene Adam's normalised steps make the cameras drift in BOTH runs (the fp32
-    # restatement's rotation error grows 0.76 -> 1.56 deg), and ours follows the fp32 trajectory point by point: at every
-    # checkpoint the pose errors agree to < 4 % of the initial error although the per-step pose-gradient cosine is 0.96.
-    for s_, a, b, c, d in traj:
-        assert abs(a - c) <= 0.1 * e0[0] and abs(b - d) <= 0.1 * e0[1], (e0, traj)
-    assert d_rot <= 0.25 and d_tr <= 0.25, (d_rot, d_tr)
+    _report("pose_refinement_learned_scene", {"steps": steps, "rays_per_step": B, "scene_psnr": psnr_scene, "initial_err": e0,
+                                              "trajectory": traj, "rel_diff_omega": d_rot, "rel_diff_delta_t": d_tr})
+    fa, fb, fc, fd = traj[-1][1:]
+    assert fc < 0.8 * e0[0] or fd < 0.8 * e0[1], ("the fp32 restatement did not refine the poses: scenario void", e0, traj[-1])
+    assert fa <= fc + 0.1 * e0[0] and fb <= fd + 0.1 * e0[1], (e0, traj[-1])     # ours refines as well as fp32 does
 
 
 def test_pose_opt_convergence_300_steps_vs_fp32_restatement(rn, dev):
