@@ -26,6 +26,7 @@
 #include "ptx.cuh"
 #include "gemm.h"
 #include "mlp_layout.h"
+#include "pe.cuh"
 #include <cuda_bf16.h>
 #include <mutex>
 
@@ -39,6 +40,7 @@ void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
 
 constexpr int kPairThreads = 608;         // 19 warps
+constexpr int kPairThreadsPE = 640;       // + the positional-encoding warp (inference, PE fused)
 constexpr int kPairMaxLayers = 12;
 constexpr int kPairMaxChunks = 8;
 constexpr int kChunkBytes = 16384;              // [128 rows][64 bf16], SWIZZLE_128B
@@ -102,6 +104,11 @@ struct PairParams {
   int64_t m_rows;
   int const_slot;              // which slot of c_pair_consts2 holds this network's fp32 section
   float* raw;
+  // PE-fused inference (mlp_chain_pair_kernel<false, true>): the kernel encodes the points itself and takes the view
+  // branch's direction term as a per-ray bias of the last layer
+  const float* pts;            // [M][3]
+  const float* dirvec;         // [M / group][128]  (encode.cu: dir_bias_kernel)
+  int64_t group;               // consecutive points per ray
 };
 
 // Biases and fp32 head weights of the network being evaluated (layout::kF32Elems floats), copied device-to-device on the
@@ -221,9 +228,10 @@ __device__ __forceinline__ void pair_epilogue(uint32_t t_addr, uint8_t* s_tile, 
   if (HEADS > 0) { h0 = hh0.x + hh0.y; h1 = hh1.x + hh1.y; h2 = hh2.x + hh2.y; }
 }
 
-template <bool TRAIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+template <bool TRAIN, bool PE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PE ? kPairThreadsPE : kPairThreads, 1)
 mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
+  static_assert(!(TRAIN && PE), "the in-kernel encoder is built for inference (training stores x_enc / d_enc for the weight gradients)");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_act = smem;                                   // [2 slots][4 chunks][16 KiB]
@@ -259,7 +267,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     prefetch_tmap(&p.tmAux[0]); prefetch_tmap(&p.tmAux[1]);
     for (int i = 0; i < kNBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&aux_full[i], 1); mbar_init(&aux_empty[i], 1);
+      mbar_init(&aux_full[i], PE ? 2 : 1); mbar_init(&aux_empty[i], 1);      // PE: one arrive per CTA's encoder warp
       mbar_init(&act_ready[i], 32); mbar_init(&tmem_full[i], 1);
       mbar_init(&staged[i], 16); mbar_init(&store_done[i], 1);
     }
@@ -285,7 +293,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
       for (int l = 0; l < p.n_layers; ++l) {
         const int n = p.L[l].n, k_chunks = p.L[l].k_chunks, aux_load = p.L[l].aux_load;
         for (int slot = 0; slot < tiles_here; ++slot) {
-          if (aux_load) {
+          if (aux_load && !PE) {
             const uint32_t j = slot ? aux_n1++ : aux_n0++;
             if (j > 0) mbar_wait(&aux_empty[slot], (j - 1) & 1u);
             if (elect_one()) {
@@ -382,19 +390,44 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     RN_TL_DECL(tl, (warp == 2 ? 1 : 2), lane == 0 && (warp == 2 || warp == 17));
     const float2* consts2 = c_pair_consts2[p.const_slot];
     const float* consts1 = reinterpret_cast<const float*>(consts2);
+    const int bt = (int)threadIdx.x - 64;             // 0..511 over the epilogue threads
+    float pref0 = 0.f, pref1 = 0.f;                   // PE: next view-layer bias value of this thread, per tile slot
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
       for (int l = 0; l < p.n_layers; ++l) {
         const PairLayer L = p.L[l];
-        // stage this layer's bias: every epilogue warp has finished the previous layer (first barrier), 256 threads copy
-        // one value each out of the constant slot, and the copies are visible to all (second barrier)
-        named_bar_sync(5, 512);
-        if (threadIdx.x - 64 < 256) s_bias[threadIdx.x - 64] = consts1[L.bias_off + (threadIdx.x - 64)];
-        named_bar_sync(5, 512);
+        const bool ray_bias = PE && (l == p.n_layers - 1);      // view layer: per-ray direction term instead of the bias
+        if (!ray_bias) {
+          // stage this layer's bias: every epilogue warp has finished the previous layer (first barrier), 256 threads copy
+          // one value each out of the constant slot, and the copies are visible to all (second barrier)
+          named_bar_sync(5, 512);
+          if (bt < 256) s_bias[bt] = consts1[L.bias_off + bt];
+          named_bar_sync(5, 512);
+        }
         for (int slot = 0; slot < tiles_here; ++slot) {
           const uint32_t i = slot ? it1++ : it0++;
-          const int64_t gr = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128 + row;
+          const int64_t row0 = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128;
+          const int64_t gr = row0 + row;
           const bool row_ok = gr < p.m_rows;
+          const float* sb = s_bias;
+          if (PE) {
+            // the tile's rows belong to at most two rays (host-checked: group == 64 or >= 128): A = ray of its first row
+            const int64_t rayA = row0 / p.group;
+            const int64_t n_rays = p.m_rows / p.group;
+            if (l == p.n_layers - 2 && bt < 256) {
+              // one layer ahead (thousands of cycles): fetch this thread's element of [dirvec[rayA] | dirvec[rayA + 1]]
+              const int64_t ray = min(rayA + (bt >> 7), n_rays - 1);
+              const float v = (ray >= 0) ? __ldg(p.dirvec + ray * 128 + (bt & 127)) : 0.f;
+              if (slot) pref1 = v; else pref0 = v;
+            }
+            if (ray_bias) {
+              named_bar_sync(5, 512);                  // all warps are done with the previous item's bias
+              if (bt < 256) s_bias[bt] = slot ? pref1 : pref0;
+              named_bar_sync(5, 512);
+              const int64_t rowsA = (rayA + 1) * p.group - row0;
+              if ((int64_t)row >= rowsA) sb = s_bias + 128;
+            }
+          }
           RN_TL(tl, 100 + l * 10 + slot);
           mbar_wait(&tmem_full[slot], i & 1u);
           RN_TL(tl, 300 + l * 10 + slot);                  // accumulator complete
@@ -416,7 +449,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
               else if (L.relu) pair_epilogue<2, 0, true, TRAIN>(t_addr, s_tile, row, cq * 2, s_bias, consts2, L.head_w_off >> 1, 256, mb, h0, h1, h2);
               else pair_epilogue<2, 0, false, false>(t_addr, s_tile, row, cq * 2, s_bias, consts2, L.head_w_off >> 1, 256, mb, h0, h1, h2);
             } else {
-              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, s_bias, consts2, L.head_w_off >> 1, 128, mb, h0, h1, h2);
+              pair_epilogue<1, 3, true, false>(t_addr, s_tile, row, cq, sb, consts2, L.head_w_off >> 1, 128, mb, h0, h1, h2);
             }
           }
           RN_TL(tl, 600 + l * 10 + slot);                  // math done
@@ -478,6 +511,42 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
         }
       }
       tma_store_wait_all0();
+    }
+  } else if (PE && warp == 19) {
+    // ---------------- encoder warp (inference): x_enc of this CTA's 128 rows, straight into the side buffer ----------------
+    // Same barrier protocol as the TMA-loaded side chunk: wait until layer 5's MMAs of the previous tile in this slot have
+    // read the buffer (aux_empty), write the tile in the SWIZZLE_128B K-major layout, make it visible to the tensor core
+    // (fence.proxy.async), arrive on the leader's aux_full (count 2: one per CTA).  The buffer is free from layer 5 on
+    // (the direction term needs no K chunk any more), so the next group's tile is encoded under layers 6-9.
+    const uint32_t aux_full_leader = mapa_u32(smem_u32(aux_full), 0);
+    uint32_t n0 = 0, n1 = 0;
+    for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+      const int tiles_here = min(2, p.n_ptiles - grp * 2);
+      for (int slot = 0; slot < tiles_here; ++slot) {
+        const uint32_t j = slot ? n1++ : n0++;
+        if (j > 0) mbar_wait(&aux_empty[slot], (j - 1) & 1u);
+        uint8_t* tile = s_aux + slot * kAuxBytes;
+        const int64_t row0 = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128;
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 32 + lane;                 // lanes of a quarter warp write eight different 16-byte columns
+          const int64_t gr = row0 + r;
+          float x[3] = {0.f, 0.f, 0.f};
+          if (gr < p.m_rows) { x[0] = __ldg(p.pts + gr * 3); x[1] = __ldg(p.pts + gr * 3 + 1); x[2] = __ldg(p.pts + gr * 3 + 2); }
+          float feat[64];
+          pe_features_fast<kPosFreqs>(x, feat);
+          feat[63] = 0.f;
+          uint8_t* rowp = tile + r * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) =
+                make_uint4(pe_pack_bf16(feat[8 * c], feat[8 * c + 1]), pe_pack_bf16(feat[8 * c + 2], feat[8 * c + 3]),
+                           pe_pack_bf16(feat[8 * c + 4], feat[8 * c + 5]), pe_pack_bf16(feat[8 * c + 6], feat[8 * c + 7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(aux_full_leader + slot * 8);
+      }
     }
   }
 
@@ -870,14 +939,23 @@ static int acquire_const_slot(const float* consts, cudaStream_t st, int* slot_ou
 // where each K chunk of A lives: activation chunks for the part produced by the previous layer, the side buffer for
 // x_enc (first chunk of layers 0 and 5) and d_enc (last chunk of the view layer).
 int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const void* x_enc, int64_t ld_x,
-                           const void* d_enc, int64_t ld_d, const float* consts, float* raw, bool training, cudaStream_t st) {
+                           const void* d_enc, int64_t ld_d, const float* consts, float* raw, bool training, cudaStream_t st,
+                           const PairEncodeArgs* pe) {
   int rc = check_arch();
   if (rc != RN_OK) return rc;
-  RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kPairMaxLayers && M > 0 && consts && raw && x_enc && d_enc);
+  RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kPairMaxLayers && M > 0 && consts && raw);
+  RN_REQUIRE(pe ? (!training && pe->pts && pe->dirvec && pair_encode_supported(pe->group) && M % pe->group == 0) : (x_enc && d_enc));
   static thread_local PairParams p;     // ~4 KB of tensor maps: built on the host, passed by value as a kernel parameter
   double flops = 0.0;
-  if ((rc = make_tmap(&p.tmAux[0], x_enc, 64, M, ld_x, 128)) != RN_OK) return rc;
-  if ((rc = make_tmap(&p.tmAux[1], d_enc, 64, M, ld_d, 128)) != RN_OK) return rc;
+  if (!pe) {
+    if ((rc = make_tmap(&p.tmAux[0], x_enc, 64, M, ld_x, 128)) != RN_OK) return rc;
+    if ((rc = make_tmap(&p.tmAux[1], d_enc, 64, M, ld_d, 128)) != RN_OK) return rc;
+  } else {
+    // never dereferenced in this mode (prefetch.tensormap only): any valid map
+    if ((rc = make_tmap(&p.tmAux[0], layers[0].B, layers[0].k, layers[0].n, layers[0].ldb, layers[0].n / 2)) != RN_OK) return rc;
+    p.tmAux[1] = p.tmAux[0];
+  }
+  p.pts = pe ? pe->pts : nullptr; p.dirvec = pe ? pe->dirvec : nullptr; p.group = pe ? pe->group : 1;
   for (int l = 0; l < n_layers; ++l) {
     const ChainLayerHost& h = layers[l];
     RN_REQUIRE((h.n == 256 || h.n == 128) && (h.k == 64 || h.k == 256 || h.k == 320));
@@ -914,8 +992,9 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
   if ((rc = acquire_const_slot(consts, st, &p.const_slot)) != RN_OK) return rc;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) {
-    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
-    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
   }
   const int n_groups = (p.n_ptiles + 1) / 2;
   const int max_clusters = num_sms() / 2;
@@ -923,8 +1002,9 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
   g_prof_next_flops = flops;
   int slot;
   prof_begin(0 /*MODE_NT*/, st, &slot);
-  if (training) mlp_chain_pair_kernel<true><<<grid, kPairThreads, kPairSmem, st>>>(p);
-  else mlp_chain_pair_kernel<false><<<grid, kPairThreads, kPairSmem, st>>>(p);
+  if (training) mlp_chain_pair_kernel<true, false><<<grid, kPairThreads, kPairSmem, st>>>(p);
+  else if (pe) mlp_chain_pair_kernel<false, true><<<grid, kPairThreadsPE, kPairSmem, st>>>(p);
+  else mlp_chain_pair_kernel<false, false><<<grid, kPairThreads, kPairSmem, st>>>(p);
   prof_end(slot, st);
   RN_LAUNCH_CHECK();
   return RN_OK;

@@ -5,6 +5,7 @@
 //   and the backward passes of all of them.
 #include "common.cuh"
 #include "mlp_layout.h"
+#include "pe.cuh"
 
 namespace rn {
 
@@ -72,6 +73,44 @@ encode_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, int
       stg256_zero(dd + 32);
       stg256_zero(dd + 48);
     }
+  }
+}
+
+// View-direction branch hoisted per RAY (inference): every point of a ray shares one direction, so its contribution to
+// dir_linear (model.py:187-192: cat[features, d_enc] @ W_d^T + b_d) is the same 128-vector for all of them:
+//   dirvec[r][j] = b_d[j] + sum_{i<27} bf16(d_enc[r][i]) * W_d[j][256 + i]
+// (bf16-rounded operands, fp32 accumulation: what the tensor core did with the d_enc K-chunk).  The forward chain adds it
+// as a per-row bias of the view layer instead of streaming a 64-wide K chunk per POINT: 84 -> 60 sin/cos per point, no
+// d_enc tile in HBM, one K chunk less in the view layer.  One warp per ray.
+__global__ void __launch_bounds__(256)
+dir_bias_kernel(const float* __restrict__ dirs, int64_t R, const __nv_bfloat16* __restrict__ WD /*[128][320]*/,
+                const float* __restrict__ f32sec, float* __restrict__ dirvec /*[R][128]*/) {
+  __shared__ float s_w[27][128];                       // W_d[:, 256:283] transposed, fp32 copy of the bf16 values
+  __shared__ float s_b[128];
+  for (int i = threadIdx.x; i < 27 * 128; i += blockDim.x) {
+    const int f = i / 128, j = i - f * 128;
+    s_w[f][j] = __bfloat162float(WD[(size_t)j * 320 + 256 + f]);
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_b[i] = f32sec[kBD + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const float d[3] = {__ldg(dirs + r * 3), __ldg(dirs + r * 3 + 1), __ldg(dirs + r * 3 + 2)};
+    float feat[27];
+    pe_features_fast<kDirFreqs>(d, feat);
+    float acc[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc[m] = s_b[lane + 32 * m];
+#pragma unroll
+    for (int f = 0; f < 27; ++f) {
+      const float v = __bfloat162float(__float2bfloat16_rn(feat[f]));
+#pragma unroll
+      for (int m = 0; m < 4; ++m) acc[m] = fmaf(v, s_w[f][lane + 32 * m], acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) dirvec[r * 128 + lane + 32 * m] = acc[m];
   }
 }
 
@@ -362,6 +401,13 @@ namespace rn {
 int launch_encode(const float* pts, const float* dirs, int64_t M, int group, void* XC, int ldx, void* FD, int ldf,
                   cudaStream_t st) {
   encode_kernel<<<grid_for(M, 256), 256, 0, st>>>(pts, dirs, M, group, (__nv_bfloat16*)XC, ldx, (__nv_bfloat16*)FD, ldf);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+int launch_dir_bias(const float* dirs, int64_t R, const void* packed, float* dirvec, cudaStream_t st) {
+  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(packed);
+  const float* F = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kBf16Bytes);
+  dir_bias_kernel<<<grid_for(R * 32, 256, 4), 256, 0, st>>>(dirs, R, W + kWD, F, dirvec);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

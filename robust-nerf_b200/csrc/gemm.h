@@ -38,8 +38,13 @@ struct ChainLayerHost {
   // is d_enc), whether that side chunk is (re)loaded before this layer (1 = x_enc, 2 = d_enc) and released after it
   int aux_kind, aux_load, aux_release;
 };
+// PE-fused inference: the kernel encodes `pts` itself (no x_enc tensor), and the view layer takes dirvec[ray] as its bias
+// (no d_enc K chunk: that layer's k is 256).  A 128-row tile may touch at most two rays.
+struct PairEncodeArgs { const float* pts; const float* dirvec; int64_t group; };
+inline bool pair_encode_supported(int64_t group) { return group == 64 || group >= 128; }
 int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const void* x_enc, int64_t ld_x,
-                           const void* d_enc, int64_t ld_d, const float* consts, float* raw, bool training, cudaStream_t st);
+                           const void* d_enc, int64_t ld_d, const float* consts, float* raw, bool training, cudaStream_t st,
+                           const PairEncodeArgs* pe = nullptr);
 // one layer of the data-gradient chain (chain_pair.cu): D[M,256] = (A[M,k] B[k, n_off : n_off+256]) .* mask
 struct BwdLayerHost {
   const void* B; int64_t ldb; int b_cols;      // weight matrix [k rows][b_cols], leading dimension ldb
@@ -53,6 +58,8 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
 int mlp_chain_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const float* consts, float* raw, bool wmask,
                       cudaStream_t st);
 
+// inference: per-ray view-direction projection dirvec[R][128] (encode.cu: dir_bias_kernel)
+int launch_dir_bias(const float* dirs, int64_t R, const void* packed, float* dirvec, cudaStream_t st);
 int launch_encode(const float* pts, const float* dirs, int64_t M, int group, void* XC, int ldx, void* FD, int ldf, cudaStream_t st);
 size_t heads_bwd_scratch_bytes(int64_t M);
 int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,

@@ -34,9 +34,13 @@ struct TrainWs {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 constexpr int kTnLaunches = 10;      // weight-gradient launches per backward pass: each keeps its own partial-tile region
 
+// inference: per-ray direction term of the view layer, [M / group][128] fp32 with group >= 64 (PE-fused chain)
+static size_t dirvec_bytes(int64_t M) { return align_up((size_t)(M / 64 + 1) * 128 * sizeof(float), 256); }
+
 static size_t workspace_bytes(int64_t M, int training) {
   const size_t elems = training ? (size_t)(kTrainFwdElems + kTrainBwdElems) : (size_t)kInferElems;
   size_t b = align_up((size_t)M * elems * 2, 256);
+  if (!training) b += dirvec_bytes(M);
   if (training) b += kTnLaunches * align_up(gemm_tn_scratch_bytes(), 256) + align_up(heads_bwd_scratch_bytes(M), 256);
   return b + 256;
 }
@@ -75,6 +79,10 @@ int g_chain_bwd = 1;      // rn_set_flag(3, v): 1 = data gradients as one CTA-pa
 // rn_set_flag(0, v): 0 = one launch per layer, 1 = layer-chained persistent launch (activations round-trip through L2),
 // 2 = CTA-pair chain with shared-memory-resident activations (chain_pair.cu; default)
 int g_chain_fwd = 2;
+// rn_set_flag(4, v): 1 = inference encodes the points inside the forward chain and hoists the view-direction term per ray
+// (default), 0 = separate encode kernel + TMA-loaded x_enc / d_enc chunks (the training layout; kept for A/B and as the
+// path for direction groups the fused kernel does not cover)
+int g_pe_fused = 1;
 
 static int mlp_forward(const void* packed, const float* pts, const float* dirs, int64_t M, int group, void* ws,
                        int training, float* raw, cudaStream_t st) {
@@ -96,7 +104,14 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
     HC = p;
     H[0] = HA; H[1] = HB; H[2] = HA; H[3] = HB; H[4] = XC + 64; H[5] = HA; H[6] = HB; H[7] = HA;
   }
-  RN_TRY(launch_encode(pts, dirs, M, group, XC, 320, FD, 320, st));
+  const bool pe_fused = !training && g_chain_fwd == 2 && g_pe_fused && pair_encode_supported(group);
+  float* dirvec = nullptr;
+  if (pe_fused) {
+    dirvec = reinterpret_cast<float*>(align_up(reinterpret_cast<uintptr_t>(ws), 256) + align_up((size_t)M * kInferElems * 2, 256));
+    RN_TRY(launch_dir_bias(dirs, M / group, packed, dirvec, st));
+  } else {
+    RN_TRY(launch_encode(pts, dirs, M, group, XC, 320, FD, 320, st));
+  }
   if (g_chain_fwd) {
     ChainLayerHost L[10];
     for (int l = 0; l < 8; ++l) {
@@ -111,6 +126,11 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
     if (g_chain_fwd == 2) {
       L[0].aux_kind = 1; L[0].aux_load = 1;
       L[5].aux_kind = 1; L[5].aux_release = 1;
+      if (pe_fused) {
+        L[9].k = 256;                                   // the d_enc K chunk became the per-ray bias dirvec
+        const PairEncodeArgs pe{pts, dirvec, group};
+        return mlp_chain_pair_forward(L, 10, M, nullptr, 0, nullptr, 0, F, raw, false, st, &pe);
+      }
       L[9].aux_kind = 2; L[9].aux_load = 2; L[9].aux_release = 1;
       return mlp_chain_pair_forward(L, 10, M, XC, 320, FD + 256, 320, F, raw, training != 0, st);
     }
@@ -212,6 +232,7 @@ int rn_set_flag(int flag, int value) {
 #endif
   if (flag == 2) { g_chain_ring = value; return RN_OK; }
   if (flag == 3) { g_chain_bwd = value; return RN_OK; }
+  if (flag == 4) { g_pe_fused = value; return RN_OK; }
   return RN_ERR_INVALID_ARG;
 }
 

@@ -733,6 +733,42 @@ def test_chained_forward_equals_per_layer_forward(rn, dev):
         lib.rn_set_flag(0, 2)
 
 
+def test_pe_fused_inference_chain(rn, dev):
+    """Inference with the positional encoding computed inside the forward chain and the view-direction term hoisted per
+    ray (rn_set_flag(4, 1), default; north_star subsystem 3) against (a) the same chain fed by the separate encode kernel
+    (flag 4 = 0) and (b) the fp32 oracle.  Direction groups 64 / 128 / 192 / 320 take the fused kernel, 1 / 32 / 96 the
+    unfused one; ragged point counts exercise partial tiles and tiles that straddle two rays."""
+    from robust_nerf_b200 import _lib
+    lib = _lib.lib()
+    w = O.make_weights(13, sharpen=True)
+    net = load_net(rn, w, dev)
+    rng = np.random.default_rng(9)
+    try:
+        for group, rays in ((64, 1), (64, 37), (192, 5), (192, 301), (128, 9), (320, 3), (96, 7), (32, 11)):
+            M = group * rays
+            pts = rng.uniform(-4, 4, (M, 3)).astype(np.float32)
+            dirs = rng.standard_normal((rays, 3)).astype(np.float32)
+            dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+            outs = {}
+            for fused in (1, 0):
+                lib.rn_set_flag(4, fused)
+                with torch.no_grad():
+                    outs[fused] = net.forward_raw(T(pts, dev), T(dirs, dev), group).clone()
+            torch.cuda.synchronize()
+            a, b = outs[1], outs[0]
+            # same bf16 operands up to one feature in 10^4 rounding to the neighbouring bf16 value (angle-doubling
+            # sin/cos, csrc/pe.cuh) and the direction term accumulated in fp32 instead of inside the tensor core
+            err = (a - b).abs()
+            scale = b.abs().max().item()
+            assert err.max().item() <= 4e-3 * scale and err.mean().item() <= 2e-4 * scale, (group, rays, err.max().item(), scale)
+            if M <= 4096:
+                rgb, sigma = O.nerf_forward(w, pts, np.repeat(dirs, group, 0))
+                got_rgb = torch.sigmoid(a[:, :3]).cpu().numpy()
+                assert np.abs(got_rgb - rgb).max() < 1e-2
+    finally:
+        lib.rn_set_flag(4, 1)
+
+
 def test_chained_data_gradients_equal_per_layer(rn, dev):
     """The CTA-pair data-gradient chain (one launch: dHC -> dF -> dH7 ... dH0, masks applied from the packed bits)
     must reproduce the per-layer NN GEMM chain bit for bit -- same MMAs in the same K order, same mask, same bf16
