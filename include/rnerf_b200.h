@@ -216,6 +216,8 @@ int rn_clip_adam_step(float* params, float* grads /*scaled in place by the clip*
                       float* norms_out /*scratch+output, 8 + 8*64 floats; [0..n_groups) = gradient norms*/,
                       const float* hyper_dev /*NULL, or device [lr, 1-beta1^step, sqrt(1-beta2^step)] overriding lr/step
                                                (so a captured CUDA graph can be replayed across steps)*/,
+                      float grad_scale /*applied to grads on load: 1 / world size when the buffer holds an all-reduced SUM
+                                         (the mean is taken here instead of in a separate launch), else 1*/,
                       rn_stream_t stream);
 
 #ifdef __cplusplus

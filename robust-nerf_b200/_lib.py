@@ -71,7 +71,7 @@ _SIGS = {
                              _P, _P, _P, c_size_t, _P]),
     "rn_gemm_scratch_bytes": (c_size_t, []),
     "rn_clip_adam_step": (c_int, [_P, _P, _P, _P, c_int64, POINTER(c_int64), POINTER(c_float), c_int, c_float, c_float,
-                                  c_float, c_float, c_int, _P, _P, _P]),
+                                  c_float, c_float, c_int, _P, _P, c_float, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

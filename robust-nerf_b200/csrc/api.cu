@@ -27,14 +27,14 @@ constexpr int kNormChunks = 64;      // CTAs per clip group
 
 // grid (kNormChunks, n_groups): fixed-order partial sums of squares -> part[group][chunk]
 __global__ void __launch_bounds__(256)
-grad_sumsq_kernel(const float* __restrict__ g, Groups gr, float* __restrict__ part) {
+grad_sumsq_kernel(const float* __restrict__ g, Groups gr, float gscale, float* __restrict__ part) {
   __shared__ float red[8];
   const int grp = blockIdx.y;
   const int64_t lo = gr.off[grp], hi = gr.off[grp + 1];
   const int64_t per = (hi - lo + kNormChunks - 1) / kNormChunks;
   const int64_t a = lo + per * blockIdx.x, b = (a + per < hi) ? a + per : hi;
   float acc = 0.f;
-  for (int64_t i = a + threadIdx.x; i < b; i += 256) { const float v = g[i]; acc = fmaf(v, v, acc); }
+  for (int64_t i = a + threadIdx.x; i < b; i += 256) { const float v = g[i] * gscale; acc = fmaf(v, v, acc); }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -51,7 +51,9 @@ grad_sumsq_kernel(const float* __restrict__ g, Groups gr, float* __restrict__ pa
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, Groups gr, const float* __restrict__ part, float* __restrict__ norms, float lr, float b1,
-                 float b2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ hyper) {
+                 float b2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ hyper, float gscale) {
+  // gscale: 1 / world size under data parallelism -- the buffer holds the all-reduced SUM of the ranks' gradients and the
+  // mean is taken here (and in grad_sumsq_kernel) instead of in a separate elementwise launch
   // hyper (device, optional): [lr, 1 - beta1^t, sqrt(1 - beta2^t)] -- lets a captured CUDA graph be replayed
   // with a changing learning rate / step count without re-capturing
   if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }
@@ -69,7 +71,7 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
     int grp = 0;
 #pragma unroll
     for (int k = 1; k < kMaxGroups; ++k) if (k < gr.n && i >= gr.off[k]) grp = k;
-    const float gi = g[i] * s_coef[grp];
+    const float gi = (g[i] * gscale) * s_coef[grp];
     g[i] = gi;
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
@@ -114,7 +116,7 @@ int rn_device_sm_count(int* out) {
 int rn_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const int64_t* group_offsets_host, const float* group_max_norm_host, int n_groups, float lr,
                       float beta1, float beta2, float eps, int step, float* norms_out, const float* hyper_dev,
-                      rn_stream_t stream) {
+                      float grad_scale, rn_stream_t stream) {
   RN_REQUIRE(params && grads && exp_avg && exp_avg_sq && norms_out && group_offsets_host && group_max_norm_host);
   RN_REQUIRE(n > 0 && n_groups >= 1 && n_groups <= kMaxGroups && step >= 1);
   Groups gr{};
@@ -124,12 +126,12 @@ int rn_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_av
   RN_REQUIRE(gr.off[0] == 0 && gr.off[n_groups] == n);
   cudaStream_t st = (cudaStream_t)stream;
   float* part = norms_out + kMaxGroups;     // norms_out must hold kMaxGroups + kMaxGroups*64 floats
-  grad_sumsq_kernel<<<dim3(kNormChunks, n_groups), 256, 0, st>>>(grads, gr, part);
+  grad_sumsq_kernel<<<dim3(kNormChunks, n_groups), 256, 0, st>>>(grads, gr, grad_scale, part);
   RN_LAUNCH_CHECK();
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
   clip_adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, gr, part, norms_out, lr, beta1,
-                                                     beta2, eps, bc1, bc2_sqrt, hyper_dev);
+                                                     beta2, eps, bc1, bc2_sqrt, hyper_dev, grad_scale);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

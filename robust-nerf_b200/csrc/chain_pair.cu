@@ -40,7 +40,7 @@ void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
 
 constexpr int kPairThreads = 608;         // 19 warps
-constexpr int kPairThreadsPE = 640;       // + the positional-encoding warp (inference, PE fused)
+constexpr int kPairThreadsPE = 672;       // + two positional-encoding warps, one per tile slot (inference, PE fused)
 constexpr int kPairMaxLayers = 12;
 constexpr int kPairMaxChunks = 8;
 constexpr int kChunkBytes = 16384;              // [128 rows][64 bf16], SWIZZLE_128B
@@ -512,41 +512,43 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
       }
       tma_store_wait_all0();
     }
-  } else if (PE && warp == 19) {
-    // ---------------- encoder warp (inference): x_enc of this CTA's 128 rows, straight into the side buffer ----------------
+  } else if (PE && warp >= 19) {
+    // ---------------- encoder warps (inference): x_enc of this CTA's 128 rows, straight into the side buffer ----------------
+    // One warp per tile slot (warp 19 <-> slot 0, warp 20 <-> slot 1): a tile costs one warp ~11,000 cycles and both
+    // slots' buffers come free within one layer of each other, so a single warp encoding them back to back delivered the
+    // second one late (first build: render 1.5 % SLOWER than with the separate encode kernel, profiles/r02_pe_fused.md).
     // Same barrier protocol as the TMA-loaded side chunk: wait until layer 5's MMAs of the previous tile in this slot have
     // read the buffer (aux_empty), write the tile in the SWIZZLE_128B K-major layout, make it visible to the tensor core
     // (fence.proxy.async), arrive on the leader's aux_full (count 2: one per CTA).  The buffer is free from layer 5 on
     // (the direction term needs no K chunk any more), so the next group's tile is encoded under layers 6-9.
     const uint32_t aux_full_leader = mapa_u32(smem_u32(aux_full), 0);
-    uint32_t n0 = 0, n1 = 0;
+    const int slot = warp - 19;
+    uint32_t j = 0;
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
-      const int tiles_here = min(2, p.n_ptiles - grp * 2);
-      for (int slot = 0; slot < tiles_here; ++slot) {
-        const uint32_t j = slot ? n1++ : n0++;
-        if (j > 0) mbar_wait(&aux_empty[slot], (j - 1) & 1u);
-        uint8_t* tile = s_aux + slot * kAuxBytes;
-        const int64_t row0 = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128;
+      if (slot >= min(2, p.n_ptiles - grp * 2)) continue;
+      if (j > 0) mbar_wait(&aux_empty[slot], (j - 1) & 1u);
+      ++j;
+      uint8_t* tile = s_aux + slot * kAuxBytes;
+      const int64_t row0 = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128;
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 32 + lane;                 // lanes of a quarter warp write eight different 16-byte columns
-          const int64_t gr = row0 + r;
-          float x[3] = {0.f, 0.f, 0.f};
-          if (gr < p.m_rows) { x[0] = __ldg(p.pts + gr * 3); x[1] = __ldg(p.pts + gr * 3 + 1); x[2] = __ldg(p.pts + gr * 3 + 2); }
-          float feat[64];
-          pe_features_fast<kPosFreqs>(x, feat);
-          feat[63] = 0.f;
-          uint8_t* rowp = tile + r * 128;
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 32 + lane;                 // lanes of a quarter warp write eight different 16-byte columns
+        const int64_t gr = row0 + r;
+        float x[3] = {0.f, 0.f, 0.f};
+        if (gr < p.m_rows) { x[0] = __ldg(p.pts + gr * 3); x[1] = __ldg(p.pts + gr * 3 + 1); x[2] = __ldg(p.pts + gr * 3 + 2); }
+        float feat[64];
+        pe_features_fast<kPosFreqs>(x, feat);
+        feat[63] = 0.f;
+        uint8_t* rowp = tile + r * 128;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) =
-                make_uint4(pe_pack_bf16(feat[8 * c], feat[8 * c + 1]), pe_pack_bf16(feat[8 * c + 2], feat[8 * c + 3]),
-                           pe_pack_bf16(feat[8 * c + 4], feat[8 * c + 5]), pe_pack_bf16(feat[8 * c + 6], feat[8 * c + 7]));
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(aux_full_leader + slot * 8);
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) =
+              make_uint4(pe_pack_bf16(feat[8 * c], feat[8 * c + 1]), pe_pack_bf16(feat[8 * c + 2], feat[8 * c + 3]),
+                         pe_pack_bf16(feat[8 * c + 4], feat[8 * c + 5]), pe_pack_bf16(feat[8 * c + 6], feat[8 * c + 7]));
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(aux_full_leader + slot * 8);
     }
   }
 
