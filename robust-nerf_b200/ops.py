@@ -313,6 +313,7 @@ class PackedWeights:
         # the sink was armed overwrites, any further one (chunked rendering, gradient accumulation) adds.
         self.grad_sink: Optional[torch.Tensor] = None
         self.sink_dirty = False
+        self.on_grads_ready = None             # Trainer hook: called after this net's gradients landed in the sink
 
     def get(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
         key = tuple((p.data_ptr(), p._version) for p in params)
@@ -391,6 +392,8 @@ class NeRFMLP(torch.autograd.Function):
             if accumulate:
                 sink.add_(flat)
             ctx.cache.sink_dirty = True
+            if ctx.cache.on_grads_ready is not None and not accumulate:
+                ctx.cache.on_grads_ready()
             return (g_pts, g_dirs, None, None, None) + (None,) * L.NUM_PARAM_TENSORS
         grads = split_flat_grads(flat)
         grads = [g if ctx.needs_input_grad[n_in + i] else None for i, g in enumerate(grads)]

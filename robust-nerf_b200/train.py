@@ -190,6 +190,10 @@ class Trainer:
         nets = [model_coarse] + ([model_fine] if model_fine is not None else [])
         dev = next(model_coarse.parameters()).device
         self.device = dev
+        # Flat layout [fine | coarse | omega | delta_t]: autograd runs the fine network's backward first, so its slice is
+        # final while the coarse backward still runs and can be all-reduced underneath it; what is left afterwards
+        # (coarse + poses) is one contiguous range.  `net_params` keeps the reference's optimiser order (coarse, fine).
+        flat_order = list(reversed(nets))
         self.net_params: List[List[nn.Parameter]] = [m.kernel_params() for m in nets]
         self.pose_params: List[nn.Parameter] = list(camera_params.parameters()) if camera_params is not None else []
         n_net = sum(p.numel() for ps in self.net_params for p in ps)
@@ -201,14 +205,24 @@ class Trainer:
         self.exp_avg = torch.zeros(total, device=dev)
         self.exp_avg_sq = torch.zeros(total, device=dev)
         off = 0
-        self.net_offsets = [0]
-        self._sink_slices: List[torch.Tensor] = []
-        for m, ps in zip(nets, self.net_params):
+        self.net_offsets = [0]                       # boundaries of the nets in FLAT order (clip groups)
+        self._sinks = {}                             # net -> its slice of gflat
+        self._param_off = {}                         # id(param) -> offset in the flat buffers
+        for m in flat_order:
             start = off
-            off = _flatten_into(ps, self.flat, self.gflat, off)
+            for q in m.kernel_params():
+                self._param_off[id(q)] = off + 0
+                off += q.numel()
+            _flatten_into(m.kernel_params(), self.flat, self.gflat, start)
             self.net_offsets.append(off)
-            self._sink_slices.append(self.gflat[start:off])  # armed as the net's gradient sink only inside a Trainer step
-        off = _flatten_into(self.pose_params, self.flat, self.gflat, off)
+            self._sinks[m] = self.gflat[start:off]   # armed as the net's gradient sink only inside a Trainer step
+        self._early = (0, self.net_offsets[1]) if (len(nets) == 2 and self.world > 1) else None   # fine slice
+        for q in self.pose_params:
+            self._param_off[id(q)] = off
+            off += q.numel()
+        _flatten_into(self.pose_params, self.flat, self.gflat, n_net)
+        self._side = torch.cuda.Stream(device=dev) if self._early else None
+        self._early_issued = False
         self.norms = torch.zeros(2 * (8 + 8 * 64), device=dev)    # two rn_clip_adam_step scratch areas
         # [lr, 1-b1^t, sqrt(1-b2^t)] for the nets and for the poses: read by the Adam kernel from device memory so
         # a captured CUDA graph can be replayed while the schedule advances
@@ -230,9 +244,23 @@ class Trainer:
         """Point the nets' backward kernels at the flat gradient buffer for the duration of a Trainer step only:
         outside it the models behave like ordinary modules (p.grad filled by autograd), so the reference-style
         train_step / train_step_with_poses on the same models keep working."""
-        for m, sl in zip(self.nets, self._sink_slices):
-            m._packed.grad_sink = sl if on else None
+        for m in self.nets:
+            m._packed.grad_sink = self._sinks[m] if on else None
             m._packed.sink_dirty = False
+            m._packed.on_grads_ready = None
+        self._early_issued = False
+        if on and self._early is not None:
+            self.model_fine._packed.on_grads_ready = self._allreduce_early
+
+    def _allreduce_early(self):
+        """Called by the fine network's backward as soon as its gradient slice is final: all-reduce it on a side stream,
+        underneath the coarse network's backward (captured into the step's CUDA graph like everything else)."""
+        lo, hi = self._early
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            torch.distributed.all_reduce(self.gflat[lo:hi], op=torch.distributed.ReduceOp.SUM, group=self.group)
+        self._early_issued = True
 
     def _neutral_hyper(self):
         """lr = 0 with unit bias corrections: warm-up / capture passes leave the parameters untouched (all-zero rows
@@ -243,15 +271,22 @@ class Trainer:
         self._check_aliasing()
         if self.n_pose:
             self.gflat[self.n_net:].zero_()                  # net gradients are overwritten by the kernels
-        off = 0
         for p in [q for ps in self.net_params for q in ps] + self.pose_params:
-            n = p.numel()
+            off, n = self._param_off[id(p)], p.numel()
             if p.grad is None or p.grad.data_ptr() != self.gflat.data_ptr() + 4 * off:
                 p.grad = self.gflat[off:off + n].view(p.shape)   # somebody called zero_grad(set_to_none=True)
-            off += n
 
     def _allreduce(self):
-        allreduce_mean_(self.gflat, self.world, self.group)
+        """SUM over ranks of whatever has not been reduced yet; the 1 / world of the mean is applied by the clip + Adam
+        kernel on load (`grad_scale`), not by another launch."""
+        if self.world <= 1:
+            return
+        if self._early_issued:
+            lo = self._early[1]
+            torch.distributed.all_reduce(self.gflat[lo:], op=torch.distributed.ReduceOp.SUM, group=self.group)
+            torch.cuda.current_stream().wait_stream(self._side)
+        else:
+            torch.distributed.all_reduce(self.gflat, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
     def _adam(self, lo: int, hi: int, groups: Sequence[int], max_norms: Sequence[float], hyper_slot: int, norm_slot: int):
         n = hi - lo
@@ -260,7 +295,7 @@ class Trainer:
         call("rn_clip_adam_step", self.flat[lo:hi].data_ptr(), self.gflat[lo:hi].data_ptr(), self.exp_avg[lo:hi].data_ptr(),
              self.exp_avg_sq[lo:hi].data_ptr(), n, offs, mx, len(max_norms), 0.0, float(self.betas[0]),
              float(self.betas[1]), float(self.eps), 1, self.norms[norm_slot:].data_ptr(),
-             self.hyper[hyper_slot:].data_ptr(), stream_ptr())
+             self.hyper[hyper_slot:].data_ptr(), 1.0 / self.world, stream_ptr())
 
     def _advance_schedule(self, optimize_poses: bool):
         """Host side of the optimiser schedule (train.py:405-411: lr * 0.1^(step/250k)); uploaded to the device
@@ -307,15 +342,14 @@ class Trainer:
         return loss.detach()
 
     # -- checkpointing (train.py:248-271, train_pose_opt.py:563-597: optimizer.state_dict() travels with the model) ------
-    def _adam_state(self, params: Sequence[nn.Parameter], lo: int, base_lr: float, steps: int) -> dict:
-        state, off = {}, lo
+    def _adam_state(self, params: Sequence[nn.Parameter], base_lr: float, steps: int) -> dict:
+        state = {}
         if steps > 0:
             for i, p in enumerate(params):
-                n = p.numel()
+                off, n = self._param_off[id(p)], p.numel()
                 state[i] = {"step": torch.tensor(float(steps)),
                             "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
                             "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
-                off += n
         group = {"lr": base_lr * (0.1 ** (steps / self.lr_decay_steps)), "betas": tuple(self.betas), "eps": self.eps,
                  "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
                  "differentiable": False, "fused": None, "decoupled_weight_decay": False, "initial_lr": base_lr,
@@ -328,16 +362,16 @@ class Trainer:
         checkpoint's `optimizer_state_dict` loads here and ours loads into `torch.optim.Adam`.  The models and the camera
         parameters are saved through their own `state_dict()` as in the reference."""
         net_params = [p for ps in self.net_params for p in ps]
-        out = {"optimizer_nerf": self._adam_state(net_params, 0, self.lr, self.iteration), "iteration": self.iteration,
+        out = {"optimizer_nerf": self._adam_state(net_params, self.lr, self.iteration), "iteration": self.iteration,
                "pose_steps": self.pose_steps}
         if self.n_pose:
-            out["optimizer_poses"] = self._adam_state(self.pose_params, self.n_net, self.pose_lr, self.pose_steps)
+            out["optimizer_poses"] = self._adam_state(self.pose_params, self.pose_lr, self.pose_steps)
         return out
 
-    def _load_adam_state(self, sd: dict, params: Sequence[nn.Parameter], lo: int) -> int:
-        off, steps = lo, 0
+    def _load_adam_state(self, sd: dict, params: Sequence[nn.Parameter]) -> int:
+        steps = 0
         for i, p in enumerate(params):
-            n = p.numel()
+            off, n = self._param_off[id(p)], p.numel()
             st = sd["state"].get(i, sd["state"].get(str(i)))
             if st is None:
                 self.exp_avg[off:off + n].zero_(); self.exp_avg_sq[off:off + n].zero_()
@@ -347,16 +381,15 @@ class Trainer:
                 self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
                 self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
                 steps = max(steps, int(float(st["step"])))
-            off += n
         return steps
 
     def load_state_dict(self, sd: dict) -> None:
         """Accepts `Trainer.state_dict()` or a dict holding `torch.optim.Adam.state_dict()`s under the same keys."""
         net_params = [p for ps in self.net_params for p in ps]
-        steps = self._load_adam_state(sd["optimizer_nerf"], net_params, 0)
+        steps = self._load_adam_state(sd["optimizer_nerf"], net_params)
         self.iteration = int(sd.get("iteration", steps))
         if self.n_pose and "optimizer_poses" in sd:
-            psteps = self._load_adam_state(sd["optimizer_poses"], self.pose_params, self.n_net)
+            psteps = self._load_adam_state(sd["optimizer_poses"], self.pose_params)
             self.pose_steps = int(sd.get("pose_steps", psteps))
         # schedule rows are rebuilt from the step counters on the next _advance_schedule; the pose row must survive a
         # clean-mode step, so seed the previous slot with it
@@ -369,12 +402,10 @@ class Trainer:
 
     def _check_aliasing(self):
         """Parameters must still be views of the flat buffer (model.to(), p.data = ... after construction detaches them)."""
-        off = 0
         for p in [q for ps in self.net_params for q in ps] + self.pose_params:
-            if p.data_ptr() != self.flat.data_ptr() + 4 * off:
+            if p.data_ptr() != self.flat.data_ptr() + 4 * self._param_off[id(p)]:
                 raise RuntimeError("a parameter no longer aliases the Trainer's flat buffer (was the model moved or "
                                    "re-assigned after the Trainer was built?); rebuild the Trainer")
-            off += p.numel()
 
     # -- public steps -----------------------------------------------------------------------------
     def _step_rays_body(self, rays_o, rays_d, target, optimise):

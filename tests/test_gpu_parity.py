@@ -612,7 +612,7 @@ def test_trainer_clean_step_matches_reference_semantics(rn, dev):
         d.mean().item(), d.max().item(), (d > 1e-4).float().mean().item())
     # parameters stay nn.Parameters with the reference's state_dict; views of the flat buffer
     assert set(mc.state_dict().keys()) == set(nc.state_dict().keys())
-    assert mc.pts_linears[0].weight.data_ptr() == tr.flat.data_ptr()
+    assert mf.pts_linears[0].weight.data_ptr() == tr.flat.data_ptr()      # flat layout: [fine | coarse | poses]
 
 
 def test_trainer_pose_step_matches_reference_semantics(rn, dev):
@@ -801,6 +801,67 @@ def test_chained_data_gradients_equal_per_layer(rn, dev):
             assert outs[("grad", 1)].abs().max().item() > 0
     finally:
         lib.rn_set_flag(3, 1)
+
+
+def test_trainer_state_dict_and_module_semantics(rn, dev):
+    """(a) the Trainer's optimiser state round-trips in torch.optim.Adam format (train.py:248-271 checkpoints
+    carry optimizer.state_dict()) and a restored Trainer continues bit-identically; (b) the models stay ordinary modules
+    outside a Trainer step -- the reference-style train_step on the same models still fills p.grad and trains, and a
+    backward that passes through a net twice (chunked training render) accumulates."""
+    data, ds, sampler, pb = _scene_batch(rn, dev, 256)
+    with torch.no_grad():
+        ro, rd = sampler.get_rays_for_batch(pb, data.poses)
+    cfg = rn.RenderConfig()
+    mc, mf = _two_nets(rn, dev)
+    tr = rn.Trainer(mc, mf, cfg, lr=5e-4, lr_decay_steps=1e30)
+    for it in range(3):
+        torch.manual_seed(it)
+        tr.step_rays(ro, rd, pb.target_rgb)
+    # (a) checkpoint after 3 steps: model state_dicts + Trainer.state_dict()
+    sd = tr.state_dict()
+    wc3 = {k: v.clone() for k, v in mc.state_dict().items()}
+    wf3 = {k: v.clone() for k, v in mf.state_dict().items()}
+    ref_opt = torch.optim.Adam(list(mc.parameters()) + list(mf.parameters()), lr=5e-4)
+    ref_opt.load_state_dict(sd["optimizer_nerf"])                     # torch accepts it as its own format
+    st = ref_opt.state[mc.pts_linears[0].weight]
+    assert float(st["step"]) == 3.0 and st["exp_avg"].shape == mc.pts_linears[0].weight.shape and st["exp_avg"].abs().sum() > 0
+    torch.manual_seed(3)
+    la = tr.step_rays(ro, rd, pb.target_rgb).clone()
+    mc2, mf2 = _two_nets(rn, dev)
+    mc2.load_state_dict(wc3); mf2.load_state_dict(wf3)
+    tr2 = rn.Trainer(mc2, mf2, cfg, lr=5e-4, lr_decay_steps=1e30)
+    tr2.load_state_dict(sd)
+    assert tr2.iteration == 3
+    torch.manual_seed(3)
+    lb = tr2.step_rays(ro, rd, pb.target_rgb)
+    assert torch.equal(la, lb)
+    for a, b in zip(list(mc.parameters()) + list(mf.parameters()), list(mc2.parameters()) + list(mf2.parameters())):
+        assert torch.equal(a, b)                                      # the restored run continued bit-identically
+    # a torch.optim.Adam state_dict (what a reference checkpoint holds) loads too
+    tr2.load_state_dict({"optimizer_nerf": ref_opt.state_dict()})
+    assert tr2.iteration == 3
+    # (b) reference-style step on the same models after the Trainer was built
+    renderer = rn.NeRFRenderer(mc, mf, cfg)
+    opt = torch.optim.Adam(renderer.parameters(), lr=5e-4)
+    before = mf.pts_linears[3].weight.detach().clone()
+    torch.manual_seed(7)
+    rn.train_step(renderer, opt, {"rays_o": ro, "rays_d": rd, "target_rgb": pb.target_rgb})
+    assert mf.pts_linears[3].weight.grad is not None and mf.pts_linears[3].weight.grad.abs().sum().item() > 0
+    assert (mf.pts_linears[3].weight.detach() - before).abs().max().item() > 0
+    # chunked training render: two passes through each net accumulate into p.grad
+    opt.zero_grad()
+    torch.manual_seed(8)
+    out = renderer(ro, rd, chunk_size=128, is_train=True)
+    ((out["rgb_fine"] - pb.target_rgb) ** 2).mean().backward()
+    g_chunked = mf.pts_linears[3].weight.grad.clone()
+    opt.zero_grad()
+    torch.manual_seed(8)                     # the chunked call drew rand(128, 64), rand(128, 128) per chunk, in this order
+    tr0, u0 = torch.rand(128, 64, device=dev), torch.rand(128, 128, device=dev)
+    tr1, u1 = torch.rand(128, 64, device=dev), torch.rand(128, 128, device=dev)
+    o0 = rn.render_rays(mc, mf, ro[:128], rd[:128], cfg, is_train=True, t_rand=tr0, u=u0)
+    o1 = rn.render_rays(mc, mf, ro[128:], rd[128:], cfg, is_train=True, t_rand=tr1, u=u1)
+    ((torch.cat([o0["rgb_fine"], o1["rgb_fine"]]) - pb.target_rgb) ** 2).mean().backward()
+    assert torch.allclose(g_chunked, mf.pts_linears[3].weight.grad, rtol=1e-5, atol=1e-9)
 
 
 def test_trainer_cuda_graph_step(rn, dev):
