@@ -170,6 +170,11 @@ int rn_composite_bwd(const float* rgb, const float* sigma, const float* raw4, co
  * g_rgb_map = 2*(rgb_map-target)/(3B) * loss_scale.  loss_out is accumulated (caller zero-fills). */
 int rn_mse_loss_fwd_bwd(const float* rgb_map, const float* target, int64_t B, float loss_scale,
                         float* loss_out /*[1]*/, float* g_rgb_map /*[B,3]*/, rn_stream_t stream);
+/* The whole training loss of train.py:88-99 / train_pose_opt.py:355-375 in one launch: loss_out[0] = mse(coarse) +
+ * mse(fine), [1] = coarse, [2] = fine (written, not accumulated); g_* = 2*(rgb-target)/(3B).  rgb_fine / g_fine may both
+ * be NULL (no fine network). */
+int rn_mse2_loss_fwd_bwd(const float* rgb_coarse, const float* rgb_fine, const float* target, int64_t B,
+                         float* loss_out /*[3]*/, float* g_coarse /*[B,3]*/, float* g_fine /*[B,3] or NULL*/, rn_stream_t stream);
 
 /* ---- NeRF MLP: model.py:20-196 (PE fused in; bf16 tcgen05 GEMMs, fp32 accumulate) ---- */
 size_t rn_mlp_packed_weight_bytes(void);

@@ -243,6 +243,27 @@ def positional_encoding(x: np.ndarray, num_freqs: int) -> np.ndarray:
     return np.concatenate(out, -1).astype(F32)
 
 
+def positional_encoding_fast(x: np.ndarray, num_freqs: int) -> np.ndarray:
+    """The features as the CUDA path builds its bf16 operand (csrc/pe.cuh): accurate sin/cos at k = 0, 3, 6, 9 and two
+    angle doublings after each -- sin 2a = (s + s) c, cos 2a = 1 - (s + s) s, every operation rounded to fp32 in this
+    order.  Within 5e-7 of `positional_encoding`; used by the `emulate_bf16` mode only."""
+    x = _f32(x)
+    out = [x]
+    s = c = None
+    for k in range(num_freqs):
+        if k % 3 == 0:
+            a = (F32(2.0 ** k) * x).astype(F32)
+            s, c = np.sin(a).astype(F32), np.cos(a).astype(F32)
+        else:
+            s2 = (s + s).astype(F32)
+            cn = (F32(1.0) - (s2 * s).astype(F32)).astype(F32)
+            s = (s2 * c).astype(F32)
+            c = cn
+        out.append(s)
+        out.append(c)
+    return np.concatenate(out, -1).astype(F32)
+
+
 def positional_encoding_backward(x: np.ndarray, num_freqs: int, g: np.ndarray) -> np.ndarray:
     x, g = _f32(x), _f32(g)
     C = x.shape[-1]
@@ -340,7 +361,8 @@ def nerf_forward(params: Dict[str, np.ndarray], x, d, cfg: Optional[ModelConfig]
     rr = _rounders(emulate_bf16)
     rW, rA, rE = rr["w"], rr["act"], rr["enc"]
     x = _f32(x)
-    x_enc = rE(positional_encoding(x, cfg.pos_freqs))
+    pe = positional_encoding_fast if (emulate_bf16 and BF16_POINTS["enc"]) else positional_encoding
+    x_enc = rE(pe(x, cfg.pos_freqs))
     h = x_enc
     cache = {"x": x, "x_enc": x_enc, "ins": [], "pre": [], "emulate": emulate_bf16}
     for i in range(cfg.num_hidden_layers):
@@ -358,7 +380,7 @@ def nerf_forward(params: Dict[str, np.ndarray], x, d, cfg: Optional[ModelConfig]
         if d is None:
             raise ValueError("reference crashes for d=None with use_view_dirs (model.py:187-193)")
         d = _f32(d)
-        d_enc = rE(positional_encoding(d, cfg.dir_freqs))
+        d_enc = rE(pe(d, cfg.dir_freqs))
         hc_in = np.concatenate([feats, d_enc], -1)
     else:
         d_enc, hc_in = None, feats

@@ -58,6 +58,7 @@ _SIGS = {
     "rn_composite_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "rn_composite_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rn_mse_loss_fwd_bwd": (c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
+    "rn_mse2_loss_fwd_bwd": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P]),
     "rn_mlp_packed_weight_bytes": (c_size_t, []),
     "rn_mlp_pack_weights": (c_int, [POINTER(c_void_p), _P, _P]),
     "rn_mlp_workspace_bytes": (c_size_t, [c_int64, c_int]),

@@ -40,7 +40,7 @@ void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
 
 constexpr int kPairThreads = 608;         // 19 warps
-constexpr int kPairThreadsPE = 672;       // + two positional-encoding warps, one per tile slot (inference, PE fused)
+constexpr int kPairThreadsPE = 640;       // + one warp: with the (idle in inference) store warp, two encoder warps, one per tile slot
 constexpr int kPairMaxLayers = 12;
 constexpr int kPairMaxChunks = 8;
 constexpr int kChunkBytes = 16384;              // [128 rows][64 bf16], SWIZZLE_128B
@@ -490,7 +490,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
         }
       }
     }
-  } else if (warp == 18) {
+  } else if (warp == 18 && !PE) {
     // ---------------- store warp (training): activation tiles -> global for the backward pass ----------------
     if (TRAIN && lane == 0) {
       uint32_t it0 = 0, it1 = 0;
@@ -512,9 +512,10 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
       }
       tma_store_wait_all0();
     }
-  } else if (PE && warp >= 19) {
+  } else if (PE && warp >= 18) {
     // ---------------- encoder warps (inference): x_enc of this CTA's 128 rows, straight into the side buffer ----------------
-    // One warp per tile slot (warp 19 <-> slot 0, warp 20 <-> slot 1): a tile costs one warp ~11,000 cycles and both
+    // One warp per tile slot (warp 18, the store warp of the training kernel, <-> slot 0; warp 19 <-> slot 1; 640 threads
+    // keep the 96-register budget -- at 672 ptxas sizes for 768 and squeezes the epilogue into 80): a tile costs one warp ~11,000 cycles and both
     // slots' buffers come free within one layer of each other, so a single warp encoding them back to back delivered the
     // second one late (first build: render 1.5 % SLOWER than with the separate encode kernel, profiles/r02_pe_fused.md).
     // Same barrier protocol as the TMA-loaded side chunk: wait until layer 5's MMAs of the previous tile in this slot have
@@ -522,7 +523,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     // (fence.proxy.async), arrive on the leader's aux_full (count 2: one per CTA).  The buffer is free from layer 5 on
     // (the direction term needs no K chunk any more), so the next group's tile is encoded under layers 6-9.
     const uint32_t aux_full_leader = mapa_u32(smem_u32(aux_full), 0);
-    const int slot = warp - 19;
+    const int slot = warp - 18;
     uint32_t j = 0;
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       if (slot >= min(2, p.n_ptiles - grp * 2)) continue;

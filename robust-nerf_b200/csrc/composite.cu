@@ -370,6 +370,37 @@ mse_kernel(const float* __restrict__ rgb_map, const float* __restrict__ target, 
   }
 }
 
+// The training loss of train.py:88-99 in ONE launch: loss = mean((rgb_coarse - t)^2) [+ mean((rgb_fine - t)^2)], written
+// (not accumulated) as out[0] = total, out[1] = coarse, out[2] = fine, with both gradients 2 (rgb - t) / (3B).  One CTA,
+// fixed reduction order (deterministic).  Replaces two mse_kernel launches, two zero fills, an add and two multiplies.
+__global__ void __launch_bounds__(1024)
+mse2_kernel(const float* __restrict__ rgb_c, const float* __restrict__ rgb_f, const float* __restrict__ target, int64_t n,
+            float* __restrict__ out, float* __restrict__ g_c, float* __restrict__ g_f) {
+  __shared__ float red[2][32];
+  float ac = 0.f, af = 0.f;
+  const float inv = 1.0f / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const float t = target[i];
+    const float dc = rgb_c[i] - t;
+    ac = fmaf(dc, dc, ac);
+    g_c[i] = 2.0f * dc * inv;
+    if (rgb_f) {
+      const float df = rgb_f[i] - t;
+      af = fmaf(df, df, af);
+      g_f[i] = 2.0f * df * inv;
+    }
+  }
+  ac = warp_sum(ac); af = warp_sum(af);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ac; red[1][threadIdx.x >> 5] = af; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tc = 0.f, tf = 0.f;
+    for (int w = 0; w < 32; ++w) { tc += red[0][w]; tf += red[1][w]; }
+    tc *= inv; tf *= inv;
+    out[0] = tc + tf; out[1] = tc; out[2] = tf;
+  }
+}
+
 template <bool RAW>
 static int launch_bwd(int rounds, dim3 grid, cudaStream_t st, const float* rgb, const float* sigma, const float4* raw4,
                       const float* z, const float* rd, const float* noise, int64_t B, int S, int white, const float* g_map,
@@ -450,6 +481,14 @@ int rn_composite_bwd(const float* rgb, const float* sigma, const float* raw4, co
     rc = launch_bwd<false>(rounds, dim3(grid), (cudaStream_t)stream, rgb, sigma, nullptr, z, rd, noise, B, S, white, g_map,
                            g_depth, g_acc, g_w, d_rgb, d_sigma, nullptr, d_rd);
   if (rc != RN_OK) return rc;
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int rn_mse2_loss_fwd_bwd(const float* rgb_coarse, const float* rgb_fine, const float* target, int64_t B, float* loss_out,
+                         float* g_coarse, float* g_fine, rn_stream_t stream) {
+  RN_REQUIRE(rgb_coarse && target && loss_out && g_coarse && B > 0 && ((rgb_fine == nullptr) == (g_fine == nullptr)));
+  mse2_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rgb_coarse, rgb_fine, target, B * 3, loss_out, g_coarse, g_fine);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

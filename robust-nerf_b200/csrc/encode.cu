@@ -54,7 +54,7 @@ encode_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, int
   for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
     float feat[64];
     const float x[3] = {__ldcs(pts + m * 3), __ldcs(pts + m * 3 + 1), __ldcs(pts + m * 3 + 2)};
-    encode3<kPosFreqs>(x, feat);
+    pe_features_fast<kPosFreqs>(x, feat);       // csrc/pe.cuh: four accurate sincosf per coordinate + angle doubling
     feat[63] = 0.f;
     // one full 32-byte sector per store instruction (rows are 32-byte aligned: ld is a multiple of 16 elements)
     __nv_bfloat16* dst = XC + m * ldx;
@@ -64,7 +64,7 @@ encode_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, int
       const int64_t r = m / group;
       const float d[3] = {__ldg(dirs + r * 3), __ldg(dirs + r * 3 + 1), __ldg(dirs + r * 3 + 2)};
       float df[32];
-      encode3<kDirFreqs>(d, df);
+      pe_features_fast<kDirFreqs>(d, df);
 #pragma unroll
       for (int i = 27; i < 32; ++i) df[i] = 0.f;
       __nv_bfloat16* dd = FD + m * ldf + 256;

@@ -297,6 +297,19 @@ def mse_loss_and_grad(rgb_map, target, loss_out, scale=1.0, want_grad=True):
     return g
 
 
+def mse2_loss_and_grads(rgb_coarse, rgb_fine, target):
+    """loss[0] = mse(coarse) + mse(fine), loss[1] = coarse, loss[2] = fine and both gradients w.r.t. the rendered colours,
+    one launch (train.py:88-99).  rgb_fine may be None."""
+    rc, tg = _f32(rgb_coarse.detach(), "rgb_coarse"), _f32(target, "target")
+    rf = None if rgb_fine is None else _f32(rgb_fine.detach(), "rgb_fine")
+    B = rc.shape[0]
+    loss = _empty((3,), rc)
+    g_c = _empty((B, 3), rc)
+    g_f = None if rf is None else _empty((B, 3), rc)
+    call("rn_mse2_loss_fwd_bwd", ptr(rc), ptr(rf), ptr(tg), B, ptr(loss), ptr(g_c), ptr(g_f), stream_ptr())
+    return loss, g_c, g_f
+
+
 # --------------------------------------------------------------------------------------------
 # NeRF MLP (model.py:145-196)
 # --------------------------------------------------------------------------------------------

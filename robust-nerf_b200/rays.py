@@ -44,12 +44,23 @@ def get_rays_batch(H: int, W: int, focal: float, c2w_batch: torch.Tensor) -> Tup
     return torch.stack([o for o, _ in outs], 0), torch.stack([d for _, d in outs], 0)
 
 
+_Z_BASE_CACHE = {}
+
+
 def _z_base(near, far, num_samples, lindisp, device):
-    # rays.py:185-192, evaluated with the same torch ops on the same device
-    t_vals = torch.linspace(0.0, 1.0, num_samples, device=device)
-    if lindisp:
-        return 1.0 / (1.0 / near * (1.0 - t_vals) + 1.0 / far * t_vals)
-    return near * (1.0 - t_vals) + far * t_vals
+    """rays.py:185-192, evaluated with the same torch ops on the same device; constant per (near, far, N, lindisp, device),
+    so it is built once (four launches) instead of on every call."""
+    key = (float(near), float(far), int(num_samples), bool(lindisp), str(device))
+    z = _Z_BASE_CACHE.get(key)
+    if z is None:
+        t_vals = torch.linspace(0.0, 1.0, num_samples, device=device)
+        if lindisp:
+            z = 1.0 / (1.0 / near * (1.0 - t_vals) + 1.0 / far * t_vals)
+        else:
+            z = near * (1.0 - t_vals) + far * t_vals
+        if not torch.cuda.is_current_stream_capturing():
+            _Z_BASE_CACHE[key] = z
+    return z
 
 
 def sample_along_rays(rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float, num_samples: int,

@@ -334,12 +334,22 @@ class Trainer:
             m._packed.key = None          # parameters changed under the bf16 cache
 
     def _backward(self, outputs, target, extra_loss=None):
-        loss_c, loss_f = _losses(outputs, target)
-        loss = loss_c if loss_f is None else loss_c + loss_f
+        """Loss and the start of the backward pass without an autograd node for the loss: one kernel produces
+        mse(coarse) + mse(fine) and both gradients w.r.t. the rendered colours (train.py:88-99), which are fed straight
+        into autograd.backward on the two rgb maps (the optional pose regulariser, a scalar, rides along)."""
+        rgb_c, rgb_f = outputs["rgb_coarse"], outputs.get("rgb_fine")
+        loss3, g_c, g_f = ops.mse2_loss_and_grads(rgb_c, rgb_f, target)
+        tensors, grads = [rgb_c], [g_c]
+        if rgb_f is not None:
+            tensors.insert(0, rgb_f)             # fine first: its gradient slice is then final first (early all-reduce)
+            grads.insert(0, g_f)
+        loss = loss3[0]
         if extra_loss is not None:
-            loss = loss + extra_loss
-        loss.backward()
-        return loss.detach()
+            tensors.append(extra_loss)
+            grads.append(torch.ones_like(extra_loss))
+            loss = loss + extra_loss.detach()
+        torch.autograd.backward(tensors, grads)
+        return loss
 
     # -- checkpointing (train.py:248-271, train_pose_opt.py:563-597: optimizer.state_dict() travels with the model) ------
     def _adam_state(self, params: Sequence[nn.Parameter], base_lr: float, steps: int) -> dict:

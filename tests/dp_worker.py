@@ -48,6 +48,15 @@ def main():
         g_sum += tr1.gflat
     grad_diff = float((g_dp - g_sum).abs().max())
     grad_scale = float(g_sum.abs().max())
+    nf = tr.net_offsets[1]
+    diff_fine, diff_coarse = float((g_dp[:nf] - g_sum[:nf]).abs().max()), float((g_dp[nf:] - g_sum[nf:]).abs().max())
+    # the same gradient with the early (side-stream) all-reduce switched off: one all-reduce of the whole buffer
+    early = tr._early
+    tr._early = None
+    torch.manual_seed(100 + rank)
+    tr.step_rays(shard(ro, rank), shard(rd, rank), shard(tgt, rank), optimise=False)
+    diff_noearly = float((tr.gflat - g_sum).abs().max())
+    tr._early = early
     # ---- 2. optimised steps, eager and graph-replayed: replicas stay bit-identical ----
     for it in range(3):
         torch.manual_seed(200 + 10 * it + rank)
@@ -63,6 +72,7 @@ def main():
     moved = float((tr.flat - tr1.flat).abs().max())       # tr1 never stepped: the parameters did move
     if rank == 0:
         print(json.dumps({"world": world, "grad_max_abs_diff_vs_local_sum": grad_diff, "grad_max_abs": grad_scale,
+                          "diff_fine_slice": diff_fine, "diff_coarse_slice": diff_coarse, "diff_without_early_allreduce": diff_noearly,
                           "replica_max_abs_diff": float(d.item()), "params_moved": moved}), flush=True)
     tr._graphs.clear()
     torch.cuda.synchronize()
