@@ -244,23 +244,26 @@ def positional_encoding(x: np.ndarray, num_freqs: int) -> np.ndarray:
 
 
 def positional_encoding_fast(x: np.ndarray, num_freqs: int) -> np.ndarray:
-    """The features as the CUDA path builds its bf16 operand (csrc/pe.cuh): accurate sin/cos at k = 0, 3, 6, 9 and two
-    angle doublings after each -- sin 2a = (s + s) c, cos 2a = 1 - (s + s) s, every operation rounded to fp32 in this
-    order.  Within 5e-7 of `positional_encoding`; used by the `emulate_bf16` mode only."""
+    """The features as the CUDA path builds its bf16 operand (csrc/pe.cuh): the argument is reduced once, in turns --
+    t = x / (2 pi) as a two-float value (FMA residual), r_k = frac(2^k t_hi) + 2^k t_lo, angle = 2 pi r_k in fp32 -- and
+    the hardware's approximate sin / cos of the reduced angle (absolute error 2^-21.4) is modelled by the exact one.
+    Within 8e-7 of `positional_encoding` at every frequency; used by the `emulate_bf16` mode only."""
     x = _f32(x)
+    c = 1.0 / (2.0 * np.pi)
+    c_hi = F32(c)
+    c_lo = F32(c - float(c_hi))
+    t_hi = (x * c_hi).astype(F32)
+    resid = (x.astype(np.float64) * float(c_hi) - t_hi.astype(np.float64)).astype(F32)      # fma(x, c_hi, -t_hi): exact
+    t_lo = (x.astype(np.float64) * float(c_lo) + resid.astype(np.float64)).astype(F32)      # fma(x, c_lo, resid)
     out = [x]
-    s = c = None
     for k in range(num_freqs):
-        if k % 3 == 0:
-            a = (F32(2.0 ** k) * x).astype(F32)
-            s, c = np.sin(a).astype(F32), np.cos(a).astype(F32)
-        else:
-            s2 = (s + s).astype(F32)
-            cn = (F32(1.0) - (s2 * s).astype(F32)).astype(F32)
-            s = (s2 * c).astype(F32)
-            c = cn
-        out.append(s)
-        out.append(c)
+        f = F32(2.0 ** k)
+        y = (t_hi * f).astype(F32)
+        d = (y - np.rint(y)).astype(F32)
+        r = (t_lo.astype(np.float64) * float(f) + d.astype(np.float64)).astype(F32)          # fma(t_lo, f, d)
+        ang = (r * F32(6.2831855)).astype(F32)
+        out.append(np.sin(ang.astype(np.float64)).astype(F32))
+        out.append(np.cos(ang.astype(np.float64)).astype(F32))
     return np.concatenate(out, -1).astype(F32)
 
 

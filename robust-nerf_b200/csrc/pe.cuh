@@ -2,12 +2,14 @@
 // sin(2^k xyz), cos(2^k xyz); no pi factor), shared by the in-kernel encoder of the forward chain (chain_pair.cu) and
 // the per-ray view-direction projection (encode.cu).
 //
-// The features feed a bf16 operand (8 mantissa bits), so they are produced with FOUR accurate sincosf per coordinate
-// (k = 0, 3, 6, 9: Cody-Waite range reduction, arguments reach 3,000 rad) and two angle doublings after each
-//     sin 2a = 2 sin a cos a,   cos 2a = 1 - 2 sin^2 a
-// instead of ten accurate calls.  Absolute error of the doubled values: <= 5e-7 (measured against float64 on 200,000
-// points in [-6, 6]: profiles/r02_pe_recurrence.md), i.e. 1e-4 of the bf16 rounding step; one feature in 10^4 lands on
-// the neighbouring bf16 value.  The fp32 PositionalEncoding.forward of the API (posenc_fwd_kernel) keeps ten accurate calls.
+// The features feed a bf16 operand (8 mantissa bits), so instead of ten accurate sincosf per coordinate (Cody-Waite range
+// reduction of arguments that reach 3,000 rad: ~2,000 instructions per point) the argument is reduced ONCE, in turns:
+//     t = x / (2 pi) as a two-float value (t_hi + t_lo, FMA residual), so that 2^k t is exact scaling;
+//     r_k = frac(2^k t_hi) + 2^k t_lo  in [-0.5, 0.5];   sin/cos(2^k x) = sin/cos(2 pi r_k)  through MUFU (sin.approx /
+//     cos.approx, absolute error 2^-21.4 on [-pi, pi]).
+// Measured against float64 (profiles/r02_pe_recurrence.md): absolute error <= 8e-7 at EVERY frequency, i.e. 2e-4 of the
+// bf16 rounding step; 3.5 features in 10^4 land on the neighbouring bf16 value.  ~10 instructions per (frequency,
+// coordinate).  The fp32 PositionalEncoding.forward of the API (posenc_fwd_kernel) keeps the accurate sincosf.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,22 +19,22 @@ namespace rn {
 // feat[0 .. 3 + 6L) for one 3-vector
 template <int L>
 __device__ __forceinline__ void pe_features_fast(const float x[3], float* feat) {
+  constexpr float kInv2PiHi = 0.15915494f;                 // fl32(1 / (2 pi))
+  constexpr float kInv2PiLo = 6.4206382e-09f;              // fl32(1 / (2 pi) - kInv2PiHi)
+  constexpr float k2Pi = 6.2831855f;
   feat[0] = x[0]; feat[1] = x[1]; feat[2] = x[2];
-  float s[3], c[3];
 #pragma unroll
-  for (int k = 0; k < L; ++k) {
+  for (int a = 0; a < 3; ++a) {
+    const float t_hi = __fmul_rn(x[a], kInv2PiHi);
+    const float t_lo = __fmaf_rn(x[a], kInv2PiLo, __fmaf_rn(x[a], kInv2PiHi, -t_hi));
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (k % 3 == 0) {
-        sincosf(__fmul_rn((float)(1 << k), x[a]), &s[a], &c[a]);
-      } else {
-        const float s2 = __fadd_rn(s[a], s[a]);
-        const float cn = __fsub_rn(1.0f, __fmul_rn(s2, s[a]));
-        s[a] = __fmul_rn(s2, c[a]);
-        c[a] = cn;
-      }
-      feat[3 + 6 * k + a] = s[a];
-      feat[3 + 6 * k + 3 + a] = c[a];
+    for (int k = 0; k < L; ++k) {
+      const float f = (float)(1 << k);
+      const float y = __fmul_rn(t_hi, f);                  // exact
+      const float r = __fmaf_rn(t_lo, f, __fsub_rn(y, rintf(y)));
+      const float ang = __fmul_rn(r, k2Pi);
+      feat[3 + 6 * k + a] = __sinf(ang);
+      feat[3 + 6 * k + 3 + a] = __cosf(ang);
     }
   }
 }

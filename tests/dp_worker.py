@@ -57,6 +57,30 @@ def main():
     tr.step_rays(shard(ro, rank), shard(rd, rank), shard(tgt, rank), optimise=False)
     diff_noearly = float((tr.gflat - g_sum).abs().max())
     tr._early = early
+    # diagnostics of the early path
+    diag = {}
+    local = None
+    for name in ("sync_before", "main_stream"):
+        orig = tr._allreduce_early
+
+        def hook(name=name):
+            lo, hi = tr._early
+            if name == "sync_before":
+                torch.cuda.synchronize()
+                orig()
+            else:
+                dist.all_reduce(tr.gflat[lo:hi], op=dist.ReduceOp.SUM)
+                tr._early_issued = True
+                tr._side.wait_stream(torch.cuda.current_stream())
+        tr._allreduce_early = hook
+        torch.manual_seed(100 + rank)
+        tr.step_rays(shard(ro, rank), shard(rd, rank), shard(tgt, rank), optimise=False)
+        d_ = (tr.gflat - g_sum).abs()
+        diag[name] = float(d_.max())
+        tr._allreduce_early = orig
+    bad = (g_dp - g_sum).abs() > 0
+    diag["n_bad"] = int(bad.sum()); diag["first_bad"] = int(torch.nonzero(bad)[0]) if bad.any() else -1
+    diag["last_bad"] = int(torch.nonzero(bad)[-1]) if bad.any() else -1
     # ---- 2. optimised steps, eager and graph-replayed: replicas stay bit-identical ----
     for it in range(3):
         torch.manual_seed(200 + 10 * it + rank)
@@ -72,7 +96,7 @@ def main():
     moved = float((tr.flat - tr1.flat).abs().max())       # tr1 never stepped: the parameters did move
     if rank == 0:
         print(json.dumps({"world": world, "grad_max_abs_diff_vs_local_sum": grad_diff, "grad_max_abs": grad_scale,
-                          "diff_fine_slice": diff_fine, "diff_coarse_slice": diff_coarse, "diff_without_early_allreduce": diff_noearly,
+                          "diff_fine_slice": diff_fine, "diff_coarse_slice": diff_coarse, "diff_without_early_allreduce": diff_noearly, "diag": diag,
                           "replica_max_abs_diff": float(d.item()), "params_moved": moved}), flush=True)
     tr._graphs.clear()
     torch.cuda.synchronize()
