@@ -248,9 +248,10 @@ class Trainer:
             m._packed.grad_sink = self._sinks[m] if on else None
             m._packed.sink_dirty = False
             m._packed.on_grads_ready = None
-        self._early_issued = False
-        if on and self._early is not None:
-            self.model_fine._packed.on_grads_ready = self._allreduce_early
+        if on:
+            self._early_issued = False           # (cleared again by _allreduce, which runs after the sinks are disarmed)
+            if self._early is not None:
+                self.model_fine._packed.on_grads_ready = self._allreduce_early
 
     def _allreduce_early(self):
         """Called by the fine network's backward as soon as its gradient slice is final: all-reduce it on a side stream,
@@ -285,6 +286,7 @@ class Trainer:
             lo = self._early[1]
             torch.distributed.all_reduce(self.gflat[lo:], op=torch.distributed.ReduceOp.SUM, group=self.group)
             torch.cuda.current_stream().wait_stream(self._side)
+            self._early_issued = False
         else:
             torch.distributed.all_reduce(self.gflat, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
