@@ -531,21 +531,35 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
       ++j;
       uint8_t* tile = s_aux + slot * kAuxBytes;
       const int64_t row0 = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128;
+      // Deliberately ROLLED (one frequency per iteration, 2-byte stores): the unrolled version (63 features in registers,
+      // eight 16-byte stores) is ~1,500 instructions of straight-line code that shares the instruction cache of its SM
+      // partition with the epilogue loop -- the stage that paces the kernel (profiles/r02_pe_fused.md).
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
-        const int r = i * 32 + lane;                 // lanes of a quarter warp write eight different 16-byte columns
+        const int r = i * 32 + lane;                 // lanes of a quarter warp hit eight different 16-byte columns
         const int64_t gr = row0 + r;
         float x[3] = {0.f, 0.f, 0.f};
         if (gr < p.m_rows) { x[0] = __ldg(p.pts + gr * 3); x[1] = __ldg(p.pts + gr * 3 + 1); x[2] = __ldg(p.pts + gr * 3 + 2); }
-        float feat[64];
-        pe_features_fast<kPosFreqs>(x, feat);
-        feat[63] = 0.f;
         uint8_t* rowp = tile + r * 128;
+        const int sw = r & 7;
+        auto put = [&](int f, float v) {             // feature f of this row -> its swizzled 2-byte slot
+          *reinterpret_cast<__nv_bfloat16*>(rowp + (((f >> 3) ^ sw) << 4) + ((f & 7) << 1)) = __float2bfloat16_rn(v);
+        };
+        float t_hi[3], t_lo[3];
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) =
-              make_uint4(pe_pack_bf16(feat[8 * c], feat[8 * c + 1]), pe_pack_bf16(feat[8 * c + 2], feat[8 * c + 3]),
-                         pe_pack_bf16(feat[8 * c + 4], feat[8 * c + 5]), pe_pack_bf16(feat[8 * c + 6], feat[8 * c + 7]));
+        for (int a = 0; a < 3; ++a) { put(a, x[a]); pe_turns(x[a], t_hi[a], t_lo[a]); }
+        put(63, 0.f);
+#pragma unroll 1
+        for (int k = 0; k < kPosFreqs; ++k) {
+          const float f = (float)(1 << k);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            float sn, cs;
+            pe_sincos_turns(t_hi[a], t_lo[a], f, sn, cs);
+            put(3 + 6 * k + a, sn);
+            put(6 + 6 * k + a, cs);
+          }
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();

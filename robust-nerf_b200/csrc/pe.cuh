@@ -16,26 +16,33 @@
 
 namespace rn {
 
+// t = x / (2 pi) as a two-float value
+__device__ __forceinline__ void pe_turns(float x, float& t_hi, float& t_lo) {
+  constexpr float kInv2PiHi = 0.15915494f;                 // fl32(1 / (2 pi))
+  constexpr float kInv2PiLo = 6.4206382e-09f;              // fl32(1 / (2 pi) - kInv2PiHi)
+  t_hi = __fmul_rn(x, kInv2PiHi);
+  t_lo = __fmaf_rn(x, kInv2PiLo, __fmaf_rn(x, kInv2PiHi, -t_hi));
+}
+// sin / cos of f * x for f = 2^k, from the turns of x
+__device__ __forceinline__ void pe_sincos_turns(float t_hi, float t_lo, float f, float& sn, float& cs) {
+  constexpr float k2Pi = 6.2831855f;
+  const float y = __fmul_rn(t_hi, f);                      // exact
+  const float r = __fmaf_rn(t_lo, f, __fsub_rn(y, rintf(y)));
+  const float ang = __fmul_rn(r, k2Pi);
+  sn = __sinf(ang);
+  cs = __cosf(ang);
+}
+
 // feat[0 .. 3 + 6L) for one 3-vector
 template <int L>
 __device__ __forceinline__ void pe_features_fast(const float x[3], float* feat) {
-  constexpr float kInv2PiHi = 0.15915494f;                 // fl32(1 / (2 pi))
-  constexpr float kInv2PiLo = 6.4206382e-09f;              // fl32(1 / (2 pi) - kInv2PiHi)
-  constexpr float k2Pi = 6.2831855f;
   feat[0] = x[0]; feat[1] = x[1]; feat[2] = x[2];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float t_hi = __fmul_rn(x[a], kInv2PiHi);
-    const float t_lo = __fmaf_rn(x[a], kInv2PiLo, __fmaf_rn(x[a], kInv2PiHi, -t_hi));
+    float t_hi, t_lo;
+    pe_turns(x[a], t_hi, t_lo);
 #pragma unroll
-    for (int k = 0; k < L; ++k) {
-      const float f = (float)(1 << k);
-      const float y = __fmul_rn(t_hi, f);                  // exact
-      const float r = __fmaf_rn(t_lo, f, __fsub_rn(y, rintf(y)));
-      const float ang = __fmul_rn(r, k2Pi);
-      feat[3 + 6 * k + a] = __sinf(ang);
-      feat[3 + 6 * k + 3 + a] = __cosf(ang);
-    }
+    for (int k = 0; k < L; ++k) pe_sincos_turns(t_hi, t_lo, (float)(1 << k), feat[3 + 6 * k + a], feat[3 + 6 * k + 3 + a]);
   }
 }
 

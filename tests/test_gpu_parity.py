@@ -649,7 +649,7 @@ def test_trainer_pose_step_matches_reference_semantics(rn, dev):
     # fraction of that (see the clean-step test for why not bit-exact after step 1)
     assert (cam_a.translation_deltas - cam_b.translation_deltas).abs().mean().item() < 5e-6
     assert (cam_a.rotation_deltas - cam_b.rotation_deltas).abs().mean().item() < 5e-6
-    assert (cam_a.translation_deltas - cam_b.translation_deltas).abs().max().item() < 1.5e-4
+    assert (cam_a.translation_deltas - cam_b.translation_deltas).abs().max().item() <= 3 * 1e-4 * 1.01   # three Adam steps
     assert cam_b.translation_deltas.abs().max().item() > 1e-4          # poses moved
     pa = torch.cat([p.detach().reshape(-1) for p in nf.parameters()])
     pb_ = torch.cat([p.detach().reshape(-1) for p in mf.parameters()])
