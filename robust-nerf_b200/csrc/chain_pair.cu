@@ -410,22 +410,25 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
           const int64_t gr = row0 + row;
           const bool row_ok = gr < p.m_rows;
           const float* sb = s_bias;
-          if (PE) {
-            // the tile's rows belong to at most two rays (host-checked: group == 64 or >= 128): A = ray of its first row
-            const int64_t rayA = row0 / p.group;
-            const int64_t n_rays = p.m_rows / p.group;
-            if (l == p.n_layers - 2 && bt < 256) {
-              // one layer ahead (thousands of cycles): fetch this thread's element of [dirvec[rayA] | dirvec[rayA + 1]]
-              const int64_t ray = min(rayA + (bt >> 7), n_rays - 1);
-              const float v = (ray >= 0) ? __ldg(p.dirvec + ray * 128 + (bt & 127)) : 0.f;
-              if (slot) pref1 = v; else pref0 = v;
-            }
-            if (ray_bias) {
+          if (PE && l >= p.n_layers - 2) {
+            // the tile's rows belong to at most two rays (host-checked: group == 64 or >= 128): A = ray of its first row.
+            // 32-bit arithmetic, last two layers only: a 64-bit division per item in every layer cost 3 % of the kernel.
+            const uint32_t grp_pts = (uint32_t)p.group;
+            const uint32_t rayA = (uint32_t)row0 / grp_pts;
+            if (!ray_bias) {
+              if (bt < 256) {
+                // one layer ahead (thousands of cycles): fetch this thread's element of [dirvec[rayA] | dirvec[rayA + 1]]
+                const uint32_t n_rays = (uint32_t)p.m_rows / grp_pts;
+                const uint32_t ray = min(rayA + (uint32_t)(bt >> 7), n_rays - 1u);
+                const float v = __ldg(p.dirvec + (size_t)ray * 128 + (bt & 127));
+                if (slot) pref1 = v; else pref0 = v;
+              }
+            } else {
               named_bar_sync(5, 512);                  // all warps are done with the previous item's bias
               if (bt < 256) s_bias[bt] = slot ? pref1 : pref0;
               named_bar_sync(5, 512);
-              const int64_t rowsA = (rayA + 1) * p.group - row0;
-              if ((int64_t)row >= rowsA) sb = s_bias + 128;
+              const uint32_t rowsA = (rayA + 1u) * grp_pts - (uint32_t)row0;
+              if ((uint32_t)row >= rowsA) sb = s_bias + 128;
             }
           }
           RN_TL(tl, 100 + l * 10 + slot);
@@ -961,7 +964,8 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
   int rc = check_arch();
   if (rc != RN_OK) return rc;
   RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kPairMaxLayers && M > 0 && consts && raw);
-  RN_REQUIRE(pe ? (!training && pe->pts && pe->dirvec && pair_encode_supported(pe->group) && M % pe->group == 0) : (x_enc && d_enc));
+  RN_REQUIRE(pe ? (!training && pe->pts && pe->dirvec && pair_encode_supported(pe->group) && M % pe->group == 0 &&
+                   M < (int64_t)0x7FFFFF00 && pe->group < (int64_t)0x7FFFFFFF) : (x_enc && d_enc));
   static thread_local PairParams p;     // ~4 KB of tensor maps: built on the host, passed by value as a kernel parameter
   double flops = 0.0;
   if (!pe) {

@@ -104,7 +104,7 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
     HC = p;
     H[0] = HA; H[1] = HB; H[2] = HA; H[3] = HB; H[4] = XC + 64; H[5] = HA; H[6] = HB; H[7] = HA;
   }
-  const bool pe_fused = !training && g_chain_fwd == 2 && g_pe_fused && pair_encode_supported(group);
+  const bool pe_fused = !training && g_chain_fwd == 2 && g_pe_fused && pair_encode_supported(group) && M < (int64_t)0x7FFFFF00;
   float* dirvec = nullptr;
   if (pe_fused) {
     dirvec = reinterpret_cast<float*>(align_up(reinterpret_cast<uintptr_t>(ws), 256) + align_up((size_t)M * kInferElems * 2, 256));
