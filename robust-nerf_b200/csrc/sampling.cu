@@ -179,7 +179,9 @@ __device__ __forceinline__ void warp_bitonic_sort(float* s, int P, int lane) {
 constexpr int kWarpsPerCta = 8;
 // floats of shared memory per warp of sample_hierarchical_kernel: z, bins, w, cdf [Nc each]; u, samples [NS each];
 // merged depths [Nc + Nf]; bucket starts [NS + 1] ints; two uint16 index arrays [NS each] (= NS floats); + padding
-__host__ __device__ constexpr int hier_smem_floats(int Nc, int NS, int Nf) { return 4 * Nc + 2 * NS + (Nc + Nf) + (NS + 1) + NS + 3; }
+__host__ __device__ constexpr int hier_smem_floats(int Nc, int NS, int Nf, bool inds) {
+  return 4 * Nc + 2 * NS + (Nc + Nf) + (NS + 1) + (inds ? NS : 0) + 3;
+}
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, int64_t B, int nb,
@@ -240,23 +242,40 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[E], int lane) 
   }
 }
 
+// ascending sort of E registers (odd-even transposition network, E <= 8)
+template <int E>
+__device__ __forceinline__ void sort_regs(float (&v)[E]) {
+#pragma unroll
+  for (int pass = 0; pass < E; ++pass) {
+#pragma unroll
+    for (int i = (pass & 1); i + 1 < E; i += 2) {
+      const float a = v[i], b = v[i + 1];
+      v[i] = fminf(a, b);
+      v[i + 1] = fmaxf(a, b);
+    }
+  }
+}
+
 // sample_hierarchical, fast path (Nf <= 32*E <= 256).  Work per ray is kept near the byte count instead of the
 // 2 x 256 binary searches + 36-stage bitonic network of the first version (0.18 of the HBM roofline at 128 + 256 samples,
 // 69 % issue-bound: profiles/r01_ncu_full_hbm_kernels.raw.csv):
 //   1. the draws u are put in ascending order FIRST: deterministic draws (linspace) already are -- one vote; random draws
-//      are uniform by construction (torch.rand), so a counting sort into Nf buckets by floor(u * Nf) leaves ~1 draw per
-//      bucket and the within-bucket rank is a handful of compares (any other distribution stays correct, only slower);
+//      are uniform by construction (torch.rand), so a counting sort into 32 E buckets by floor(u * 32 E) leaves ~1 draw per
+//      bucket; what is left to order inside the buckets is done by two passes of an E-register sorting network over
+//      lane-contiguous windows (offset 0 and E / 2), and a vote -- any other distribution of caller-supplied draws
+//      falls through to the register bitonic network and stays correct, only slower;
 //   2. with ascending u the searchsorted index is non-decreasing: each lane inverts E CONSECUTIVE draws, the first by
 //      binary search, the rest by stepping from the previous index (same predicate #{cdf <= u}, so the indices are the
 //      ones torch.searchsorted(right=True) returns);
 //   3. a sample of bin `ind` lies between the mid-points around z[ind], so its rank among the coarse depths is ind or
-//      ind + 1: one or two compares instead of a binary search (a short local walk keeps it exact in every rounding case);
+//      ind + 1: two compares (checked; a local walk keeps it exact in every rounding case);
 //   4. the samples come out ascending except for 1-ulp inversions at bin borders (fl(b + t (a - b)) may exceed a):
-//      checked with a vote, and only then sorted (register bitonic network, the previous version's hot loop);
+//      checked with a vote, and only then sorted (register bitonic network, the first version's hot loop);
 //   5. the coarse depths find their slots by binary search over the ascending samples (Nc / 32 searches per lane).
-// Values are those of sort(cat(z, samples)) bit for bit; `inds_out` (tests) is scattered back through the sort permutation.
-template <int E>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+// Values are those of sort(cat(z, samples)) bit for bit.  INDS (tests): also returns the searchsorted index of every draw
+// in the caller's order; that variant ranks inside the buckets exactly (value, slot) so the permutation is known.
+template <int E, bool INDS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict__ rd,
                            const float* __restrict__ zc, const float* __restrict__ weights, int64_t B, int Nc,
                            const float* __restrict__ u, int64_t u_stride, int Nf,
@@ -265,28 +284,31 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nb = Nc - 1, Nt = Nc + Nf;
   constexpr int NS = 32 * E;                 // padded draw count = bucket count
-  float* s_z = smem + (size_t)w * hier_smem_floats(Nc, NS, Nf);
+  float* s_z = smem + (size_t)w * hier_smem_floats(Nc, NS, Nf, INDS);
   float* s_bins = s_z + Nc;
   float* s_w = s_bins + Nc;
   float* s_cdf = s_w + Nc;
-  float* s_u = s_cdf + Nc;                   // [NS] draws, ascending
+  float* s_u = s_cdf + Nc;                   // [NS] draws (caller's order, then ascending)
   float* s_smp = s_u + NS;                   // [NS] samples, ascending (scratch of the counting sort before that)
   float* s_out = s_smp + NS;                 // [Nc + Nf] merged depths
   int* s_cnt = reinterpret_cast<int*>(s_out + Nt);                       // [NS + 1] bucket counts -> starts
-  unsigned short* s_id = reinterpret_cast<unsigned short*>(s_cnt + NS + 1);    // [NS] original index of the sorted draw
-  unsigned short* s_id2 = s_id + NS;                                     // [NS] scratch
+  unsigned short* s_id = reinterpret_cast<unsigned short*>(s_cnt + NS + 1);    // INDS: [NS] original index of the sorted draw
+  unsigned short* s_id2 = s_id + NS;                                     // INDS: [NS] scratch
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(z_all) | reinterpret_cast<uintptr_t>(pts) |
                         (uintptr_t)__cvta_generic_to_shared(s_out)) & 15) == 0;
   for (int64_t b = blockIdx.x * (int64_t)kWarpsPerCta + w; b < B; b += (int64_t)gridDim.x * kWarpsPerCta) {
-    for (int k = lane; k < Nc; k += 32) s_z[k] = __ldcs(zc + b * Nc + k);
-    for (int k = lane; k < Nc - 2; k += 32) s_w[k] = __ldcs(weights + b * Nc + k + 1);   // interior weights, rays.py:321
+    const float* zrow_in = zc + b * Nc;
+    const float* wrow_in = weights + b * Nc + 1;                        // interior weights, rays.py:321
+    const float* urow = u + b * u_stride;
+    for (int k = lane; k < Nc; k += 32) s_z[k] = __ldcs(zrow_in + k);
+    for (int k = lane; k < Nc - 2; k += 32) s_w[k] = __ldcs(wrow_in + k);
     float ur[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int j = e * 32 + lane;            // coalesced over u
-      ur[e] = (j < Nf) ? __ldg(u + b * u_stride + j) : CUDART_INF_F;
+      ur[e] = (j < Nf) ? __ldg(urow + j) : CUDART_INF_F;
       s_u[j] = ur[e];
-      s_id[j] = (unsigned short)j;
+      if (INDS) s_id[j] = (unsigned short)j;
     }
     __syncwarp();
     for (int k = lane; k < nb; k += 32) s_bins[k] = __fmul_rn(0.5f, __fadd_rn(s_z[k + 1], s_z[k]));   // rays.py:316
@@ -297,7 +319,11 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
       const int j = e * 32 + lane;
       if (j + 1 < Nf) ok = ok && (ur[e] <= s_u[j + 1]);
     }
-    if (!__all_sync(0xffffffffu, ok)) {
+    float uq[E];                              // ascending draws, lane-contiguous: uq[e] <-> position lane * E + e
+    if (__all_sync(0xffffffffu, ok)) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) uq[e] = s_u[lane * E + e];
+    } else {
       for (int k = lane; k <= NS; k += 32) s_cnt[k] = 0;
       __syncwarp();
       int bk[E], arr[E];
@@ -322,25 +348,64 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
 #pragma unroll
       for (int e = 0; e < E; ++e) { s_cnt[lane * E + e] = run; run += cnt[e]; }
       if (lane == 31) s_cnt[NS] = run;
-      __syncwarp();
-      // scatter into bucket order (arrival order inside a bucket), then rank inside the bucket by (value, slot)
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int j = e * 32 + lane;
-        if (j < Nf) { const int pos = s_cnt[bk[e]] + arr[e]; s_smp[pos] = ur[e]; s_id2[pos] = (unsigned short)j; }
-      }
+      for (int e = 0; e < E; ++e) s_smp[e * 32 + lane] = CUDART_INF_F;      // padding beyond Nf stays +inf
       __syncwarp();
+      // scatter into bucket order (arrival order inside a bucket)
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int j = e * 32 + lane;
         if (j < Nf) {
-          const int b0 = s_cnt[bk[e]], b1 = s_cnt[bk[e] + 1], pos = b0 + arr[e];
-          const float x = ur[e];
-          int rank = 0;
-          for (int q = b0; q < b1; ++q) { const float y = s_smp[q]; rank += (y < x || (y == x && q < pos)) ? 1 : 0; }
-          s_u[b0 + rank] = x;
-          s_id[b0 + rank] = (unsigned short)j;
+          const int pos = s_cnt[bk[e]] + arr[e];
+          s_smp[pos] = ur[e];
+          if (INDS) s_id2[pos] = (unsigned short)j;
         }
+      }
+      __syncwarp();
+      if (INDS) {
+        // exact rank inside the bucket by (value, slot): the permutation is needed for inds_out
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int j = e * 32 + lane;
+          if (j < Nf) {
+            const int b0 = s_cnt[bk[e]], b1 = s_cnt[bk[e] + 1], pos = b0 + arr[e];
+            const float x = ur[e];
+            int rank = 0;
+            for (int q = b0; q < b1; ++q) { const float y = s_smp[q]; rank += (y < x || (y == x && q < pos)) ? 1 : 0; }
+            s_u[b0 + rank] = x;
+            s_id[b0 + rank] = (unsigned short)j;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < E; ++e) uq[e] = s_u[lane * E + e];
+      } else {
+        // two passes of an E-register sorting network over lane-contiguous windows (offsets 0 and E / 2): orders every
+        // bucket that fits a window; anything else is caught by the vote below
+#pragma unroll
+        for (int e = 0; e < E; ++e) uq[e] = s_smp[lane * E + e];
+        sort_regs<E>(uq);
+        if (E >= 2) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) s_smp[lane * E + e] = uq[e];
+          __syncwarp();
+          if (lane < 31) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) uq[e] = s_smp[lane * E + E / 2 + e];
+            sort_regs<E>(uq);
+#pragma unroll
+            for (int e = 0; e < E; ++e) s_smp[lane * E + E / 2 + e] = uq[e];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int e = 0; e < E; ++e) uq[e] = s_smp[lane * E + e];
+        }
+        bool asc = true;
+#pragma unroll
+        for (int e = 0; e + 1 < E; ++e) asc = asc && (uq[e] <= uq[e + 1]);
+        const float nxt = __shfl_down_sync(0xffffffffu, uq[0], 1);
+        if (lane < 31) asc = asc && (uq[E - 1] <= nxt);
+        if (!__all_sync(0xffffffffu, asc)) warp_bitonic_sort_regs<E>(uq, lane);
       }
     }
     __syncwarp();
@@ -356,7 +421,7 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
       v[e] = CUDART_INF_F;
       cind[e] = 0;
       if (j < Nf) {
-        const float x = s_u[j];
+        const float x = uq[e];
         if (!have) {
           int lo = 0, hi = nb;
           while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cdf[mid] <= x) lo = mid + 1; else hi = mid; }
@@ -372,7 +437,7 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
         const float t = __fdiv_rn(__fsub_rn(x, cb), denom);
         v[e] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                 // rays.py:259-277
         cind[e] = ind;
-        if (inds_out) inds_out[b * Nf + s_id[j]] = ind;
+        if (INDS) inds_out[b * Nf + s_id[j]] = ind;
       }
     }
     // ---- 4. ascending?  (1-ulp inversions at bin borders are possible; sort only then) ----
@@ -393,10 +458,14 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
       const int j = lane * E + e;
       if (j < Nf) {
         const float sj = v[e];
-        // #{coarse <= sj}: the sample's bin puts it next to z[ind]; walk from there (0-2 steps)
-        int c = min(cind[e], Nc);
-        while (c < Nc && s_z[c] <= sj) ++c;
-        while (c > 0 && s_z[c - 1] > sj) --c;
+        // #{coarse <= sj}: the sample's bin puts it next to z[ind] -> ind or ind + 1; verified, walked otherwise
+        int c = min(cind[e], Nc - 1);
+        c += (s_z[c] <= sj) ? 1 : 0;
+        const bool fine_ = (c == Nc || s_z[c] > sj) && (c == 0 || s_z[c - 1] <= sj);
+        if (!fine_) {
+          while (c < Nc && s_z[c] <= sj) ++c;
+          while (c > 0 && s_z[c - 1] > sj) --c;
+        }
         s_out[j + c] = sj;
       }
     }
@@ -484,19 +553,27 @@ sample_hierarchical_generic_kernel(const float* __restrict__ ro, const float* __
   }
 }
 
+template <int E, bool INDS>
+static int launch_hier_v(const float* ro, const float* rd, const float* zc, const float* weights, int64_t B, int Nc,
+                         const float* u, int64_t u_stride, int Nf, float* z_all, float* pts, int64_t* inds_out, cudaStream_t st) {
+  const size_t smem = (size_t)kWarpsPerCta * hier_smem_floats(Nc, 32 * E, Nf, INDS) * sizeof(float);
+  if (smem > 200 * 1024) return RN_ERR_INVALID_ARG;
+  static unsigned long long configured = 0;
+  if (smem > 48 * 1024 || first_use_on_device(configured))
+    RN_CUDA_CHECK(cudaFuncSetAttribute(sample_hierarchical_kernel<E, INDS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+  const int64_t want = ceil_div(B, kWarpsPerCta);
+  const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  sample_hierarchical_kernel<E, INDS><<<grid, kWarpsPerCta * 32, smem, st>>>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all,
+                                                                            pts, inds_out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
 template <int E>
 static int launch_hier(const float* ro, const float* rd, const float* zc, const float* weights, int64_t B, int Nc,
                        const float* u, int64_t u_stride, int Nf, float* z_all, float* pts, int64_t* inds_out, cudaStream_t st) {
-  const size_t smem = (size_t)kWarpsPerCta * hier_smem_floats(Nc, 32 * E, Nf) * sizeof(float);
-  if (smem > 200 * 1024) return RN_ERR_INVALID_ARG;
-  if (smem > 48 * 1024)
-    RN_CUDA_CHECK(cudaFuncSetAttribute(sample_hierarchical_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t want = ceil_div(B, kWarpsPerCta);
-  const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
-  sample_hierarchical_kernel<E><<<grid, kWarpsPerCta * 32, smem, st>>>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts,
-                                                                      inds_out);
-  RN_LAUNCH_CHECK();
-  return RN_OK;
+  return inds_out ? launch_hier_v<E, true>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts, inds_out, st)
+                  : launch_hier_v<E, false>(ro, rd, zc, weights, B, Nc, u, u_stride, Nf, z_all, pts, nullptr, st);
 }
 
 }  // namespace rn

@@ -296,6 +296,9 @@ def test_sample_hierarchical(rn, dev, Nc, Nf, B):
         assert np.array_equal(z_all.cpu().numpy(), z_ref)                           # sorted merge, bit-exact
         close(N(pts), pts_ref, atol=2e-6)
         assert (z_all[:, 1:] >= z_all[:, :-1]).all()
+        # the production variant (no index output: window sorting network instead of exact bucket ranks)
+        z_all2, pts2, _ = ops.sample_hierarchical(T(ro, dev), T(rd, dev), T(z, dev), T(w, dev), T(u, dev))
+        assert torch.equal(z_all2, z_all) and torch.equal(pts2, pts)
     g = load_golden("sample_pdf")
     if Nc == 64:
         p, zf = rn.sample_hierarchical(T(g["rays_o"], dev), T(g["rays_d"], dev), T(g["z"], dev), T(g["weights"], dev), 128,
@@ -331,6 +334,8 @@ def test_sample_hierarchical_any_draw_distribution(rn, dev, kind):
     assert np.array_equal(inds.cpu().numpy(), i_ref)
     assert np.array_equal(z_all.cpu().numpy(), z_ref)
     close(N(pts), pts_ref, atol=2e-6)
+    z_all2, pts2, _ = ops.sample_hierarchical(T(ro, dev), T(rd, dev), T(z, dev), T(w, dev), T(u, dev))     # production variant
+    assert torch.equal(z_all2, z_all) and torch.equal(pts2, pts)
 
 
 # ------------------------------------------------------------------------------------------------
