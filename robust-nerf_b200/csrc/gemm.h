@@ -29,7 +29,7 @@ int tn_batch_add(TnBatch* b, const TnInfo& info, int row0, int nrows, int col0, 
                  float* colsum_dst);
 int gemm_tn_reduce_batch(const TnBatch& b, cudaStream_t st);
 
-// one layer of the chained forward (mlp_chain_forward): D[M,n] = act(A[M,k] B[n,k]^T + bias), bf16 views
+// one layer of the chained forward (mlp_chain_pair_forward): D[M,n] = act(A[M,k] B[n,k]^T + bias), bf16 views
 struct ChainLayerHost {
   const void* A; int64_t lda; const void* B; int64_t ldb; void* D; int64_t ldd;
   int k, n, relu, heads, head_col, bias_off, head_w_off, head_b_off, dep;
@@ -55,8 +55,6 @@ struct BwdLayerHost {
 };
 int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M, const void* in, int64_t ld_in, int in_cols,
                             const void* aux, int64_t ld_aux, int aux_cols, cudaStream_t st);
-int mlp_chain_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const float* consts, float* raw, bool wmask,
-                      cudaStream_t st);
 
 // inference: per-ray view-direction projection dirvec[R][128] (encode.cu: dir_bias_kernel)
 int launch_dir_bias(const float* dirs, int64_t R, const void* packed, float* dirvec, cudaStream_t st);

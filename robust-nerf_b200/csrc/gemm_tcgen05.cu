@@ -685,415 +685,6 @@ int gemm_tn_reduce_batch(const TnBatch& b, cudaStream_t st) {
   return RN_OK;
 }
 
-// =====================================================================================================
-// Layer-chained forward: ONE persistent launch runs all ten GEMM layers of a network.
-//
-// Rows of the MLP are independent, so a CTA can push a group of G = 4 row tiles through the whole layer
-// chain by itself: layer l+1 of a tile reads what layer l of the same tile just stored.  Those re-reads
-// hit L2 (the tile was written by this SM microseconds earlier), so HBM sees each activation once (the
-// store that the backward pass needs anyway) or -- in inference, where the ping-pong buffers are
-// overwritten before they are evicted -- almost never.  Work items are ordered (layer, tile-in-group):
-// four tiles share each layer back to back, so the A ring, the TMEM double buffer and the staged
-// stores pipeline across items exactly as in the per-layer kernel, and the store->load round trip of a
-// tile (store warp: TMA store, wait for completion, arrive on stored[g]) is hidden behind the three
-// other tiles of the group.
-//
-// Warp roles (256 threads): 0 = A producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue,
-// 6 = B (weight) producer, 7 = store warp (TMA stores + completion signalling).
-// =====================================================================================================
-constexpr int kChainMaxLayers = 10;
-constexpr int kChainG = 4;
-constexpr int kChainThreads = 256;
-constexpr int kChainConsts = 3328;          // >= layout::kF32Elems (3212): every bias + fp32 head weight, staged in smem
-constexpr int kChainRingBytes = 5 * kABytes + 2 * 32768;      // A ring + B ring: (NA,NB) = (5,2) or (3,3), same bytes
-constexpr int kChainSmem = kChainRingBytes + 2 * 32768 + kChainConsts * 4 + 1024 /*barriers*/ + 1024;
-static_assert(kChainSmem <= kMaxSmem, "chain kernel shared memory budget exceeded");
-static_assert(3 * kABytes + 3 * 32768 <= kChainRingBytes, "ring configurations must fit the same budget");
-int g_chain_ring = 0;        // rn_set_flag(2, v): 0 -> (NA,NB) = (5,2), 1 -> (3,3)
-
-struct ChainLayer {
-  int k_chunks, k_total, n;     // n = 256 or 128 output columns
-  int relu, heads, head_col;    // heads: 0, 1 (sigma -> raw[:,3]) or 3 (rgb -> raw[:,0:3])
-  int bias_off, head_w_off, head_b_off;   // float offsets into the staged fp32 constants
-  int dep;                      // 1: this layer's A operand is produced by the previous layer inside the kernel
-  uint32_t* mask_out;           // packed ReLU mask of this layer's output or null
-};
-// measurement knobs, compiled in only with -DRN_EXPERIMENTS (RN_EXPERIMENTS=1 python robust-nerf_b200/build.py;
-// the shipped library has none).  rn_set_flag(1, bits); results are WRONG when any bit is set:
-// bit 0: B producer loads nothing (MMA reuses stale weights)   bit 1: store warp issues no TMA stores
-// bit 2: A producer loads nothing                               bit 3: epilogue skips the TMEM->smem conversion
-#ifdef RN_EXPERIMENTS
-int g_chain_dbg = 0;
-#define RN_DBG(p, bit) ((p).dbg & (bit))
-#else
-#define RN_DBG(p, bit) (0)
-#endif
-
-struct ChainParams {
-  int dbg;
-  CUtensorMap tmA[kChainMaxLayers], tmB[kChainMaxLayers], tmD[kChainMaxLayers];
-  ChainLayer L[kChainMaxLayers];
-  int n_layers, m_tiles;
-  int64_t m_rows;
-  const float* consts;
-  float* raw;
-};
-
-// one 128-column half of an output tile: TMEM -> bias/ReLU -> bf16 -> swizzled staging (+ mask bits, fused heads)
-template <int HEADS, bool WMASK>
-__device__ __forceinline__ void chain_epilogue_half(uint32_t t_half, uint8_t* s_half, int row, const float* s_bias,
-                                                    const float* s_head, int n, int col0, float relu_lo,
-                                                    uint32_t (&mbits)[4], float& h0, float& h1, float& h2) {
-#pragma unroll
-  for (int cg = 0; cg < 4; ++cg) {
-    uint32_t v[32];
-    tmem_ld_x32(t_half + cg * 32, v);
-    tmem_ld_wait();
-    uint8_t* box = s_half + (cg >> 1) * 16384 + row * 128;
-    uint32_t outbits = 0u;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int lchunk = (cg & 1) * 4 + cc;
-      uint4* dst = reinterpret_cast<uint4*>(box + ((lchunk ^ (row & 7)) << 4));
-      const int j0 = col0 + cg * 32 + cc * 8;           // first output column of this 8-wide chunk
-      float x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[cc * 8 + e]);
-      const float4 b0 = *reinterpret_cast<const float4*>(s_bias + j0);
-      const float4 b1 = *reinterpret_cast<const float4*>(s_bias + j0 + 4);
-      x[0] = fmaxf(x[0] + b0.x, relu_lo); x[1] = fmaxf(x[1] + b0.y, relu_lo);
-      x[2] = fmaxf(x[2] + b0.z, relu_lo); x[3] = fmaxf(x[3] + b0.w, relu_lo);
-      x[4] = fmaxf(x[4] + b1.x, relu_lo); x[5] = fmaxf(x[5] + b1.y, relu_lo);
-      x[6] = fmaxf(x[6] + b1.z, relu_lo); x[7] = fmaxf(x[7] + b1.w, relu_lo);
-      if (WMASK) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) outbits |= (x[e] > 0.f) ? (1u << layout::relu_mask_bit(cc * 8 + e)) : 0u;
-      }
-      uint32_t packed[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __nv_bfloat162 p = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-        packed[e] = *reinterpret_cast<uint32_t*>(&p);
-      }
-      if (HEADS > 0) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xFFFF0000u);
-          const int j = j0 + 2 * e;
-          h0 = fmaf(r0, s_head[j], h0); h0 = fmaf(r1, s_head[j + 1], h0);
-          if (HEADS == 3) {
-            h1 = fmaf(r0, s_head[n + j], h1); h1 = fmaf(r1, s_head[n + j + 1], h1);
-            h2 = fmaf(r0, s_head[2 * n + j], h2); h2 = fmaf(r1, s_head[2 * n + j + 1], h2);
-          }
-        }
-      }
-      *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    }
-    mbits[cg] = outbits;
-  }
-}
-
-template <bool WMASK, int kChainNA, int kChainNB>
-__global__ void __launch_bounds__(kChainThreads, 1)
-mlp_chain_fwd_kernel(const __grid_constant__ ChainParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_a = smem;
-  uint8_t* s_b = s_a + kChainNA * kABytes;
-  uint8_t* s_staging = s_a + kChainRingBytes;           // two 32 KiB half-tile buffers
-  float* s_consts = reinterpret_cast<float*>(s_staging + 2 * 32768);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_consts + kChainConsts);
-  uint64_t* full_a = bars;               // [8]
-  uint64_t* empty_a = bars + 8;          // [8]
-  uint64_t* full_b = bars + 16;          // [4]
-  uint64_t* empty_b = bars + 20;         // [4]
-  uint64_t* tmem_full = bars + 24;       // [2]
-  uint64_t* tmem_empty = bars + 26;      // [2]
-  uint64_t* staged = bars + 28;          // [2]  epilogue -> store warp
-  uint64_t* sfree = bars + 30;           // [2]  store warp -> epilogue
-  uint64_t* stored = bars + 32;          // [4]  store warp -> A producer (tile slot g fully written)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  constexpr int G = kChainG;
-
-  if (warp == 0 && lane == 0) {
-    for (int l = 0; l < p.n_layers; ++l) { prefetch_tmap(&p.tmA[l]); prefetch_tmap(&p.tmB[l]); prefetch_tmap(&p.tmD[l]); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
-      mbar_init(&staged[i], 4); mbar_init(&sfree[i], 1);
-    }
-    for (int i = 0; i < G; ++i) mbar_init(&stored[i], 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  for (int i = threadIdx.x; i < kChainConsts; i += kChainThreads) s_consts[i] = (i < (int)layout::kF32Elems) ? p.consts[i] : 0.f;
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int n_groups = (p.m_tiles + G - 1) / G;
-
-  if (warp == 0) {
-    // ---------------- A producer ----------------
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0, stored_ph = 0;
-      for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
-        for (int l = 0; l < p.n_layers; ++l)
-          for (int g = 0; g < G; ++g) {
-            const int tile = grp * G + g;
-            if (tile >= p.m_tiles) break;
-            if (p.L[l].dep) {                              // wait until this tile's previous layer is in global memory
-              mbar_wait(&stored[g], (stored_ph >> g) & 1u);
-              stored_ph ^= 1u << g;
-              fence_proxy_async_all();
-            }
-            for (int kc = 0; kc < p.L[l].k_chunks; ++kc) {
-              mbar_wait(&empty_a[s], ph ^ 1);
-              if RN_DBG(p, 4) { mbar_arrive(&full_a[s]); }
-              else {
-                mbar_arrive_expect_tx(&full_a[s], kABytes);
-                tma_load_2d(s_a + s * kABytes, &p.tmA[l], &full_a[s], kc * kBlockK, tile * kBlockM);
-              }
-              if (++s == kChainNA) { s = 0; ph ^= 1; }
-            }
-          }
-    }
-  } else if (warp == 6) {
-    // ---------------- B producer (weights, L2) ----------------
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
-        for (int l = 0; l < p.n_layers; ++l)
-          for (int g = 0; g < G; ++g) {
-            if (grp * G + g >= p.m_tiles) break;
-            const uint32_t bytes = (uint32_t)p.L[l].n * 128u;
-            for (int kc = 0; kc < p.L[l].k_chunks; ++kc) {
-              mbar_wait(&empty_b[s], ph ^ 1);
-              if RN_DBG(p, 1) { mbar_arrive(&full_b[s]); }
-              else {
-                mbar_arrive_expect_tx(&full_b[s], bytes);
-                tma_load_2d(s_b + s * 32768, &p.tmB[l], &full_b[s], kc * kBlockK, 0);
-              }
-              if (++s == kChainNB) { s = 0; ph ^= 1; }
-            }
-          }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer (whole warp converged, one elected lane issues; see gemm_kernel) ----------------
-    constexpr uint32_t kHi = desc_hi_sw128(1024);
-    const uint32_t a_lo0 = desc_lo_sw128(smem_u32(s_a), 16);
-    const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_b), 16);
-    int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int acc = 0; uint32_t acc_ph = 0;
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
-      for (int l = 0; l < p.n_layers; ++l) {
-        const uint32_t idesc = make_idesc_bf16(kBlockM, p.L[l].n, 0, 0);
-        const int k_chunks = p.L[l].k_chunks, k_total = p.L[l].k_total;
-        for (int g = 0; g < G; ++g) {
-          if (grp * G + g >= p.m_tiles) break;
-          mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
-          const uint32_t d_tmem = tmem_base + acc * 256;
-          for (int kc = 0; kc < k_chunks; ++kc) {
-            mbar_wait(&full_b[sb], phb);
-            mbar_wait(&full_a[sa], pha);
-            tcgen05_fence_after();
-            if (elect_one()) {
-              const uint32_t al = a_lo0 + sa * (kABytes >> 4), bl = b_lo0 + sb * (32768 >> 4);
-              const int krem = k_total - kc * kBlockK;
-              umma_bf16(d_tmem, pack64(al, kHi), pack64(bl, kHi), idesc, kc != 0);
-#pragma unroll
-              for (int k = 1; k < 4; ++k)
-                if (krem > k * 16) umma_bf16(d_tmem, pack64(al + 2 * k, kHi), pack64(bl + 2 * k, kHi), idesc, 1u);
-              umma_commit(&empty_a[sa]);
-              umma_commit(&empty_b[sb]);
-              if (kc == k_chunks - 1) umma_commit(&tmem_full[acc]);
-            }
-            __syncwarp();
-            if (++sa == kChainNA) { sa = 0; pha ^= 1; }
-            if (++sb == kChainNB) { sb = 0; phb ^= 1; }
-          }
-          acc ^= 1; if (acc == 0) acc_ph ^= 1;
-        }
-      }
-  } else if (warp == 7) {
-    // ---------------- store warp: staged half tiles -> global, completion signalling ----------------
-    // Completion is tracked lazily: after item i's stores are issued, wait until at most those bulk groups
-    // are still in flight (=> item i-1 is complete) and only then signal item i-1.  A group with a single
-    // tile has nothing to hide the round trip behind and signals eagerly.
-    if (lane == 0) {
-      int sbuf = 0; uint32_t st_ph = 0;
-      int pend_g = -1;                                     // tile slot of the previous item if it still needs a signal
-      for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int tiles_here = min(G, p.m_tiles - grp * G);
-        for (int l = 0; l < p.n_layers; ++l) {
-          const int halves = p.L[l].n / 128;
-          const bool signal = (l + 1 < p.n_layers) && p.L[l + 1].dep;
-          for (int g = 0; g < tiles_here; ++g) {
-            const int tile = grp * G + g;
-            for (int h = 0; h < halves; ++h) {
-              mbar_wait(&staged[sbuf], (st_ph >> sbuf) & 1u);
-              st_ph ^= 1u << sbuf;
-              uint8_t* s_half = s_staging + sbuf * 32768;
-              if (!RN_DBG(p, 2)) {
-                tma_store_2d(&p.tmD[l], s_half, h * 128, tile * kBlockM);
-                tma_store_2d(&p.tmD[l], s_half + 16384, h * 128 + 64, tile * kBlockM);
-              }
-              tma_store_commit();
-              tma_store_wait_read0();
-              mbar_arrive(&sfree[sbuf]);
-              sbuf ^= 1;
-            }
-            if (pend_g >= 0) {                             // previous item: complete once only this item's groups remain
-              if (halves == 2) tma_store_wait_all2(); else tma_store_wait_all1();
-              fence_proxy_async_all();
-              mbar_arrive(&stored[pend_g]);
-              pend_g = -1;
-            }
-            if (signal) {
-              if (tiles_here == 1) {
-                tma_store_wait_all0();
-                fence_proxy_async_all();
-                mbar_arrive(&stored[g]);
-              } else {
-                pend_g = g;
-              }
-            }
-          }
-        }
-      }
-      tma_store_wait_all0();
-    }
-  } else {
-    // ---------------- epilogue warps ----------------
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    int acc = 0; uint32_t acc_ph = 0;
-    int sbuf = 0; uint32_t fr_ph = 0;
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
-      for (int l = 0; l < p.n_layers; ++l) {
-        const ChainLayer L = p.L[l];
-        const float relu_lo = L.relu ? 0.f : -3.0e38f;
-        const float* s_bias = s_consts + L.bias_off;
-        const float* s_head = s_consts + L.head_w_off;
-        for (int g = 0; g < G; ++g) {
-          const int tile = grp * G + g;
-          if (tile >= p.m_tiles) break;
-          const int64_t gr = (int64_t)tile * kBlockM + row;
-          const bool row_ok = gr < p.m_rows;
-          mbar_wait(&tmem_full[acc], acc_ph);
-          tcgen05_fence_after();
-          const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-          float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-          uint32_t mb[8];
-          const int halves = L.n / 128;
-          for (int h = 0; h < halves; ++h) {
-            mbar_wait(&sfree[sbuf], ((fr_ph >> sbuf) & 1u) ^ 1u);     // first use of a buffer passes immediately
-            fr_ph ^= 1u << sbuf;
-            uint8_t* s_half = s_staging + sbuf * 32768;
-            uint32_t mh[4] = {0u, 0u, 0u, 0u};
-            if RN_DBG(p, 16) { }
-            else if RN_DBG(p, 8) {
-#pragma unroll 1
-              for (int cg = 0; cg < 4; ++cg) { uint32_t v[32]; tmem_ld_x32(t_base + h * 128 + cg * 32, v); tmem_ld_wait(); if (v[0] == 0x7fc12345u) mh[0] ^= v[1]; }
-            }
-            else if (L.heads == 0) chain_epilogue_half<0, WMASK>(t_base + h * 128, s_half, row, s_bias, s_head, L.n, h * 128, relu_lo, mh, h0, h1, h2);
-            else if (L.heads == 1) chain_epilogue_half<1, WMASK>(t_base + h * 128, s_half, row, s_bias, s_head, L.n, h * 128, relu_lo, mh, h0, h1, h2);
-            else chain_epilogue_half<3, false>(t_base + h * 128, s_half, row, s_bias, s_head, L.n, h * 128, relu_lo, mh, h0, h1, h2);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) mb[(h & 1) * 4 + i] = mh[i];
-            if (h == halves - 1) {                     // accumulator drained -> back to the MMA warp
-              tcgen05_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&staged[sbuf]);
-            sbuf ^= 1;
-          }
-          acc ^= 1; if (acc == 0) acc_ph ^= 1;
-          if (row_ok) {
-            if (WMASK && L.mask_out) {
-              uint4* mo = reinterpret_cast<uint4*>(L.mask_out + gr * 8);
-              mo[0] = make_uint4(mb[0], mb[1], mb[2], mb[3]);
-              mo[1] = make_uint4(mb[4], mb[5], mb[6], mb[7]);
-            }
-            if (L.heads > 0) {
-              float* o = p.raw + gr * 4 + L.head_col;
-              const float* hb = s_consts + L.head_b_off;
-              o[0] = h0 + hb[0];
-              if (L.heads == 3) { o[1] = h1 + hb[1]; o[2] = h2 + hb[2]; }
-            }
-          }
-        }
-      }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// Forward chain launcher.  Layer l: D_l[M, n_l] = act(A_l[M, K_l] * B_l[n_l, K_l]^T + bias) with the operands given as
-// (pointer, leading dimension) views; see mlp.cu for the table.
-int mlp_chain_forward(const ChainLayerHost* layers, int n_layers, int64_t M, const float* consts, float* raw, bool wmask,
-                      cudaStream_t st) {
-  int rc = check_arch();
-  if (rc != RN_OK) return rc;
-  RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kChainMaxLayers && M > 0 && consts && raw);
-  static thread_local ChainParams p;   // ~5 KB of tensor maps: built on the host, passed by value as a kernel parameter
-  double flops = 0.0;
-  for (int l = 0; l < n_layers; ++l) {
-    const ChainLayerHost& h = layers[l];
-    RN_REQUIRE((h.n == 256 || h.n == 128) && h.k > 0 && h.k % 8 == 0 && (h.heads == 0 || h.heads == 1 || h.heads == 3));
-    RN_REQUIRE(!(h.mask_out && h.n != 256));
-    if ((rc = make_tmap(&p.tmA[l], h.A, h.k, M, h.lda, kBlockM)) != RN_OK) return rc;
-    if ((rc = make_tmap(&p.tmB[l], h.B, h.k, h.n, h.ldb, h.n)) != RN_OK) return rc;
-    if ((rc = make_tmap(&p.tmD[l], h.D, h.n, M, h.ldd, kBlockM)) != RN_OK) return rc;
-    ChainLayer& L = p.L[l];
-    L.k_chunks = (int)ceil_div(h.k, kBlockK); L.k_total = h.k; L.n = h.n; L.relu = h.relu; L.heads = h.heads;
-    L.head_col = h.head_col; L.bias_off = h.bias_off; L.head_w_off = h.head_w_off; L.head_b_off = h.head_b_off;
-    L.dep = h.dep; L.mask_out = wmask ? h.mask_out : nullptr;
-    flops += 2.0 * (double)M * h.n * h.k;
-  }
-#ifdef RN_EXPERIMENTS
-  p.dbg = g_chain_dbg;
-#else
-  p.dbg = 0;
-#endif
-  p.n_layers = n_layers;
-  p.m_tiles = (int)ceil_div(M, kBlockM);
-  p.m_rows = M; p.consts = consts; p.raw = raw;
-  static unsigned long long configured = 0;
-  if (first_use_on_device(configured)) {
-    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fwd_kernel<true, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fwd_kernel<false, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fwd_kernel<true, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fwd_kernel<false, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-  }
-  const int n_groups = (int)ceil_div(p.m_tiles, kChainG);
-  const int grid = n_groups < num_sms() ? n_groups : num_sms();
-  g_prof_next_flops = flops;
-  int slot;
-  prof_begin(MODE_NT, st, &slot);
-  if (g_chain_ring == 0) {
-    if (wmask) mlp_chain_fwd_kernel<true, 5, 2><<<grid, kChainThreads, kChainSmem, st>>>(p);
-    else mlp_chain_fwd_kernel<false, 5, 2><<<grid, kChainThreads, kChainSmem, st>>>(p);
-  } else {
-    if (wmask) mlp_chain_fwd_kernel<true, 3, 3><<<grid, kChainThreads, kChainSmem, st>>>(p);
-    else mlp_chain_fwd_kernel<false, 3, 3><<<grid, kChainThreads, kChainSmem, st>>>(p);
-  }
-  prof_end(slot, st);
-  RN_LAUNCH_CHECK();
-  return RN_OK;
-}
-
 }  // namespace rn
 
 using namespace rn;

@@ -72,12 +72,13 @@ static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimen
   } while (0)
 
 #ifdef RN_EXPERIMENTS
-extern int g_chain_dbg;
+int g_chain_dbg = 0;
 #endif
-extern int g_chain_ring;
 int g_chain_bwd = 1;      // rn_set_flag(3, v): 1 = data gradients as one CTA-pair chain launch (chain_pair.cu), 0 = one launch per layer
-// rn_set_flag(0, v): 0 = one launch per layer, 1 = layer-chained persistent launch (activations round-trip through L2),
-// 2 = CTA-pair chain with shared-memory-resident activations (chain_pair.cu; default)
+// rn_set_flag(0, v): 0 = one launch per layer (gemm_tcgen05.cu: the building-block kernels, kept as the cross-check of the
+// chain), 2 = CTA-pair chain with shared-memory-resident activations (chain_pair.cu; default).  (Round 1's third variant,
+// a layer-chained launch whose activations round-tripped through L2, was measured slower than the pair chain on every
+// shape and has been removed.)
 int g_chain_fwd = 2;
 // rn_set_flag(4, v): 1 = inference encodes the points inside the forward chain and hoists the view-direction term per ray
 // (default), 0 = separate encode kernel + TMA-loaded x_enc / d_enc chunks (the training layout; kept for A/B and as the
@@ -134,7 +135,7 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
       L[9].aux_kind = 2; L[9].aux_load = 2; L[9].aux_release = 1;
       return mlp_chain_pair_forward(L, 10, M, XC, 320, FD + 256, 320, F, raw, training != 0, st);
     }
-    return mlp_chain_forward(L, 10, M, F, raw, training != 0, st);
+    return RN_ERR_INVALID_ARG;        // unreachable: g_chain_fwd is 0 or 2
   }
   RN_TRY(gemm_nt(XC, 320, W + kW0, 64, H[0], 256, M, 256, 64, F + kB0, 1, st, MB[0]));
   for (int l = 1; l < 8; ++l) {
@@ -226,11 +227,10 @@ using namespace rn;
 extern "C" {
 
 int rn_set_flag(int flag, int value) {
-  if (flag == 0) { g_chain_fwd = value; return RN_OK; }
+  if (flag == 0) { if (value != 0 && value != 2) return RN_ERR_INVALID_ARG; g_chain_fwd = value; return RN_OK; }
 #ifdef RN_EXPERIMENTS
   if (flag == 1) { g_chain_dbg = value; return RN_OK; }
 #endif
-  if (flag == 2) { g_chain_ring = value; return RN_OK; }
   if (flag == 3) { g_chain_bwd = value; return RN_OK; }
   if (flag == 4) { g_pe_fused = value; return RN_OK; }
   return RN_ERR_INVALID_ARG;

@@ -698,10 +698,9 @@ def test_pose_gradients_through_full_render(rn, dev):
 
 
 def test_chained_forward_equals_per_layer_forward(rn, dev):
-    """The layer-chained persistent forward (one launch) must reproduce the per-layer GEMM chain bit for bit
-    (same MMAs, same epilogue arithmetic), in inference and in training mode, including ragged tile counts.
-    The CTA-pair chain (shared-memory-resident activations, cta_group::2 MMAs) computes identical activations; its fused
-    heads sum the two 128-column halves separately, so raw differs from the per-layer kernel by fp32 rounding only."""
+    """The CTA-pair chain (one launch, shared-memory-resident activations, cta_group::2 MMAs) against the per-layer GEMM
+    chain built from the building-block kernels, in inference and in training mode, including ragged tile counts: identical
+    activations; its fused heads sum the two 128-column halves separately, so raw differs by fp32 rounding only."""
     from robust_nerf_b200 import _lib
     lib = _lib.lib()
     w = O.make_weights(13, sharpen=True)
@@ -712,7 +711,7 @@ def test_chained_forward_equals_per_layer_forward(rn, dev):
             pts = T(rng.uniform(-3, 3, (M, 3)).astype(np.float32), dev)
             dirs = T(rng.standard_normal((M, 3)).astype(np.float32), dev)
             outs = {}
-            for chain in (0, 1, 2):
+            for chain in (0, 2):
                 lib.rn_set_flag(0, chain)
                 with torch.no_grad():
                     outs[("eval", chain)] = net.forward_raw(pts, dirs, 1).clone()
@@ -724,14 +723,12 @@ def test_chained_forward_equals_per_layer_forward(rn, dev):
                 outs[("grad", chain)] = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
                 outs[("dx", chain)] = x.grad.clone()
             torch.cuda.synchronize()
-            for k in ("eval", "train", "grad", "dx"):
-                assert torch.equal(outs[(k, 0)], outs[(k, 1)]), (M, k, (outs[(k, 0)] - outs[(k, 1)]).abs().max().item())
-            assert torch.equal(outs[("eval", 1)], outs[("train", 1)])
+            assert torch.equal(outs[("eval", 0)], outs[("train", 0)])
             assert torch.equal(outs[("eval", 2)], outs[("train", 2)])
             for k in ("eval", "train"):
-                torch.testing.assert_close(outs[(k, 2)], outs[(k, 1)], rtol=1e-4, atol=1e-5)
+                torch.testing.assert_close(outs[(k, 2)], outs[(k, 0)], rtol=1e-4, atol=1e-5)
             for k in ("grad", "dx"):
-                a, b = outs[(k, 2)], outs[(k, 1)]
+                a, b = outs[(k, 2)], outs[(k, 0)]
                 rel = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
                 assert rel < 2e-3, (M, k, rel)
     finally:
