@@ -242,6 +242,19 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[E], int lane) 
   }
 }
 
+// Merge-path split of two ascending shared-memory arrays: how many elements of A are among the first d outputs of the merge
+// (A goes first on ties).  Every lane of a warp takes an equal slice of the merged sequence, so the merge loops below run
+// the same number of iterations in all lanes (the per-element binary searches / stepping loops they replace ran as long as
+// the unluckiest lane: 18 % + 14 % of the kernel's instructions and its largest stall sites, profiles/r02_hier_v3_lines.md).
+__device__ __forceinline__ int merge_path_split(const float* A, int na, const float* Bm, int nbm, int d) {
+  int lo = max(0, d - nbm), hi = min(d, na);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (A[mid] <= Bm[d - mid - 1]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // ascending sort of E registers (odd-even transposition network, E <= 8)
 template <int E>
 __device__ __forceinline__ void sort_regs(float (&v)[E]) {
@@ -264,14 +277,12 @@ __device__ __forceinline__ void sort_regs(float (&v)[E]) {
 //      bucket; what is left to order inside the buckets is done by two passes of an E-register sorting network over
 //      lane-contiguous windows (offset 0 and E / 2), and a vote -- any other distribution of caller-supplied draws
 //      falls through to the register bitonic network and stays correct, only slower;
-//   2. with ascending u the searchsorted index is non-decreasing: each lane inverts E CONSECUTIVE draws, the first by
-//      binary search, the rest by stepping from the previous index (same predicate #{cdf <= u}, so the indices are the
-//      ones torch.searchsorted(right=True) returns);
-//   3. a sample of bin `ind` lies between the mid-points around z[ind], so its rank among the coarse depths is ind or
-//      ind + 1: two compares (checked; a local walk keeps it exact in every rounding case);
-//   4. the samples come out ascending except for 1-ulp inversions at bin borders (fl(b + t (a - b)) may exceed a):
+//   2. with ascending u the searchsorted indices of ALL draws come out of one merge of the cdf knots with the draws
+//      (knots first on ties = the predicate #{cdf <= u} of torch.searchsorted(right=True)), split evenly over the lanes
+//      by merge-path partitioning; the interpolation then runs on E consecutive draws per lane;
+//   3. the samples come out ascending except for 1-ulp inversions at bin borders (fl(b + t (a - b)) may exceed a):
 //      checked with a vote, and only then sorted (register bitonic network, the first version's hot loop);
-//   5. the coarse depths find their slots by binary search over the ascending samples (Nc / 32 searches per lane).
+//   4. the final order is a second merge-path merge, of the coarse depths with the ascending samples.
 // Values are those of sort(cat(z, samples)) bit for bit.  INDS (tests): also returns the searchsorted index of every draw
 // in the caller's order; that variant ranks inside the buckets exactly (value, slot) so the permutation is known.
 template <int E, bool INDS>
@@ -410,33 +421,41 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
     }
     __syncwarp();
     warp_build_cdf(s_w, s_cdf, nb, lane);
-    // ---- 2. inversion of E consecutive ascending draws per lane ----
+    // ---- 2. inversion: ind_j = #{k : cdf[k] <= u_j} for all draws by ONE merge of the cdf knots with the ascending draws ----
+#pragma unroll
+    for (int e = 0; e < E; ++e) s_u[lane * E + e] = uq[e];
+    __syncwarp();
+    {
+      const int total = nb + Nf, per = (total + 31) >> 5;
+      const int d0 = min(lane * per, total), d1 = min(d0 + per, total);
+      int ai = merge_path_split(s_cdf, nb, s_u, Nf, d0), bi = d0 - ai;
+      float ah = ai < nb ? s_cdf[ai] : CUDART_INF_F, bh = bi < Nf ? s_u[bi] : CUDART_INF_F;
+      for (int d = d0; d < d1; ++d) {
+        if (bi >= Nf || (ai < nb && ah <= bh)) {
+          ++ai;
+          ah = ai < nb ? s_cdf[ai] : CUDART_INF_F;
+        } else {
+          s_cnt[bi] = ai;                      // searchsorted(right=True) index of draw bi (bucket starts are dead by now)
+          ++bi;
+          bh = bi < Nf ? s_u[bi] : CUDART_INF_F;
+        }
+      }
+    }
+    __syncwarp();
     float v[E];
-    int cind[E];                              // searchsorted index of each draw: the starting guess of its rank among z
-    int ind = 0;
-    bool have = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int j = lane * E + e;
       v[e] = CUDART_INF_F;
-      cind[e] = 0;
       if (j < Nf) {
         const float x = uq[e];
-        if (!have) {
-          int lo = 0, hi = nb;
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cdf[mid] <= x) lo = mid + 1; else hi = mid; }
-          ind = lo;
-          have = true;
-        } else {
-          while (ind < nb && s_cdf[ind] <= x) ++ind;   // ascending draws: a step or two from the previous index
-        }
+        const int ind = s_cnt[j];
         const int below = max(ind - 1, 0), above = min(ind, nb - 1);
         const float cb = s_cdf[below], ca = s_cdf[above], bb = s_bins[below], ba = s_bins[above];
         float denom = __fsub_rn(ca, cb);
         if (denom < 1e-5f) denom = 1.0f;
         const float t = __fdiv_rn(__fsub_rn(x, cb), denom);
         v[e] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                 // rays.py:259-277
-        cind[e] = ind;
         if (INDS) inds_out[b * Nf + s_id[j]] = ind;
       }
     }
@@ -452,28 +471,23 @@ sample_hierarchical_kernel(const float* __restrict__ ro, const float* __restrict
 #pragma unroll
     for (int e = 0; e < E; ++e) s_smp[lane * E + e] = v[e];
     __syncwarp();
-    // ---- 3. rank merge (rays.py:328: sort of the concatenation, values only) ----
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int j = lane * E + e;
-      if (j < Nf) {
-        const float sj = v[e];
-        // #{coarse <= sj}: the sample's bin puts it next to z[ind] -> ind or ind + 1; verified, walked otherwise
-        int c = min(cind[e], Nc - 1);
-        c += (s_z[c] <= sj) ? 1 : 0;
-        const bool fine_ = (c == Nc || s_z[c] > sj) && (c == 0 || s_z[c - 1] <= sj);
-        if (!fine_) {
-          while (c < Nc && s_z[c] <= sj) ++c;
-          while (c > 0 && s_z[c - 1] > sj) --c;
+    // ---- 3. merge of the coarse depths with the ascending samples (rays.py:328: sort of the concatenation, values only) ----
+    {
+      const int per = (Nt + 31) >> 5;
+      const int d0 = min(lane * per, Nt), d1 = min(d0 + per, Nt);
+      int ai = merge_path_split(s_z, Nc, s_smp, Nf, d0), bi = d0 - ai;
+      float ah = ai < Nc ? s_z[ai] : CUDART_INF_F, bh = bi < Nf ? s_smp[bi] : CUDART_INF_F;
+      for (int d = d0; d < d1; ++d) {
+        if (bi >= Nf || (ai < Nc && ah <= bh)) {
+          s_out[d] = ah;
+          ++ai;
+          ah = ai < Nc ? s_z[ai] : CUDART_INF_F;
+        } else {
+          s_out[d] = bh;
+          ++bi;
+          bh = bi < Nf ? s_smp[bi] : CUDART_INF_F;
         }
-        s_out[j + c] = sj;
       }
-    }
-    for (int i = lane; i < Nc; i += 32) {
-      const float zi = s_z[i];
-      int lo = 0, hi = Nf;                    // #{samples < zi}
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_smp[mid] < zi) lo = mid + 1; else hi = mid; }
-      s_out[i + lo] = zi;
     }
     __syncwarp();
     float* zrow = z_all + b * Nt;
