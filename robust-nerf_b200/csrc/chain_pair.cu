@@ -115,7 +115,7 @@ struct PairParams {
 // launching stream before each launch.  Every lane of an epilogue warp needs the SAME values: read through the
 // constant cache they cost no LSU/L1 cycles (a uniform LDG.128 per 4 columns made the load/store unit -- shared with the
 // tensor core's operand reads -- the bottleneck of the epilogue, profiles/r01_pair_experiments.md; reading the head
-// weights with warp-uniform __ldg instead cost +10 % of the training forward, profiles/r02_ab_consts.md).
+// weights with warp-uniform __ldg instead cost +10 % of the training forward, profiles/r02_ab_log.md).
 //
 // The staging area is NOT one global: it is kConstSlots slots keyed by the packed-weight buffer (acquire_const_slot
 // below), so forwards of different networks -- coarse and fine overlapped on two streams, an evaluation render beside a
@@ -520,7 +520,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     // One warp per tile slot (warp 18, the store warp of the training kernel, <-> slot 0; warp 19 <-> slot 1; 640 threads
     // keep the 96-register budget -- at 672 ptxas sizes for 768 and squeezes the epilogue into 80): a tile costs one warp ~11,000 cycles and both
     // slots' buffers come free within one layer of each other, so a single warp encoding them back to back delivered the
-    // second one late (first build: render 1.5 % SLOWER than with the separate encode kernel, profiles/r02_pe_fused.md).
+    // second one late (first build: render 1.5 % SLOWER than with the separate encode kernel, profiles/r02_ab_log.md).
     // Same barrier protocol as the TMA-loaded side chunk: wait until layer 5's MMAs of the previous tile in this slot have
     // read the buffer (aux_empty), write the tile in the SWIZZLE_128B K-major layout, make it visible to the tensor core
     // (fence.proxy.async), arrive on the leader's aux_full (count 2: one per CTA).  The buffer is free from layer 5 on
@@ -534,9 +534,9 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
       ++j;
       uint8_t* tile = s_aux + slot * kAuxBytes;
       const int64_t row0 = ((int64_t)(grp * 2 + slot) * 2 + rank) * 128;
-      // Deliberately ROLLED (one frequency per iteration, 2-byte stores): the unrolled version (63 features in registers,
-      // eight 16-byte stores) is ~1,500 instructions of straight-line code that shares the instruction cache of its SM
-      // partition with the epilogue loop -- the stage that paces the kernel (profiles/r02_pe_fused.md).
+      // Rolled (one frequency per iteration, 2-byte stores): ~340 SASS instructions instead of ~1,500 of straight-line
+      // code next to the epilogue loop that paces the kernel; measured neutral against the unrolled version
+      // (profiles/r02_ab_log.md, block 8), kept for its size.
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
         const int r = i * 32 + lane;                 // lanes of a quarter warp hit eight different 16-byte columns

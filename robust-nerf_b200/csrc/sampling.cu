@@ -245,7 +245,7 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[E], int lane) 
 // Merge-path split of two ascending shared-memory arrays: how many elements of A are among the first d outputs of the merge
 // (A goes first on ties).  Every lane of a warp takes an equal slice of the merged sequence, so the merge loops below run
 // the same number of iterations in all lanes (the per-element binary searches / stepping loops they replace ran as long as
-// the unluckiest lane: 18 % + 14 % of the kernel's instructions and its largest stall sites, profiles/r02_hier_v3_lines.md).
+// the unluckiest lane: 25 % of the kernel's instructions and its two largest stall sites, profiles/r02_ncu_hier_v3.md).
 __device__ __forceinline__ int merge_path_split(const float* A, int na, const float* Bm, int nbm, int d) {
   int lo = max(0, d - nbm), hi = min(d, na);
   while (lo < hi) {
