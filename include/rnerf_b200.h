@@ -212,6 +212,22 @@ int rn_gemm_bf16(int mode, const void* A, int64_t lda, const void* B, int64_t ld
                  rn_stream_t stream);
 size_t rn_gemm_scratch_bytes(void);
 
+/* ---- one-call evaluation render (rendering.py:119-323 with is_train=False; train.py:122-160, inference.py:76-105) ---- */
+/* Renders the rays [ray_begin, ray_end) of one view in tiles of `tile_rays`, dealing tiles round-robin: this call renders
+ * tiles tile_first, tile_first + tile_step, ... (rank r of n: tile_first = r, tile_step = n; no collective).  Rays come
+ * from the camera (`pose`: DEVICE 4x4 c2w; pixel (u, v) = (i % W, i / W), rays.py:17-99) or are given (rays_o / rays_d
+ * [ray_end - ray_begin, 3], pose NULL).  z_base [Nc] and u_det [Nf] are the reference's linspace rows (rays.py:185-192,
+ * 252), built once by the caller.  packed_fine NULL or Nf = 0: coarse only.  Outputs are indexed by ray - ray_begin; rays
+ * of tiles this call does not own are left untouched.  workspace: rn_render_workspace_bytes(tile_rays, Nc, Nf).
+ * *rays_rendered_host (optional, HOST) receives the number of rays rendered.  Nine launches per tile, no synchronisation. */
+size_t rn_mlp_infer_workspace_bytes(int64_t M, int dir_group);
+size_t rn_render_workspace_bytes(int64_t tile_rays, int Nc, int Nf);
+int rn_render_view(const void* packed_coarse, const void* packed_fine, const float* pose, const float* rays_o, const float* rays_d,
+                   int H, int W, float focal, float cx, float cy, int64_t ray_begin, int64_t ray_end, int64_t tile_rays,
+                   int tile_first, int tile_step, const float* z_base, int Nc, const float* u_det, int Nf, int white_background,
+                   void* workspace, float* rgb_out /*[n,3]*/, float* depth_out /*[n] or NULL*/, float* acc_out /*[n] or NULL*/,
+                   int64_t* rays_rendered_host, rn_stream_t stream);
+
 /* ---- optimiser tail (train.py:115-117, train_pose_opt.py:398-409): clip_grad_norm_ + Adam ---- */
 /* One launch pair over a flat fp32 parameter/gradient/moment buffer.  `norm_groups` partitions the
  * buffer into ranges clipped independently (joint clip = 1 group; pose-opt = one group per net). */

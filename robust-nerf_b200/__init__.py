@@ -10,6 +10,7 @@ from .rays import (get_ray_directions, get_rays, get_rays_batch, sample_along_ra
                    sample_hierarchical)
 from .pose import CameraPoseParameters
 from .data_pose_opt import PixelBatch, PixelDataset, PixelSampler, create_pixel_dataset
+from .data import RayDataset, RaySampler
 from .train import (train_step, train_step_with_poses, render_image, render_image_with_pose, compute_psnr,
                     Trainer, render_views_sharded)
 from .synthetic import BlenderData, make_scene, lego_poses, hemisphere_poses, add_noise_to_poses
@@ -21,7 +22,7 @@ __all__ = [
     "NeRFConfig", "ModelConfig", "RenderConfig", "DataConfig", "TrainConfig", "PoseOptConfig",
     "NeRF", "PositionalEncoding", "create_nerf", "NeRFRenderer", "render_rays", "raw2outputs",
     "get_ray_directions", "get_rays", "get_rays_batch", "sample_along_rays", "sample_pdf", "sample_hierarchical",
-    "CameraPoseParameters", "PixelBatch", "PixelDataset", "PixelSampler", "create_pixel_dataset",
+    "CameraPoseParameters", "PixelBatch", "PixelDataset", "PixelSampler", "create_pixel_dataset", "RayDataset", "RaySampler",
     "train_step", "train_step_with_poses", "render_image", "render_image_with_pose", "compute_psnr", "Trainer",
     "render_views_sharded", "BlenderData", "make_scene", "lego_poses", "hemisphere_poses", "add_noise_to_poses",
     "image_metrics", "compute_ssim", "compute_mse",

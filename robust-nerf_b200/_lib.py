@@ -62,6 +62,10 @@ _SIGS = {
     "rn_mlp_packed_weight_bytes": (c_size_t, []),
     "rn_mlp_pack_weights": (c_int, [POINTER(c_void_p), _P, _P]),
     "rn_mlp_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "rn_mlp_infer_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "rn_render_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "rn_render_view": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, c_float, c_int64, c_int64, c_int64, c_int, c_int,
+                               _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, POINTER(c_int64), _P]),
     "rn_mlp_fwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, _P, _P]),
     "rn_mlp_bwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P]),
     "rn_head_act_fwd": (c_int, [_P, c_int64, _P, _P, _P]),

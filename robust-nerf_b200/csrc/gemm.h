@@ -58,6 +58,11 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
 
 // inference: per-ray view-direction projection dirvec[R][128] (encode.cu: dir_bias_kernel)
 int launch_dir_bias(const float* dirs, int64_t R, const void* packed, float* dirvec, cudaStream_t st);
+// inference forward of one network (mlp.cu) and the per-view ray generator (raygen.cu), used by render.cu
+size_t mlp_infer_workspace_bytes(int64_t M, int group);
+int mlp_infer(const void* packed, const float* pts, const float* dirs, int64_t M, int group, void* ws, float* raw, cudaStream_t st);
+int launch_view_rays(const float* pose, int W, float focal, float cx, float cy, int64_t ray0, int64_t B, float* ro, float* rd,
+                     float* vd, cudaStream_t st);
 int launch_encode(const float* pts, const float* dirs, int64_t M, int group, void* XC, int ldx, void* FD, int ldf, cudaStream_t st);
 size_t heads_bwd_scratch_bytes(int64_t M);
 int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,

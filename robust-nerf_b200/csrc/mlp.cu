@@ -37,7 +37,15 @@ constexpr int kTnLaunches = 10;      // weight-gradient launches per backward pa
 // inference: per-ray direction term of the view layer, [M / group][128] fp32 with group >= 64 (PE-fused chain)
 static size_t dirvec_bytes(int64_t M) { return align_up((size_t)(M / 64 + 1) * 128 * sizeof(float), 256); }
 
-static size_t workspace_bytes(int64_t M, int training) {
+extern int g_chain_fwd, g_pe_fused;
+static bool infer_fused(int64_t M, int group) {
+  return g_chain_fwd == 2 && g_pe_fused && pair_encode_supported(group) && M < (int64_t)0x7FFFFF00;
+}
+
+// group > 0: the caller knows the direction grouping, and when the PE-fused chain will take it the workspace is just
+// the per-ray direction term (8 B per point instead of 2,560)
+static size_t workspace_bytes(int64_t M, int training, int group = 0) {
+  if (!training && group > 0 && infer_fused(M, group)) return dirvec_bytes(M) + 256;
   const size_t elems = training ? (size_t)(kTrainFwdElems + kTrainBwdElems) : (size_t)kInferElems;
   size_t b = align_up((size_t)M * elems * 2, 256);
   if (!training) b += dirvec_bytes(M);
@@ -105,10 +113,10 @@ static int mlp_forward(const void* packed, const float* pts, const float* dirs, 
     HC = p;
     H[0] = HA; H[1] = HB; H[2] = HA; H[3] = HB; H[4] = XC + 64; H[5] = HA; H[6] = HB; H[7] = HA;
   }
-  const bool pe_fused = !training && g_chain_fwd == 2 && g_pe_fused && pair_encode_supported(group) && M < (int64_t)0x7FFFFF00;
+  const bool pe_fused = !training && infer_fused(M, group);
   float* dirvec = nullptr;
   if (pe_fused) {
-    dirvec = reinterpret_cast<float*>(align_up(reinterpret_cast<uintptr_t>(ws), 256) + align_up((size_t)M * kInferElems * 2, 256));
+    dirvec = reinterpret_cast<float*>(align_up(reinterpret_cast<uintptr_t>(ws), 256));      // the only workspace this path touches
     RN_TRY(launch_dir_bias(dirs, M / group, packed, dirvec, st));
   } else {
     RN_TRY(launch_encode(pts, dirs, M, group, XC, 320, FD, 320, st));
@@ -220,6 +228,14 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   return RN_OK;
 }
 
+// inference entry points for render.cu
+size_t mlp_infer_workspace_bytes(int64_t M, int group) { return M > 0 ? workspace_bytes(M, 0, group) : 0; }
+int mlp_infer(const void* packed, const float* pts, const float* dirs, int64_t M, int group, void* ws, float* raw, cudaStream_t st) {
+  if (M == 0) return RN_OK;
+  RN_TRY(check_arch());
+  return mlp_forward(packed, pts, dirs, M, group, ws, 0, raw, st);
+}
+
 }  // namespace rn
 
 using namespace rn;
@@ -237,6 +253,7 @@ int rn_set_flag(int flag, int value) {
 }
 
 size_t rn_mlp_workspace_bytes(int64_t M, int training) { return M > 0 ? workspace_bytes(M, training) : 0; }
+size_t rn_mlp_infer_workspace_bytes(int64_t M, int dir_group) { return mlp_infer_workspace_bytes(M, dir_group); }
 
 int rn_mlp_fwd(const void* packed, const float* pts, const float* dirs, int64_t M, int dir_group, void* workspace,
                int training, float* raw_out, rn_stream_t stream) {

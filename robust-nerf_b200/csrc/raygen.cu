@@ -185,6 +185,40 @@ __global__ void get_rays_kernel(const float* __restrict__ dirs, const float* __r
   }
 }
 
+// Rays of the flat pixel range [ray0, ray0 + B) of ONE view, straight from the camera (rays.py:17-99: direction of pixel
+// (u, v) = (i % W, i / W), rotated, normalised; origin = translation) plus the unit view direction render_rays derives
+// from them (rendering.py:165) -- no (H, W, 3) direction table, no per-view ray tensors.  With `pose == nullptr` only the
+// view directions of given rays are produced.
+__global__ void view_rays_kernel(const float* __restrict__ pose, int W, float focal, float cx, float cy, int64_t ray0, int64_t B,
+                                 float* __restrict__ ro, float* __restrict__ rd, float* __restrict__ vd) {
+  float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, t[3] = {0.f, 0.f, 0.f};
+  if (pose) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { R[i * 3] = pose[i * 4]; R[i * 3 + 1] = pose[i * 4 + 1]; R[i * 3 + 2] = pose[i * 4 + 2]; t[i] = pose[i * 4 + 3]; }
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    float d[3];
+    if (pose) {
+      const int64_t pix = ray0 + i;
+      float dir[3];
+      pixel_dir((float)(pix % W), (float)(pix / W), focal, cx, cy, dir);
+      rotate_normalise(R, dir, d);
+      rd[i * 3] = d[0]; rd[i * 3 + 1] = d[1]; rd[i * 3 + 2] = d[2];
+      ro[i * 3] = t[0]; ro[i * 3 + 1] = t[1]; ro[i * 3 + 2] = t[2];
+    } else {
+      d[0] = rd[i * 3]; d[1] = rd[i * 3 + 1]; d[2] = rd[i * 3 + 2];
+    }
+    const float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    vd[i * 3] = __fdiv_rn(d[0], n); vd[i * 3 + 1] = __fdiv_rn(d[1], n); vd[i * 3 + 2] = __fdiv_rn(d[2], n);
+  }
+}
+int launch_view_rays(const float* pose, int W, float focal, float cx, float cy, int64_t ray0, int64_t B, float* ro, float* rd,
+                     float* vd, cudaStream_t st) {
+  view_rays_kernel<<<grid_for(B, 256), 256, 0, st>>>(pose, W, focal, cx, cy, ray0, B, ro, rd, vd);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
 // fixed-order block reduction of NV values per thread; result valid in thread 0
 template <int NV, int THREADS>
 __device__ __forceinline__ void block_reduce_fixed(float (&v)[NV], float* smem /*[THREADS/32][NV]*/) {

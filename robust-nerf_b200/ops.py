@@ -377,7 +377,8 @@ class NeRFMLP(torch.autograd.Function):
         if M == 0:
             ctx.meta = None
             return raw
-        ws = torch.empty(L.lib().rn_mlp_workspace_bytes(M, int(training)), device=pts.device, dtype=torch.uint8)
+        nbytes = (L.lib().rn_mlp_workspace_bytes(M, 1) if training else L.lib().rn_mlp_infer_workspace_bytes(M, int(group)))
+        ws = torch.empty(nbytes, device=pts.device, dtype=torch.uint8)
         call("rn_mlp_fwd", ptr(packed), ptr(pts), ptr(dirs), M, int(group), ptr(ws), int(training), ptr(raw), stream_ptr())
         if training:
             ctx.save_for_backward(pts, dirs)
@@ -411,6 +412,42 @@ class NeRFMLP(torch.autograd.Function):
         grads = split_flat_grads(flat)
         grads = [g if ctx.needs_input_grad[n_in + i] else None for i, g in enumerate(grads)]
         return (g_pts, g_dirs, None, None, None, *grads)
+
+
+_render_ws = {}
+
+
+def render_view(model_coarse, model_fine, pose, H, W, focal, z_base, u_det, white_background=True, ray_begin=0, ray_end=None,
+                tile_rays=131072, tile_first=0, tile_step=1, rays_o=None, rays_d=None, out=None, want_depth_acc=True):
+    """Evaluation render of (a tile-sharded part of) one view in ONE C-ABI call (`rn_render_view`): rays generated in-kernel
+    from `pose` (or given), coarse -> deterministic resampling -> fine, nine launches per tile, no Python tile loop.
+    Returns (rgb [n,3], depth [n] | None, acc [n] | None, rays_rendered); rows of tiles this call does not own are left as
+    they are in `out` (zeros when allocated here)."""
+    dev = (pose if pose is not None else rays_o).device
+    pc = model_coarse._packed.get(model_coarse.kernel_params())
+    pf = None if model_fine is None else model_fine._packed.get(model_fine.kernel_params())
+    Nc, Nf = int(z_base.numel()), (0 if (pf is None or u_det is None) else int(u_det.numel()))
+    if ray_end is None:
+        ray_end = H * W if pose is not None else rays_o.shape[0]
+    n = int(ray_end - ray_begin)
+    rgb = out if out is not None else torch.zeros((n, 3), device=dev)
+    depth = torch.zeros((n,), device=dev) if want_depth_acc else None
+    acc = torch.zeros((n,), device=dev) if want_depth_acc else None
+    tile = int(min(tile_rays, max(n, 1)))
+    key = (dev, tile, Nc, Nf)
+    ws = _render_ws.get(key)
+    if ws is None:
+        _render_ws.clear()                      # one cached workspace per device/shape: a different shape replaces it
+        ws = _render_ws[key] = torch.empty(L.lib().rn_render_workspace_bytes(tile, Nc, Nf), device=dev, dtype=torch.uint8)
+    done = ctypes.c_int64(0)
+    p = None if pose is None else _f32(pose, "pose")
+    ro = None if rays_o is None else _f32(rays_o, "rays_o")
+    rd = None if rays_d is None else _f32(rays_d, "rays_d")
+    call("rn_render_view", ptr(pc), ptr(pf), ptr(p), ptr(ro), ptr(rd), int(H), int(W), float(focal), W / 2.0, H / 2.0,
+         int(ray_begin), int(ray_end), tile, int(tile_first), int(tile_step), ptr(_f32(z_base, "z_base")), Nc,
+         ptr(None if u_det is None else _f32(u_det, "u_det")), Nf, int(white_background), ptr(ws), ptr(rgb), ptr(depth), ptr(acc),
+         ctypes.byref(done), stream_ptr())
+    return rgb, depth, acc, int(done.value)
 
 
 class HeadAct(torch.autograd.Function):

@@ -131,10 +131,40 @@ def train_step_with_poses(model_coarse: NeRF, model_fine: Optional[NeRF], camera
     return m
 
 
+_U_DET_CACHE = {}
+
+
+def _eval_rows(cfg: RenderConfig, device):
+    """The two linspace rows of an evaluation render (rays.py:185-192 base depths, rays.py:252 deterministic draws),
+    built with the reference's torch calls on this device, once."""
+    from .rays import _z_base
+    zb = _z_base(cfg.near, cfg.far, cfg.num_samples, False, device)
+    key = (int(cfg.num_samples_fine), str(device))
+    u = _U_DET_CACHE.get(key)
+    if u is None:
+        u = torch.linspace(0.0, 1.0, cfg.num_samples_fine, device=device)
+        if not torch.cuda.is_current_stream_capturing():
+            _U_DET_CACHE[key] = u
+    return zb, u
+
+
+def _fused_render_ok(model_coarse, model_fine) -> bool:
+    return isinstance(model_coarse, NeRF) and (model_fine is None or isinstance(model_fine, NeRF))
+
+
 @torch.no_grad()
 def render_image(renderer: NeRFRenderer, pose: torch.Tensor, H: int, W: int, focal: float,
                  chunk_size: int = 1024 * 4) -> Dict[str, torch.Tensor]:
-    """noisy_src/train.py:122-160 (results are chunk-invariant in eval mode; larger chunks are faster)."""
+    """noisy_src/train.py:122-160.  One C-ABI call (`rn_render_view`): the rays are generated from the pose inside it and
+    the image is rendered in tiles without a Python loop; `chunk_size` is accepted for signature parity (results are
+    chunk-invariant in eval mode; the tile is max(chunk_size, 131072) rays)."""
+    cfg = renderer.config
+    mc, mf = renderer.model_coarse, (renderer.model_fine if cfg.use_hierarchical else None)
+    if _fused_render_ok(mc, mf):
+        zb, u = _eval_rows(cfg, pose.device)
+        rgb, depth, acc, _ = ops.render_view(mc, mf, pose, H, W, focal, zb, u if mf is not None else None,
+                                             white_background=cfg.white_background, tile_rays=max(int(chunk_size), 131072))
+        return {"rgb": rgb.reshape(H, W, 3), "depth": depth.reshape(H, W), "acc": acc.reshape(H, W)}
     directions = get_ray_directions(H, W, focal, device=pose.device)
     rays_o, rays_d = get_rays(directions, pose)
     out = renderer(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), chunk_size=chunk_size, is_train=False)
@@ -546,10 +576,25 @@ def render_views_sharded(model_coarse: NeRF, model_fine: Optional[NeRF], poses: 
     n_views = poses.shape[0]
     npix = H * W
     tiles_per_view = (npix + tile_rays - 1) // tile_rays
-    directions = get_ray_directions(H, W, focal, device=poses.device).reshape(-1, 3)
     if out is None:
         out = torch.zeros(n_views, npix, 3, device=poses.device)
+    mf = model_fine if render_config.use_hierarchical else None
     done = 0
+    if _fused_render_ok(model_coarse, mf):
+        # one C-ABI call per view: rays from the pose inside the call, this rank's tiles only (global tile id =
+        # (view + view_offset) * tiles_per_view + k, dealt round-robin: the first owned tile of a view and the stride follow)
+        zb, u = _eval_rows(render_config, poses.device)
+        poses = poses.contiguous()
+        for v in range(n_views):
+            first = (rank - (v + view_offset) * tiles_per_view) % world
+            if first >= tiles_per_view:
+                continue
+            _, _, _, n = ops.render_view(model_coarse, mf, poses[v], H, W, focal, zb, u if mf is not None else None,
+                                         white_background=render_config.white_background, tile_rays=tile_rays,
+                                         tile_first=first, tile_step=world, out=out[v], want_depth_acc=False)
+            done += n
+        return {"rgb": out, "rays_rendered": done}
+    directions = get_ray_directions(H, W, focal, device=poses.device).reshape(-1, 3)
     for v in range(n_views):
         mine = tiles_for_rank(v + view_offset, tiles_per_view, rank, world)
         if not mine:

@@ -866,6 +866,83 @@ def test_trainer_state_dict_and_module_semantics(rn, dev):
     assert torch.allclose(g_chunked, mf.pts_linears[3].weight.grad, rtol=1e-5, atol=1e-9)
 
 
+def test_ray_sampler_matches_reference_tables(rn, dev):
+    """Clean-mode batches (noisy_src/data.py:160-321): the table-free RayDataset / RaySampler against the reference's
+    construction -- per-image get_rays over the whole direction grid, concatenated -- and its iteration semantics
+    (torch.randperm per epoch, consecutive slices, short last batch, sample_batch = randint with replacement)."""
+    H, W, n = 12, 16, 5
+    data = rn.make_scene(H, W, n, seed=3, device=dev)
+    ds = rn.RayDataset(data)
+    dirs = rn.get_ray_directions(H, W, data.focal, device=dev)
+    ref_o, ref_d = [], []
+    for i in range(n):
+        ro, rd = rn.get_rays(dirs, data.poses[i])
+        ref_o.append(ro.reshape(-1, 3)); ref_d.append(rd.reshape(-1, 3))
+    ref_o, ref_d, ref_c = torch.cat(ref_o), torch.cat(ref_d), data.images.reshape(-1, 3)
+    assert len(ds) == n * H * W
+    assert torch.equal(ds.rays_o, ref_o) and torch.equal(ds.rays_d, ref_d) and torch.equal(ds.colors, ref_c)
+    item = ds[37]
+    assert torch.equal(item["rays_d"], ref_d[37]) and torch.equal(item["target_rgb"], ref_c[37])
+    sampler = rn.RaySampler(ds, batch_size=64, shuffle=True)
+    assert len(sampler) == (n * H * W + 63) // 64
+    torch.manual_seed(11)
+    seen, batches = [], 0
+    for batch in sampler:
+        idx = sampler.indices[sampler.current_idx - batch["rays_o"].shape[0]:sampler.current_idx]
+        assert torch.equal(batch["rays_o"], ref_o[idx]) and torch.equal(batch["rays_d"], ref_d[idx])
+        assert torch.equal(batch["target_rgb"], ref_c[idx])
+        seen.append(idx); batches += 1
+    seen = torch.cat(seen)
+    assert batches == len(sampler) and torch.equal(torch.sort(seen)[0], torch.arange(n * H * W, device=dev))   # one epoch = every ray once
+    torch.manual_seed(11)
+    assert torch.equal(torch.randperm(n * H * W, device=dev), seen)                                             # the reference's permutation
+    torch.manual_seed(5)
+    b = sampler.sample_batch()
+    torch.manual_seed(5)
+    idx = torch.randint(0, n * H * W, (64,), device=dev)
+    assert torch.equal(b["rays_d"], ref_d[idx])
+    # uint8 image storage and noisy poses (fixed-noise training runs): colours identical, poses perturbed
+    q = rn.ops.dequantize_images(torch.round(data.images * 255).clamp(0, 255).to(torch.uint8))      # exact k / 255
+    data8 = rn.BlenderData(images=q, poses=data.poses, H=H, W=W, focal=data.focal)
+    ds8 = rn.RayDataset(data8, uint8_images=True, noise_config=rn.NoiseConfig(5.0, 0.0, 5.0, seed=42))
+    assert ds8.images.dtype == torch.uint8 and torch.equal(ds8.colors, rn.ops.dequantize_images(ds8.images).reshape(-1, 3))
+    assert len(ds8.noise_info) == n and not torch.equal(ds8.poses, data.poses)
+
+
+def test_one_call_view_render(rn, dev):
+    """`rn_render_view` (rays generated from the pose inside the call, tiles without a Python loop, round-robin tile
+    ownership) against the Python path: get_ray_directions -> get_rays -> NeRFRenderer(..., is_train=False)."""
+    from robust_nerf_b200 import ops
+    from robust_nerf_b200.train import _eval_rows
+    nc, nf = _two_nets(rn, dev)
+    cfg = rn.RenderConfig()
+    H, W = 37, 53
+    focal = rn.synthetic.focal_from_fov(W)
+    pose = rn.lego_poses(dev)[4].contiguous()
+    dirs = rn.get_ray_directions(H, W, focal, device=dev)
+    with torch.no_grad():
+        ro, rd = rn.get_rays(dirs, pose)
+        ref = rn.NeRFRenderer(nc, nf, cfg)(ro.reshape(-1, 3), rd.reshape(-1, 3), chunk_size=4096, is_train=False)
+        img = rn.render_image(rn.NeRFRenderer(nc, nf, cfg), pose, H, W, focal)
+    for k_img, k_ref in (("rgb", "rgb_fine"), ("depth", "depth_fine"), ("acc", "acc_fine")):
+        torch.testing.assert_close(img[k_img].reshape(ref[k_ref].shape), ref[k_ref], rtol=1e-5, atol=2e-6)
+    zb, u = _eval_rows(cfg, dev)
+    # ragged tiles + two "ranks": each call fills only its own tiles, together they fill the image
+    parts, total = [], 0
+    for r in range(2):
+        rgb, _, _, n = ops.render_view(nc, nf, pose, H, W, focal, zb, u, tile_rays=300, tile_first=r, tile_step=2)
+        parts.append(rgb); total += n
+    assert total == H * W
+    assert ((parts[0] != 0).any(-1) & (parts[1] != 0).any(-1)).sum().item() == 0          # disjoint ownership
+    torch.testing.assert_close(parts[0] + parts[1], ref["rgb_fine"], rtol=1e-5, atol=2e-6)
+    # given rays instead of a pose, a sub-range, coarse only
+    rgb, depth, acc, n = ops.render_view(nc, None, None, H, W, focal, zb, None, rays_o=ro.reshape(-1, 3)[100:900].contiguous(),
+                                         rays_d=rd.reshape(-1, 3)[100:900].contiguous(), tile_rays=256)
+    assert n == 800
+    torch.testing.assert_close(rgb, ref["rgb_coarse"][100:900], rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(acc, ref["acc_coarse"][100:900], rtol=1e-5, atol=2e-6)
+
+
 def test_trainer_cuda_graph_step(rn, dev):
     """The CUDA-graph replayed step trains like the eager step (same kernels; only the Philox offsets differ)."""
     data, ds, sampler, pb = _scene_batch(rn, dev, 512, seed=21)
