@@ -220,6 +220,8 @@ size_t rn_gemm_scratch_bytes(void);
  * 252), built once by the caller.  packed_fine NULL or Nf = 0: coarse only.  Outputs are indexed by ray - ray_begin; rays
  * of tiles this call does not own are left untouched.  workspace: rn_render_workspace_bytes(tile_rays, Nc, Nf).
  * *rays_rendered_host (optional, HOST) receives the number of rays rendered.  Nine launches per tile, no synchronisation. */
+/* viewdirs = rays_d / |rays_d| (rendering.py:165), fp32, unfused multiply-adds */
+int rn_view_dirs(const float* rays_d /*[B,3]*/, int64_t B, float* viewdirs /*[B,3]*/, rn_stream_t stream);
 size_t rn_mlp_infer_workspace_bytes(int64_t M, int dir_group);
 size_t rn_render_workspace_bytes(int64_t tile_rays, int Nc, int Nf);
 int rn_render_view(const void* packed_coarse, const void* packed_fine, const float* pose, const float* rays_o, const float* rays_d,

@@ -12,7 +12,7 @@ from .pose import CameraPoseParameters
 from .data_pose_opt import PixelBatch, PixelDataset, PixelSampler, create_pixel_dataset
 from .data import RayDataset, RaySampler
 from .train import (train_step, train_step_with_poses, render_image, render_image_with_pose, compute_psnr,
-                    Trainer, render_views_sharded)
+                    Trainer, render_views_sharded, evaluate)
 from .synthetic import BlenderData, make_scene, lego_poses, hemisphere_poses, add_noise_to_poses
 from .metrics import image_metrics, compute_ssim, compute_mse
 from .noise import NoiseConfig, set_noise_seed, draw_pose_noise, compute_pose_error, compute_pose_errors_batch
@@ -24,7 +24,7 @@ __all__ = [
     "get_ray_directions", "get_rays", "get_rays_batch", "sample_along_rays", "sample_pdf", "sample_hierarchical",
     "CameraPoseParameters", "PixelBatch", "PixelDataset", "PixelSampler", "create_pixel_dataset", "RayDataset", "RaySampler",
     "train_step", "train_step_with_poses", "render_image", "render_image_with_pose", "compute_psnr", "Trainer",
-    "render_views_sharded", "BlenderData", "make_scene", "lego_poses", "hemisphere_poses", "add_noise_to_poses",
+    "render_views_sharded", "evaluate", "BlenderData", "make_scene", "lego_poses", "hemisphere_poses", "add_noise_to_poses",
     "image_metrics", "compute_ssim", "compute_mse",
     "NoiseConfig", "set_noise_seed", "draw_pose_noise", "compute_pose_error", "compute_pose_errors_batch", "noise",
 ]

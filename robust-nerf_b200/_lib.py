@@ -63,6 +63,7 @@ _SIGS = {
     "rn_mlp_pack_weights": (c_int, [POINTER(c_void_p), _P, _P]),
     "rn_mlp_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "rn_mlp_infer_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "rn_view_dirs": (c_int, [_P, c_int64, _P, _P]),
     "rn_render_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "rn_render_view": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, c_float, c_int64, c_int64, c_int64, c_int, c_int,
                                _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, POINTER(c_int64), _P]),

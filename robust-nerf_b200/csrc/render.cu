@@ -50,6 +50,12 @@ using namespace rn;
 
 extern "C" {
 
+int rn_view_dirs(const float* rays_d, int64_t B, float* viewdirs, rn_stream_t stream) {
+  if (B == 0) return RN_OK;
+  RN_REQUIRE(rays_d && viewdirs && B > 0);
+  return launch_view_rays(nullptr, 1, 1.f, 0.f, 0.f, 0, B, nullptr, const_cast<float*>(rays_d), viewdirs, (cudaStream_t)stream);
+}
+
 size_t rn_render_workspace_bytes(int64_t tile_rays, int Nc, int Nf) {
   if (tile_rays <= 0 || Nc < 3 || Nf < 0) return 0;
   return carve_render(nullptr, tile_rays, Nc, Nf).total;

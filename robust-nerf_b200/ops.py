@@ -414,6 +414,14 @@ class NeRFMLP(torch.autograd.Function):
         return (g_pts, g_dirs, None, None, None, *grads)
 
 
+def view_dirs(rays_d):
+    """rays_d / |rays_d| (rendering.py:165) in one launch; no autograd (callers with a gradient use the aten expression)."""
+    rd = _f32(rays_d, "rays_d")
+    out = _empty(rd.shape, rd)
+    call("rn_view_dirs", ptr(rd), rd.numel() // 3, ptr(out), stream_ptr())
+    return out
+
+
 _render_ws = {}
 
 

@@ -56,7 +56,10 @@ def render_rays(model_coarse: NeRF, model_fine: Optional[NeRF], rays_o: torch.Te
     raw_noise_std = config.raw_noise_std if is_train else 0.0
     B = rays_o.shape[0]
     Nc = config.num_samples
-    viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)         # rendering.py:165 (B x 3 glue)
+    if torch.is_grad_enabled() and rays_d.requires_grad:
+        viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)     # rendering.py:165, differentiable (pose optimisation)
+    else:
+        viewdirs = ops.view_dirs(rays_d)                                 # same expression, one launch
     pts_c, z_c = R.sample_along_rays(rays_o, rays_d, config.near, config.far, Nc, perturb=perturb, t_rand=t_rand)
     out_c, is_raw = _run_net(model_coarse, pts_c.reshape(-1, 3), viewdirs, Nc)
     noise_c = torch.randn(B, Nc, device=rays_o.device) * raw_noise_std if raw_noise_std > 0.0 else None

@@ -566,6 +566,43 @@ class Trainer:
 
 
 @torch.no_grad()
+def evaluate(renderer: NeRFRenderer, val_data, num_images: int = 5, host_images: Optional[torch.Tensor] = None) -> Dict[str, object]:
+    """The numeric core of noisy_src/train.py:163-233 (`evaluate`; the logger and LPIPS stay with the caller): the first
+    `num_images` validation views rendered (one C-ABI call each), MSE / PSNR / SSIM of ALL of them in one metrics launch,
+    ONE device-to-host copy of the per-image values (the reference does three `.item()` round trips per image).
+    `host_images` (optional pinned (n, H, W, 3) tensor): the renders are copied into it asynchronously, each view's copy
+    overlapping the next view's render.  Keys follow ValidationMetrics: psnr, ssim, mse, per_image_psnr, per_image_ssim."""
+    from .metrics import image_metrics
+    n = min(num_images, val_data.images.shape[0])
+    H, W = int(val_data.H), int(val_data.W)
+    dev = val_data.poses.device
+    preds = torch.empty(n, H, W, 3, device=dev)
+    depths = []
+    copy_stream = torch.cuda.Stream(device=dev) if host_images is not None else None
+    for i in range(n):
+        out = render_image(renderer, val_data.poses[i], H, W, float(val_data.focal))
+        preds[i] = out["rgb"]
+        depths.append(out["depth"])
+        if host_images is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                host_images[i].copy_(preds[i], non_blocking=True)
+    target = val_data.images[:n]
+    if target.dtype == torch.uint8:
+        target = ops.dequantize_images(target)
+    m = image_metrics(preds, target.to(dev, torch.float32))
+    vals = torch.stack([m["mse"], m["psnr"], m["ssim"]]).cpu()             # the one synchronising copy
+    if copy_stream is not None:
+        copy_stream.synchronize()
+    mse, psnr, ssim = vals[0].tolist(), vals[1].tolist(), vals[2].tolist()
+    mean = lambda x: float(sum(x) / max(len(x), 1))
+    return {"psnr": mean(psnr), "ssim": mean(ssim), "mse": mean(mse), "lpips": None, "per_image_psnr": psnr,
+            "per_image_ssim": ssim, "pred": preds, "depth": depths}
+
+
+@torch.no_grad()
 def render_views_sharded(model_coarse: NeRF, model_fine: Optional[NeRF], poses: torch.Tensor, H: int, W: int, focal: float,
                          render_config: RenderConfig, tile_rays: int = 32768, rank: int = 0, world: int = 1,
                          out: Optional[torch.Tensor] = None, view_offset: int = 0) -> Dict[str, torch.Tensor]:

@@ -943,6 +943,24 @@ def test_one_call_view_render(rn, dev):
     torch.testing.assert_close(acc, ref["acc_coarse"][100:900], rtol=1e-5, atol=2e-6)
 
 
+def test_evaluate_loop(rn, dev):
+    """train.py:163-233 `evaluate`: batched metrics of the rendered validation views against the per-image reference-style
+    calls, and the asynchronous copy of the renders to pinned host memory."""
+    nc, nf = _two_nets(rn, dev)
+    H, W = 40, 48
+    data = rn.make_scene(H, W, 4, seed=5, device=dev)
+    renderer = rn.NeRFRenderer(nc, nf, rn.RenderConfig())
+    host = torch.empty(3, H, W, 3).pin_memory()
+    m = rn.evaluate(renderer, data, num_images=3, host_images=host)
+    assert len(m["per_image_psnr"]) == 3 and m["lpips"] is None
+    for i in range(3):
+        img = rn.render_image(renderer, data.poses[i], H, W, data.focal)["rgb"]
+        assert torch.equal(img, m["pred"][i]) and torch.equal(host[i], img.cpu())
+        np.testing.assert_allclose(m["per_image_psnr"][i], float(rn.metrics.compute_psnr(img, data.images[i])), rtol=1e-6)
+        np.testing.assert_allclose(m["per_image_ssim"][i], float(rn.compute_ssim(img, data.images[i])), rtol=1e-6)
+    np.testing.assert_allclose(m["psnr"], np.mean(m["per_image_psnr"]), rtol=1e-6)
+
+
 def test_trainer_cuda_graph_step(rn, dev):
     """The CUDA-graph replayed step trains like the eager step (same kernels; only the Philox offsets differ)."""
     data, ds, sampler, pb = _scene_batch(rn, dev, 512, seed=21)
