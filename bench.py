@@ -555,9 +555,6 @@ def run_gpu(args):
     import robust_nerf_b200 as rn
     from robust_nerf_b200 import _lib
     lib = _lib.lib()
-    for kv in filter(None, os.environ.get("RN_FLAGS", "").split(",")):      # A/B of kernel variants: RN_FLAGS="4=0,..."
-        k, v = kv.split("=")
-        lib.rn_set_flag(int(k), int(v))
 
     # ---- synthetic scene: 100 views 800x800, random images, lego camera layout ----
     H = W = 800

@@ -95,6 +95,11 @@ def lib():
             fn = getattr(handle, name)      # AttributeError if the .so does not export it
             fn.restype, fn.argtypes = res, args
         _lib = handle
+        # RN_FLAGS="4=0,5=1": kernel-variant flags applied at load time (A/B timing and running the test suite under a
+        # variant; see rn_set_flag in csrc/mlp.cu)
+        for kv in filter(None, os.environ.get("RN_FLAGS", "").split(",")):
+            k, v = kv.split("=")
+            check(handle.rn_set_flag(int(k), int(v)), f"rn_set_flag({kv})")
     return _lib
 
 

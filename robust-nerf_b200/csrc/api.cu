@@ -6,6 +6,7 @@
 namespace rn {
 
 int g_last_cuda_error = 0;
+int g_pdl = 0;
 unsigned long long g_launch_count = 0;
 
 int num_sms() {

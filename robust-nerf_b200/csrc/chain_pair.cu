@@ -261,6 +261,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int l = 0; l < p.n_layers; ++l) { prefetch_tmap(&p.tmB[l]); if (TRAIN) prefetch_tmap(&p.tmD[l]); }
@@ -278,6 +279,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
   __syncthreads();
   cluster_sync_all();                    // both CTAs' barriers exist before any remote arrive / multicast commit
   tcgen05_fence_after();
+  pdl_wait();                            // PDL: everything below reads what earlier kernels wrote
   const uint32_t tmem_base = *tmem_slot;
   const int n_groups = (p.n_ptiles + 1) >> 1;
 
@@ -632,6 +634,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int l = 0; l < p.n_layers; ++l) { prefetch_tmap(&p.tmB[l]); prefetch_tmap(&p.tmD[l]); }
@@ -650,6 +653,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
   __syncthreads();
   cluster_sync_all();
   tcgen05_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int n_groups = (p.n_ptiles + 1) >> 1;
 
@@ -911,7 +915,7 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   g_prof_next_flops = flops;
   int slot;
   prof_begin(1 /*MODE_NN*/, st, &slot);
-  mlp_chain_pair_bwd_kernel<<<grid, kPairThreads, kPairSmem, st>>>(p);
+  RN_CUDA_CHECK(launch_maybe_pdl(mlp_chain_pair_bwd_kernel, dim3(grid), dim3(kPairThreads), kPairSmem, st, p));
   prof_end(slot, st);
   RN_LAUNCH_CHECK();
   return RN_OK;
@@ -1023,9 +1027,9 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
   g_prof_next_flops = flops;
   int slot;
   prof_begin(0 /*MODE_NT*/, st, &slot);
-  if (training) mlp_chain_pair_kernel<true, false><<<grid, kPairThreads, kPairSmem, st>>>(p);
-  else if (pe) mlp_chain_pair_kernel<false, true><<<grid, kPairThreadsPE, kPairSmem, st>>>(p);
-  else mlp_chain_pair_kernel<false, false><<<grid, kPairThreads, kPairSmem, st>>>(p);
+  if (training) RN_CUDA_CHECK(launch_maybe_pdl(mlp_chain_pair_kernel<true, false>, dim3(grid), dim3(kPairThreads), kPairSmem, st, p));
+  else if (pe) RN_CUDA_CHECK(launch_maybe_pdl(mlp_chain_pair_kernel<false, true>, dim3(grid), dim3(kPairThreadsPE), kPairSmem, st, p));
+  else RN_CUDA_CHECK(launch_maybe_pdl(mlp_chain_pair_kernel<false, false>, dim3(grid), dim3(kPairThreads), kPairSmem, st, p));
   prof_end(slot, st);
   RN_LAUNCH_CHECK();
   return RN_OK;

@@ -57,6 +57,26 @@ inline int grid_for(int64_t work_items, int threads, int ctas_per_sm = 8) {
   return (int)(g < 1 ? 1 : g);
 }
 
+// ---- programmatic dependent launch (PDL) ----
+// rn_set_flag(5, 1): the GEMM-family kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so a
+// kernel's CTAs may be scheduled (barrier init, TMEM allocation, tensor-map prefetch) as soon as the previous kernel's
+// CTAs leave their SMs, instead of after the whole grid has drained and a launch latency has passed.  Those kernels call
+// pdl_wait() before their first read of global memory (a no-op when launched without the attribute) and
+// pdl_launch_dependents() on entry.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- network geometry (reference default ModelConfig) ----
 constexpr int kHidden = 256;
 constexpr int kPosFreqs = 10, kDirFreqs = 4;

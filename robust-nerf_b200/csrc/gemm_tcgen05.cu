@@ -116,6 +116,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
 
   // ---------------- one-time setup ----------------
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     if (MODE != MODE_TN) prefetch_tmap(&tmD);
@@ -127,6 +128,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  pdl_wait();                                  // everything below reads what earlier kernels wrote
   if (warp >= 2 && warp < 6) {
     const int t = threadIdx.x - 64;
     if (MODE == MODE_NT) {
@@ -505,6 +507,8 @@ splitk_reduce_kernel(const float* __restrict__ partial, int m_tiles, int splits,
   splitk_reduce_block(partial, m_tiles, splits, BN, row0, nrows, col0, ncols, dst, dst_ld, colsum_dst, blockIdx.x);
 }
 __global__ void __launch_bounds__(256) splitk_reduce_batch_kernel(const __grid_constant__ TnBatch b) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = 0;
   while (i + 1 < b.n && (int)blockIdx.x >= b.d[i + 1].block0) ++i;
   const TnReduceDesc& d = b.d[i];
@@ -580,7 +584,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
                                        Cfg::kSmemBytes));
   int slot;
   prof_begin(MODE, st, &slot);
-  gemm_kernel<BN, MODE, HEADS, WMASK><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tA, tB, tD, args);
+  RN_CUDA_CHECK(launch_maybe_pdl(gemm_kernel<BN, MODE, HEADS, WMASK>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, tA, tB, tD, args));
   prof_end(slot, st);
   RN_LAUNCH_CHECK();
   return RN_OK;
@@ -708,7 +712,7 @@ int tn_batch_add(TnBatch* b, const TnInfo& info, int row0, int nrows, int col0, 
 }
 int gemm_tn_reduce_batch(const TnBatch& b, cudaStream_t st) {
   if (b.n == 0) return RN_OK;
-  splitk_reduce_batch_kernel<<<b.total_blocks, 256, 0, st>>>(b);
+  RN_CUDA_CHECK(launch_maybe_pdl(splitk_reduce_batch_kernel, dim3(b.total_blocks), dim3(256), 0, st, b));
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -249,6 +249,7 @@ int rn_set_flag(int flag, int value) {
 #endif
   if (flag == 3) { g_chain_bwd = value; return RN_OK; }
   if (flag == 4) { g_pe_fused = value; return RN_OK; }
+  if (flag == 5) { g_pdl = value ? 1 : 0; return RN_OK; }
   return RN_ERR_INVALID_ARG;
 }
 
