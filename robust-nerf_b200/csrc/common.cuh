@@ -62,7 +62,9 @@ inline int grid_for(int64_t work_items, int threads, int ctas_per_sm = 8) {
 // kernel's CTAs may be scheduled (barrier init, TMEM allocation, tensor-map prefetch) as soon as the previous kernel's
 // CTAs leave their SMs, instead of after the whole grid has drained and a launch latency has passed.  Those kernels call
 // pdl_wait() before their first read of global memory (a no-op when launched without the attribute) and
-// pdl_launch_dependents() on entry.
+// pdl_launch_dependents() on entry.  MEASURED (profiles/r02_ab_log.md, block 15): 1-3 % SLOWER for the training step --
+// the persistent kernels fill every SM until their last tile, so there is nothing to overlap and the early CTAs only add
+// scheduling work; the flag stays off.
 extern int g_pdl;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

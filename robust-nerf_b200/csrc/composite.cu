@@ -22,7 +22,11 @@ constexpr int kCompWarps = 8;
 #define RN_COMP_BWD12_BLOCKS 2      // resident CTAs asked of the 7..12-round training backward (A/B knob, scripts/ab_hbm.sh)
 #endif
 
-__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// Colour sigmoid of the raw (fused-head) input convention: the input is the bf16 tensor-core MLP's pre-activation (tolerance
+// regime 1e-2 max-abs RGB), so ex2.approx (relative error 2^-22) and a 1-ulp reciprocal are far inside it; three of the four
+// transcendentals per sample, and the kernel is issue-bound (85 % of issue slots at S = 384).  The transmittance exponential
+// keeps the accurate expf: alpha = 1 - exp(-x) cancels for small x and the fp32 contract on weights is 1e-5 relative.
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(__fadd_rn(1.0f, __expf(-x))); }
 
 // inclusive multiplicative scan over the warp
 __device__ __forceinline__ float warp_scan_mul(float v, int lane) {
@@ -69,7 +73,7 @@ template <bool RAW>
 __device__ __forceinline__ SampleIn activate_sample(const Fetched& f, bool has_noise, int s, int S, float nrm) {
   SampleIn o;
   if (RAW) {
-    o.c0 = sigmoidf_acc(f.a); o.c1 = sigmoidf_acc(f.b); o.c2 = sigmoidf_acc(f.c);                  // model.py:181,194
+    o.c0 = sigmoidf_fast(f.a); o.c1 = sigmoidf_fast(f.b); o.c2 = sigmoidf_fast(f.c);               // model.py:181,194
   } else {
     o.c0 = f.a; o.c1 = f.b; o.c2 = f.c;
   }
@@ -190,7 +194,7 @@ composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ si
         const bool valid = s < S;
         float t = 1.f;
         if (valid && LEAN) {
-          if (RAW) { c0[r] = sigmoidf_acc(c0[r]); c1[r] = sigmoidf_acc(c1[r]); c2[r] = sigmoidf_acc(c2[r]); }
+          if (RAW) { c0[r] = sigmoidf_fast(c0[r]); c1[r] = sigmoidf_fast(c1[r]); c2[r] = sigmoidf_fast(c2[r]); }
           const float dist = __fmul_rn(ds[r], nrm);                                                // rendering.py:75
           al[r] = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(sg[r], 0.f), dist)));
           t = __fadd_rn(__fsub_rn(1.0f, al[r]), 1e-10f);
@@ -297,7 +301,7 @@ composite_bwd_lean_kernel(const float* __restrict__ rgb, const float* __restrict
         const bool valid = FULL || s < S;
         float t = 1.f;
         if (valid) {
-          if (RAW) { c0[r] = sigmoidf_acc(c0[r]); c1[r] = sigmoidf_acc(c1[r]); c2[r] = sigmoidf_acc(c2[r]); }
+          if (RAW) { c0[r] = sigmoidf_fast(c0[r]); c1[r] = sigmoidf_fast(c1[r]); c2[r] = sigmoidf_fast(c2[r]); }
           const float sg = al[r];
           const float dist = __fmul_rn(ds[r], nrm);                                                // rendering.py:75
           al[r] = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(sg, 0.f), dist)));
