@@ -38,6 +38,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
 void prof_begin(int mode, cudaStream_t st, int* slot);
 void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
+extern int g_l2_hints;
 
 constexpr int kPairThreads = 608;         // 19 warps
 constexpr int kPairThreadsPE = 640;       // + one warp: with the (idle in inference) store warp, two encoder warps, one per tile slot
@@ -103,6 +104,7 @@ struct PairParams {
   int n_layers, n_ptiles;      // pair tiles of 256 rows
   int64_t m_rows;
   int const_slot;              // which slot of c_pair_consts2 holds this network's fp32 section
+  int l2_hints;                // rn_set_flag(6): weights evict_last, streamed activations evict_first
   float* raw;
   // PE-fused inference (mlp_chain_pair_kernel<false, true>): the kernel encodes the points itself and takes the view
   // branch's direction term as a per-ray bias of the last layer
@@ -289,6 +291,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
     const uint32_t aux_full_leader = mapa_u32(smem_u32(aux_full), 0);
     int s = 0; uint32_t ph = 0;
     uint32_t aux_n0 = 0, aux_n1 = 0;
+    const uint64_t pol_w = l2_policy(p.l2_hints ? 2 : 0), pol_s = l2_policy(p.l2_hints ? 1 : 0);
     RN_TL_DECL(tl, 3, lane == 0);
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
@@ -303,7 +306,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
               if RN_PDBG(p, 4) { if (rank == 0) mbar_arrive(&aux_full[slot]); }
               else {
                 if (rank == 0) mbar_arrive_expect_tx(&aux_full[slot], 2 * kAuxBytes);
-                tma_load_2d_pair(s_aux + slot * kAuxBytes, &p.tmAux[aux_load - 1], aux_full_leader + slot * 8, 0, row0);
+                tma_load_2d_pair_hint(s_aux + slot * kAuxBytes, &p.tmAux[aux_load - 1], aux_full_leader + slot * 8, 0, row0, pol_s);
               }
             }
             __syncwarp();
@@ -317,7 +320,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
               if RN_PDBG(p, 1) { if (rank == 0) mbar_arrive(&full_b[s]); }
               else {
                 if (rank == 0) mbar_arrive_expect_tx(&full_b[s], (uint32_t)n * 128u);
-                tma_load_2d_pair(s_b + s * kBStageBytes, &p.tmB[l], full_b_leader + s * 8, kc * 64, (int)rank * (n >> 1));
+                tma_load_2d_pair_hint(s_b + s * kBStageBytes, &p.tmB[l], full_b_leader + s * 8, kc * 64, (int)rank * (n >> 1), pol_w);
               }
             }
             __syncwarp();
@@ -498,6 +501,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
   } else if (warp == 18 && !PE) {
     // ---------------- store warp (training): activation tiles -> global for the backward pass ----------------
     if (TRAIN && lane == 0) {
+      const uint64_t pol_s = l2_policy(p.l2_hints ? 1 : 0);
       uint32_t it0 = 0, it1 = 0;
       for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
         const int tiles_here = min(2, p.n_ptiles - grp * 2);
@@ -508,7 +512,7 @@ mlp_chain_pair_kernel(const __grid_constant__ PairParams p) {
             const int row0 = ((grp * 2 + slot) * 2 + (int)rank) * 128;
             mbar_wait(&staged[slot], i & 1u);
             for (int c = 0; c < chunks; ++c)
-              tma_store_2d(&p.tmD[l], s_act + slot * kActBytes + c * kChunkBytes, c * 64, row0);
+              tma_store_2d_hint(&p.tmD[l], s_act + slot * kActBytes + c * kChunkBytes, c * 64, row0, pol_s);
             tma_store_commit();
             tma_store_wait_read0();
             mbar_arrive(&store_done[slot]);
@@ -607,6 +611,7 @@ struct BwdParams {
   BwdLayer L[kPairMaxLayers];
   int n_layers, n_ptiles;
   int64_t m_rows;
+  int l2_hints;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
@@ -664,6 +669,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
     const uint32_t act_full_leader = mapa_u32(smem_u32(act_full), 0);
     int s = 0; uint32_t ph = 0;
     uint32_t aux_n0 = 0, aux_n1 = 0, in_n0 = 0, in_n1 = 0;
+    const uint64_t pol_w = l2_policy(p.l2_hints ? 2 : 0), pol_s = l2_policy(p.l2_hints ? 1 : 0);
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int tiles_here = min(2, p.n_ptiles - grp * 2);
       for (int l = 0; l < p.n_layers; ++l) {
@@ -680,7 +686,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
             if (elect_one()) {
               if (rank == 0) mbar_arrive_expect_tx(&act_full[slot], (uint32_t)(2 * act_chunks * kChunkBytes));
               for (int c = 0; c < act_chunks; ++c)
-                tma_load_2d_pair(s_act + slot * kActBytes + c * kChunkBytes, &p.tmIn, act_full_leader + slot * 8, c * 64, row0);
+                tma_load_2d_pair_hint(s_act + slot * kActBytes + c * kChunkBytes, &p.tmIn, act_full_leader + slot * 8, c * 64, row0, pol_s);
             }
             __syncwarp();
           }
@@ -689,7 +695,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
             if (j > 0) mbar_wait(&aux_empty[slot], (j - 1) & 1u);
             if (elect_one()) {
               if (rank == 0) mbar_arrive_expect_tx(&aux_full[slot], 2 * kAuxBytes);
-              tma_load_2d_pair(s_aux + slot * kAuxBytes, &p.tmAux, aux_full_leader + slot * 8, aux_col, row0);
+              tma_load_2d_pair_hint(s_aux + slot * kAuxBytes, &p.tmAux, aux_full_leader + slot * 8, aux_col, row0, pol_s);
             }
             __syncwarp();
           }
@@ -701,8 +707,8 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
               // this CTA's half of the 256 output columns: two [64 k rows][64 columns] boxes
               uint8_t* dst = s_b + s * kBStageBytes;
               const int c0 = n_off + (int)rank * 128;
-              tma_load_2d_pair(dst, &p.tmB[l], full_b_leader + s * 8, c0, kc * 64);
-              tma_load_2d_pair(dst + 8192, &p.tmB[l], full_b_leader + s * 8, c0 + 64, kc * 64);
+              tma_load_2d_pair_hint(dst, &p.tmB[l], full_b_leader + s * 8, c0, kc * 64, pol_w);
+              tma_load_2d_pair_hint(dst + 8192, &p.tmB[l], full_b_leader + s * 8, c0 + 64, kc * 64, pol_w);
             }
             __syncwarp();
             if (++s == kNBStages) { s = 0; ph ^= 1; }
@@ -834,6 +840,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
   } else if (warp == 18) {
     // ---------------- store warp: every layer's data gradient goes to global for the weight-gradient GEMMs ----------------
     if (lane == 0) {
+      const uint64_t pol_s = l2_policy(p.l2_hints ? 1 : 0);
       uint32_t it0 = 0, it1 = 0;
       RN_TL_DECL(tl, 3, true);
       for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
@@ -845,7 +852,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
             mbar_wait(&staged[slot], i & 1u);
             RN_TL(tl, 3300 + l * 10 + slot);
             for (int c = 0; c < 4; ++c)
-              tma_store_2d(&p.tmD[l], s_act + slot * kActBytes + c * kChunkBytes, c * 64, row0);
+              tma_store_2d_hint(&p.tmD[l], s_act + slot * kActBytes + c * kChunkBytes, c * 64, row0, pol_s);
             tma_store_commit();
             tma_store_wait_read0();
             RN_TL(tl, 3700 + l * 10 + slot);
@@ -901,6 +908,7 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
   p.m_rows = M;
+  p.l2_hints = g_l2_hints;
 #ifdef RN_EXPERIMENTS
   p.timeline = g_pair_timeline_bwd;
 #else
@@ -1013,7 +1021,7 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
 #endif
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
-  p.m_rows = M; p.raw = raw;
+  p.m_rows = M; p.raw = raw; p.l2_hints = g_l2_hints;
   if ((rc = acquire_const_slot(consts, st, &p.const_slot)) != RN_OK) return rc;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) {

@@ -23,10 +23,11 @@ constexpr int kCompWarps = 8;
 #endif
 
 // Colour sigmoid of the raw (fused-head) input convention: the input is the bf16 tensor-core MLP's pre-activation (tolerance
-// regime 1e-2 max-abs RGB), so ex2.approx (relative error 2^-22) and a 1-ulp reciprocal are far inside it; three of the four
+// regime 1e-2 max-abs RGB), so ex2.approx (relative error 2^-22) and rcp.approx (1 ulp) are far inside it (the IEEE-rounded
+// reciprocal __frcp_rn was measured SLOWER than the accurate version: profiles/r02_ab_log.md, block 16); three of the four
 // transcendentals per sample, and the kernel is issue-bound (85 % of issue slots at S = 384).  The transmittance exponential
 // keeps the accurate expf: alpha = 1 - exp(-x) cancels for small x and the fp32 contract on weights is 1e-5 relative.
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(__fadd_rn(1.0f, __expf(-x))); }
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-x))); }
 
 // inclusive multiplicative scan over the warp
 __device__ __forceinline__ float warp_scan_mul(float v, int lane) {

@@ -56,6 +56,7 @@ struct GemmArgs {
   float* partial;         // TN: [m_tiles*splits][128*(BN+1)] fp32
   int splits;             // TN
   int chunks_per_split;   // TN
+  int l2_hints;           // TN: both operands are streamed once -> evict_first (rn_set_flag(6))
 };
 
 template <int BN, int MODE>
@@ -349,15 +350,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0) {
       if (lane == 0) {
         int s = 0; uint32_t ph = 0;
+        const uint64_t pol = l2_policy(args.l2_hints ? 1 : 0);
         for (int kc = c0; kc < c1; ++kc) {
           mbar_wait(&empty_a[s], ph ^ 1);
           uint8_t* a_s = s_a + s * Cfg::kStageBytes;
           uint8_t* b_s = a_s + kABytes;
           mbar_arrive_expect_tx(&full_a[s], Cfg::kStageBytes);
-          tma_load_2d(a_s, &tmA, &full_a[s], m_tile * kBlockM, kc * kBlockK);          // [64 pts][64 out]
-          tma_load_2d(a_s + 8192, &tmA, &full_a[s], m_tile * kBlockM + 64, kc * kBlockK);
+          tma_load_2d_hint(a_s, &tmA, &full_a[s], m_tile * kBlockM, kc * kBlockK, pol);          // [64 pts][64 out]
+          tma_load_2d_hint(a_s + 8192, &tmA, &full_a[s], m_tile * kBlockM + 64, kc * kBlockK, pol);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_s + j * 8192, &tmB, &full_a[s], j * 64, kc * kBlockK);
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d_hint(b_s + j * 8192, &tmB, &full_a[s], j * 64, kc * kBlockK, pol);
           if (++s == NS) { s = 0; ph ^= 1; }
         }
       }
@@ -559,6 +561,7 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
 double g_prof_next_flops = 0.0;
+int g_l2_hints = 0;          // rn_set_flag(6, v)
 
 void prof_begin(int mode, cudaStream_t st, int* slot) {
   *slot = -1;
@@ -679,6 +682,7 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
   a.chunks_per_split = (int)ceil_div(a.k_chunks, splits);
   a.splits = (int)ceil_div(a.k_chunks, a.chunks_per_split);
   a.partial = scratch;
+  a.l2_hints = g_l2_hints;
   RN_REQUIRE((size_t)a.splits * a.m_tiles * kBlockM * (N + 1) * sizeof(float) <= scratch_bytes);
   const int grid = a.m_tiles * a.splits;
   g_prof_next_flops = 2.0 * (double)K * N * Mo;

@@ -38,6 +38,7 @@ constexpr int kTnLaunches = 10;      // weight-gradient launches per backward pa
 static size_t dirvec_bytes(int64_t M) { return align_up((size_t)(M / 64 + 1) * 128 * sizeof(float), 256); }
 
 extern int g_chain_fwd, g_pe_fused;
+extern int g_l2_hints;
 static bool infer_fused(int64_t M, int group) {
   return g_chain_fwd == 2 && g_pe_fused && pair_encode_supported(group) && M < (int64_t)0x7FFFFF00;
 }
@@ -250,6 +251,7 @@ int rn_set_flag(int flag, int value) {
   if (flag == 3) { g_chain_bwd = value; return RN_OK; }
   if (flag == 4) { g_pe_fused = value; return RN_OK; }
   if (flag == 5) { g_pdl = value ? 1 : 0; return RN_OK; }
+  if (flag == 6) { g_l2_hints = value ? 1 : 0; return RN_OK; }
   return RN_ERR_INVALID_ARG;
 }
 
