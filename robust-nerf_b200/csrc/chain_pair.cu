@@ -908,7 +908,7 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
   p.m_rows = M;
-  p.l2_hints = g_l2_hints;
+  p.l2_hints = g_l2_hints & 1;
 #ifdef RN_EXPERIMENTS
   p.timeline = g_pair_timeline_bwd;
 #else
@@ -1021,7 +1021,7 @@ int mlp_chain_pair_forward(const ChainLayerHost* layers, int n_layers, int64_t M
 #endif
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
-  p.m_rows = M; p.raw = raw; p.l2_hints = g_l2_hints;
+  p.m_rows = M; p.raw = raw; p.l2_hints = g_l2_hints & 1;
   if ((rc = acquire_const_slot(consts, st, &p.const_slot)) != RN_OK) return rc;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) {

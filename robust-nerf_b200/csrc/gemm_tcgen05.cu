@@ -561,7 +561,7 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
 double g_prof_next_flops = 0.0;
-int g_l2_hints = 0;          // rn_set_flag(6, v)
+int g_l2_hints = 0;          // rn_set_flag(6, v): bit 0 = chain kernels, bit 1 = split-K weight-gradient kernels
 
 void prof_begin(int mode, cudaStream_t st, int* slot) {
   *slot = -1;
@@ -682,7 +682,7 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
   a.chunks_per_split = (int)ceil_div(a.k_chunks, splits);
   a.splits = (int)ceil_div(a.k_chunks, a.chunks_per_split);
   a.partial = scratch;
-  a.l2_hints = g_l2_hints;
+  a.l2_hints = (g_l2_hints >> 1) & 1;
   RN_REQUIRE((size_t)a.splits * a.m_tiles * kBlockM * (N + 1) * sizeof(float) <= scratch_bytes);
   const int grid = a.m_tiles * a.splits;
   g_prof_next_flops = 2.0 * (double)K * N * Mo;

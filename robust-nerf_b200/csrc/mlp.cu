@@ -251,7 +251,7 @@ int rn_set_flag(int flag, int value) {
   if (flag == 3) { g_chain_bwd = value; return RN_OK; }
   if (flag == 4) { g_pe_fused = value; return RN_OK; }
   if (flag == 5) { g_pdl = value ? 1 : 0; return RN_OK; }
-  if (flag == 6) { g_l2_hints = value ? 1 : 0; return RN_OK; }
+  if (flag == 6) { g_l2_hints = value & 3; return RN_OK; }
   return RN_ERR_INVALID_ARG;
 }
 

@@ -6,6 +6,6 @@ for i in $(seq 1 $R); do
     RN_FLAGS="$F" python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); pm=d['roofline']['per_mode']
-print('flags[$F]', round(d['ms_per_step'],3), 'fwd', round(pm['nt_forward']['ms_per_step'],3), 'render', round(d['render']['value'],3), 'render_e2e', round(d['render']['e2e']['value'],3))"
+print('flags[$F]', round(d['ms_per_step'],3), 'fwd', round(pm['nt_forward']['ms_per_step'],3), 'dgrad', round(pm['nn_dgrad']['ms_per_step'],3), 'wgrad', round(pm['tn_wgrad']['ms_per_step'],3), 'render', round(d['render']['value'],3), 'pose_opt_ms', round(d['pose_opt']['ms_per_step'],3))"
   done
 done
