@@ -634,9 +634,13 @@ def run_gpu(args):
     loss_val = float(loss.item())
 
     # ---- end to end: pinned host batches -> device, step, loss back to the host, every step ----
-    # The upload of step i+1 is issued on a copy stream while step i runs (double buffering, as any input pipeline does);
-    # every step's H2D copy and D2H loss read still happen inside the timed region, and the host waits for each loss.
-    loss_host = torch.zeros(1).pin_memory()
+    # An input pipeline as any trainer runs it: the upload of step i+1 is issued on a copy stream while step i runs, and
+    # the host reads the loss of step i after it has LAUNCHED step i+1 (the D2H copy of every step's loss is enqueued
+    # right behind that step; reading it one step late keeps the GPU fed instead of idling through a host round trip and
+    # a graph launch per step).  Every step's H2D copy and D2H loss read happen inside the timed region; the loop ends
+    # with the last loss on the host.
+    loss_host = torch.zeros(2).pin_memory()
+    loss_events = [torch.cuda.Event(), torch.cuda.Event()]
     copy_stream = torch.cuda.Stream()
 
     def upload(i):
@@ -648,17 +652,23 @@ def run_gpu(args):
 
     def e2e_loop(n):
         nxt = upload(0)
+        seen = []
         for i in range(n):
             b, ev = nxt
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
             for t in b:
                 t.record_stream(cur)
-            loss_host.copy_(step_fn(*b).reshape(1), non_blocking=True)
+            loss_host[i & 1:(i & 1) + 1].copy_(step_fn(*b).reshape(1), non_blocking=True)
+            loss_events[i & 1].record(cur)
             if i + 1 < n:
                 nxt = upload(i + 1)
-            cur.synchronize()                              # the caller reads the step's loss
-            _ = float(loss_host[0])
+            if i > 0:
+                loss_events[(i - 1) & 1].synchronize()         # the caller reads the previous step's loss
+                seen.append(float(loss_host[(i - 1) & 1]))
+        loss_events[(n - 1) & 1].synchronize()
+        seen.append(float(loss_host[(n - 1) & 1]))
+        return seen
 
     e2e_loop(3)
     barrier()
