@@ -610,7 +610,7 @@ def run_gpu(args):
     barrier()
     launches = int(lib.rn_launch_count() - n0)
     lib.rn_prof_enable(0)
-    ms3, fl3, ln3 = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_int * 3)()
+    ms3, fl3, ln3 = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_int * 4)()
     lib.rn_prof_collect(ms3, fl3, ln3)
     eager_ms_per_step = reduce_max(e0.elapsed_time(e1)) / K_
 
@@ -722,10 +722,10 @@ def run_gpu(args):
         dist.barrier()
 
     if rank == 0:
-        gemm_ms_per_step = (ms3[0] + ms3[1] + ms3[2]) / K_
+        gemm_ms_per_step = (ms3[0] + ms3[1] + ms3[2] + ms3[3]) / K_
         algo_flops_per_step = TRAIN_FLOP_PER_RAY * RAYS_PER_GPU
         achieved = algo_flops_per_step / (gemm_ms_per_step * 1e-3) / 1e12 if gemm_ms_per_step > 0 else None
-        n_gemm = ln3[0] + ln3[1] + ln3[2]
+        n_gemm = ln3[0] + ln3[1] + ln3[2] + ln3[3]
         traffic, hbm_view = None, None
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tp):
@@ -743,7 +743,7 @@ def run_gpu(args):
             except Exception:
                 traffic, hbm_view = None, None
         per_mode = {}
-        for i, nm in enumerate(("nt_forward", "nn_dgrad", "tn_wgrad")):
+        for i, nm in enumerate(("nt_forward", "nn_dgrad", "tn_wgrad", "dgrad_beside_wgrad")):
             if ln3[i]:
                 per_mode[nm] = {"launches_per_step": ln3[i] / K_, "ms_per_step": ms3[i] / K_,
                                 "executed_tflops": fl3[i] / (ms3[i] * 1e-3) / 1e12}

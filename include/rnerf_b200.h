@@ -41,8 +41,9 @@ int rn_device_sm_count(int* sm_count_host);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
 unsigned long long rn_launch_count(void);
 /* measurement hooks: when enabled, every tcgen05 GEMM launch is bracketed by CUDA events on its
- * stream; rn_prof_collect synchronises and returns, per mode (0 NT fwd, 1 NN dgrad, 2 TN wgrad),
- * the summed kernel milliseconds, executed FLOPs (2*M*N*K incl. padding) and launch counts. */
+ * stream; rn_prof_collect synchronises and returns, per mode (0 NT fwd, 1 NN dgrad, 2 TN wgrad,
+ * 3 = NN chain and TN stream running side by side, timed as one span), the summed kernel
+ * milliseconds, executed FLOPs (2*M*N*K incl. padding) and launch counts: arrays of FOUR. */
 /* tuning flags: flag 0 = run the MLP forward as ONE layer-chained persistent launch (default 1)
  * instead of ten per-layer GEMM launches (0). Results are identical.
  * flag 2 = operand ring depths of the chained kernel: 0 -> (A,B) = (5,2) stages, 1 -> (3,3).
@@ -50,8 +51,9 @@ unsigned long long rn_launch_count(void);
  * scripts/chain_experiments.py: switches parts of the pipeline off, results are then wrong);
  * the shipped library rejects it. */
 int rn_set_flag(int flag, int value);
+int rn_get_flag(int flag, int* value_host);
 int rn_prof_enable(int on);
-int rn_prof_collect(double* ms3_host, double* flops3_host, int* launches3_host);
+int rn_prof_collect(double* ms4_host, double* flops4_host, int* launches4_host);
 
 /* ------------------------------------------------------------------------------------------
  * Network geometry (fixed: the reference's default ModelConfig, noisy_src/config.py:10-24;

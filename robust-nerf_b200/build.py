@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librnerf_b200.so")
-SOURCES = ["api.cu", "raygen.cu", "sampling.cu", "composite.cu", "encode.cu", "gemm_tcgen05.cu", "chain_pair.cu", "mlp.cu", "render.cu", "metrics.cu", "pose_noise.cu"]
+SOURCES = ["api.cu", "raygen.cu", "sampling.cu", "composite.cu", "encode.cu", "gemm_tcgen05.cu", "chain_pair.cu", "wgrad_stream.cu", "mlp.cu", "render.cu", "metrics.cu", "pose_noise.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

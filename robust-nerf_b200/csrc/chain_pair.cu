@@ -38,7 +38,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
 void prof_begin(int mode, cudaStream_t st, int* slot);
 void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
-extern int g_l2_hints;
+extern int g_l2_hints, g_sm_limit_dgrad;
 
 constexpr int kPairThreads = 608;         // 19 warps
 constexpr int kPairThreadsPE = 640;       // + one warp: with the (idle in inference) store warp, two encoder warps, one per tile slot
@@ -612,7 +612,15 @@ struct BwdParams {
   int n_layers, n_ptiles;
   int64_t m_rows;
   int l2_hints;
+  uint32_t* flags;              // [n_layers][n_blocks] "block published" words for wgrad_stream.cu, or null
+  int n_blocks;                 // 128-row blocks
 };
+
+__device__ __forceinline__ void publish_block(uint32_t* f) {
+  // the bulk stores of this block have completed (cp.async.bulk.wait_group: their writes are performed and visible to
+  // this thread), so a release store orders them before the flag for the consumer's acquire
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
@@ -840,8 +848,16 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
   } else if (warp == 18) {
     // ---------------- store warp: every layer's data gradient goes to global for the weight-gradient GEMMs ----------------
     if (lane == 0) {
-      const uint64_t pol_s = l2_policy(p.l2_hints ? 1 : 0);
+      // with a consumer beside this launch the gradients are re-read out of L2 within microseconds: keep them (normal
+      // policy) instead of marking them evict_first
+      const uint64_t pol_s = l2_policy((p.l2_hints && !p.flags) ? 1 : 0);
       uint32_t it0 = 0, it1 = 0;
+      // flags of the last kPubLag store groups: a group is published kPubLag groups late, when cp.async.bulk.wait_group
+      // says its writes have completed without this warp ever waiting for the most recent stores (a wait for the
+      // previous group alone, ~3-4 us of write latency per layer and slot, paced the whole chain)
+      constexpr int kPubLag = 4;
+      uint32_t* pending[kPubLag] = {nullptr, nullptr, nullptr, nullptr};
+      int pend_i = 0;
       RN_TL_DECL(tl, 3, true);
       for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
         const int tiles_here = min(2, p.n_ptiles - grp * 2);
@@ -858,10 +874,19 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
             RN_TL(tl, 3700 + l * 10 + slot);
             mbar_arrive(&store_done[slot]);
             if (l == p.n_layers - 1) mbar_arrive(&act_free[slot]);
+            if (p.flags) {
+              tma_store_wait_all4();                      // every group but the last kPubLag has completed its writes
+              if (pending[pend_i]) publish_block(pending[pend_i]);
+              pending[pend_i] = (row0 < p.m_rows) ? p.flags + (size_t)l * p.n_blocks + (row0 >> 7) : nullptr;
+              pend_i = (pend_i + 1) & (kPubLag - 1);
+            }
           }
         }
       }
       tma_store_wait_all0();
+      if (p.flags)
+        for (int i = 0; i < kPubLag; ++i)
+          if (pending[i]) publish_block(pending[i]);
     }
   }
 
@@ -878,7 +903,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
 // A_0 = `in` (in_cols wide, TMA-loaded), A_l = D_{l-1} (+ the side chunk `aux` at column aux_col as LAST K chunk when
 // layers[l].aux_kind == 2).
 int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M, const void* in, int64_t ld_in, int in_cols,
-                            const void* aux, int64_t ld_aux, int aux_cols, cudaStream_t st) {
+                            const void* aux, int64_t ld_aux, int aux_cols, cudaStream_t st, uint32_t* flags, int n_sms) {
   int rc = check_arch();
   if (rc != RN_OK) return rc;
   RN_REQUIRE(layers && n_layers >= 1 && n_layers <= kPairMaxLayers && M > 0 && in && (in_cols == 128 || in_cols == 256));
@@ -909,6 +934,8 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   p.n_ptiles = (int)ceil_div(M, 256);
   p.m_rows = M;
   p.l2_hints = g_l2_hints & 1;
+  p.flags = flags;
+  p.n_blocks = (int)ceil_div(M, 128);
 #ifdef RN_EXPERIMENTS
   p.timeline = g_pair_timeline_bwd;
 #else
@@ -918,7 +945,9 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   if (first_use_on_device(configured))
     RN_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
   const int n_groups = (p.n_ptiles + 1) / 2;
-  const int max_clusters = num_sms() / 2;
+  int sms = (n_sms > 0 && n_sms < num_sms()) ? n_sms : num_sms();
+  if (g_sm_limit_dgrad > 0 && g_sm_limit_dgrad < sms) sms = g_sm_limit_dgrad;
+  const int max_clusters = sms / 2;
   const int grid = 2 * (n_groups < max_clusters ? n_groups : max_clusters);
   g_prof_next_flops = flops;
   int slot;

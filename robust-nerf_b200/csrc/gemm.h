@@ -53,8 +53,25 @@ struct BwdLayerHost {
   const uint32_t* mask_in;                     // packed ReLU mask of the rows of D, or null
   int aux_kind, aux_col;                       // 2: the last K chunk is the side chunk starting at column aux_col
 };
+// flags != null: the store warp publishes flags[l * ceil(M / 128) + block] = 1 once layer l's 128-row block is in global
+// memory (for wgrad_stream.cu, which runs beside this launch); n_sms > 0 limits the launch to that many SMs.
 int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M, const void* in, int64_t ld_in, int in_cols,
-                            const void* aux, int64_t ld_aux, int aux_cols, cudaStream_t st);
+                            const void* aux, int64_t ld_aux, int aux_cols, cudaStream_t st, uint32_t* flags = nullptr,
+                            int n_sms = 0);
+
+// wgrad_stream.cu: all weight / bias gradients of one backward pass in one persistent launch of CTA pairs that consumes
+// the chain's output block by block.  Problem i: dW[Mo, N] = A[M pts, a_col0 : a_col0 + Mo]^T B[M pts, 0 : N] with Mo <= 256;
+// a_cols / b_cols = columns the tensors really have (what lies beyond is read as zero); flag_row = the chain layer whose
+// output is A (-1: A is complete before the launch).  `ctas` = SMs the launch may use; problem i's partial tiles go to
+// scratch + i * region_floats and are described by infos[i] for tn_batch_add / gemm_tn_reduce_batch.
+constexpr int kWsMaxProblems = 11;
+struct WsHostProblem {
+  const void* A; int64_t lda; int a_cols, a_col0, Mo;
+  const void* B; int64_t ldb; int b_cols, N;
+  int flag_row;
+};
+int wgrad_stream_launch(const WsHostProblem* probs, int n, int64_t M, const uint32_t* flags, int ctas, float* scratch,
+                        size_t region_floats, TnInfo* infos, cudaStream_t st);
 
 // inference: per-ray view-direction projection dirvec[R][128] (encode.cu: dir_bias_kernel)
 int launch_dir_bias(const float* dirs, int64_t R, const void* packed, float* dirvec, cudaStream_t st);

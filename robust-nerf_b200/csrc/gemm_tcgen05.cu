@@ -556,21 +556,23 @@ int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
 
 // ---- optional per-launch CUDA-event timing (bench.py roofline: live kernel durations on the
 // launching stream inside the timed region) ----
-struct ProfRec { cudaEvent_t a, b; int mode; double flops; };
+struct ProfRec { cudaEvent_t a, b; int mode; double flops; int launches; };
 static bool g_prof_on = false;
+int g_prof_suppress = 0;     // > 0: inside a span that is recorded as a whole (the overlapped backward): skip per-launch records
 static std::vector<ProfRec> g_prof;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
 double g_prof_next_flops = 0.0;
+int g_sm_limit_dgrad = 0, g_sm_limit_wgrad = 0;    // rn_set_flag(7 / 8, n): experiments -- run that kernel family on n SMs
 int g_l2_hints = 0;          // rn_set_flag(6, v): bit 0 = chain kernels, bit 1 = split-K weight-gradient kernels
 
 void prof_begin(int mode, cudaStream_t st, int* slot) {
   *slot = -1;
-  if (!g_prof_on || g_prof.size() >= 16384) return;
+  if (!g_prof_on || g_prof.size() >= 16384 || (g_prof_suppress > 0 && mode != 3)) return;
   std::pair<cudaEvent_t, cudaEvent_t> ev;
   if (!g_prof_pool.empty()) { ev = g_prof_pool.back(); g_prof_pool.pop_back(); }
   else if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) return;
   cudaEventRecord(ev.first, st);
-  g_prof.push_back({ev.first, ev.second, mode, g_prof_next_flops});
+  g_prof.push_back({ev.first, ev.second, mode, g_prof_next_flops, mode == 3 ? 2 : 1});
   *slot = (int)g_prof.size() - 1;
 }
 void prof_end(int slot, cudaStream_t st) {
@@ -676,7 +678,8 @@ int gemm_tn_launch(const void* A, int64_t lda, int Mo, const void* B, int64_t ld
   a.m_tiles = (int)ceil_div(Mo, kBlockM);
   a.k_chunks = (int)ceil_div(K, kBlockK);
   a.k_total = (int)(K > 0x7fffffff ? 0x7fffffff : K);
-  int splits = num_sms() / a.m_tiles;
+  const int sms = (g_sm_limit_wgrad > 0 && g_sm_limit_wgrad < num_sms()) ? g_sm_limit_wgrad : num_sms();
+  int splits = sms / a.m_tiles;
   if (splits > a.k_chunks) splits = a.k_chunks;
   if (splits < 1) splits = 1;
   a.chunks_per_split = (int)ceil_div(a.k_chunks, splits);
@@ -734,16 +737,17 @@ int rn_prof_enable(int on) {
   return RN_OK;
 }
 
-// Synchronises the device, then sums the recorded GEMM launches by mode (0 NT, 1 NN, 2 TN):
-// total milliseconds, executed (padded) FLOPs and launch counts; clears the record.
-int rn_prof_collect(double* ms3_host, double* flops3_host, int* launches3_host) {
-  RN_REQUIRE(ms3_host && flops3_host && launches3_host);
+// Synchronises the device, then sums the recorded GEMM launches by mode (0 NT, 1 NN, 2 TN, 3 = the NN chain and the
+// TN stream running side by side, timed as one span): total milliseconds, executed (padded) FLOPs and launch counts;
+// clears the record.  The arrays hold FOUR entries.
+int rn_prof_collect(double* ms4_host, double* flops4_host, int* launches4_host) {
+  RN_REQUIRE(ms4_host && flops4_host && launches4_host);
   RN_CUDA_CHECK(cudaDeviceSynchronize());
-  for (int i = 0; i < 3; ++i) { ms3_host[i] = 0.0; flops3_host[i] = 0.0; launches3_host[i] = 0; }
+  for (int i = 0; i < 4; ++i) { ms4_host[i] = 0.0; flops4_host[i] = 0.0; launches4_host[i] = 0; }
   for (auto& r : g_prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
-      ms3_host[r.mode] += ms; flops3_host[r.mode] += r.flops; launches3_host[r.mode] += 1;
+      ms4_host[r.mode] += ms; flops4_host[r.mode] += r.flops; launches4_host[r.mode] += r.launches;
     }
     g_prof_pool.push_back({r.a, r.b});
   }

@@ -29,16 +29,21 @@ struct TrainWs {
   float* scratch;
   size_t scratch_bytes;
   float* heads_scratch;
+  uint32_t* flags;          // [9][ceil(M / 128)] "block published" words: data-gradient chain -> weight-gradient stream
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-constexpr int kTnLaunches = 10;      // weight-gradient launches per backward pass: each keeps its own partial-tile region
+constexpr int kTnLaunches = 11;      // weight-gradient GEMMs per backward pass (10 launches, or 11 problems of the stream): each keeps its own partial-tile region
 
 // inference: per-ray direction term of the view layer, [M / group][128] fp32 with group >= 64 (PE-fused chain)
+static size_t flags_bytes(int64_t M) { return align_up((size_t)9 * (size_t)((M + 127) / 128) * sizeof(uint32_t), 256); }
 static size_t dirvec_bytes(int64_t M) { return align_up((size_t)(M / 64 + 1) * 128 * sizeof(float), 256); }
 
 extern int g_chain_fwd, g_pe_fused;
-extern int g_l2_hints;
+extern int g_l2_hints, g_sm_limit_dgrad, g_sm_limit_wgrad, g_prof_suppress;
+extern double g_prof_next_flops;
+void prof_begin(int mode, cudaStream_t st, int* slot);
+void prof_end(int slot, cudaStream_t st);
 static bool infer_fused(int64_t M, int group) {
   return g_chain_fwd == 2 && g_pe_fused && pair_encode_supported(group) && M < (int64_t)0x7FFFFF00;
 }
@@ -50,7 +55,8 @@ static size_t workspace_bytes(int64_t M, int training, int group = 0) {
   const size_t elems = training ? (size_t)(kTrainFwdElems + kTrainBwdElems) : (size_t)kInferElems;
   size_t b = align_up((size_t)M * elems * 2, 256);
   if (!training) b += dirvec_bytes(M);
-  if (training) b += kTnLaunches * align_up(gemm_tn_scratch_bytes(), 256) + align_up(heads_bwd_scratch_bytes(M), 256);
+  if (training)
+    b += kTnLaunches * align_up(gemm_tn_scratch_bytes(), 256) + align_up(heads_bwd_scratch_bytes(M), 256) + flags_bytes(M);
   return b + 256;
 }
 
@@ -70,6 +76,23 @@ static void carve_train(void* ws, int64_t M, TrainWs* w) {
   w->scratch = reinterpret_cast<float*>(q);
   w->scratch_bytes = gemm_tn_scratch_bytes();
   w->heads_scratch = reinterpret_cast<float*>(q + kTnLaunches * align_up(w->scratch_bytes, 256));
+  w->flags = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(w->heads_scratch) + align_up(heads_bwd_scratch_bytes(M), 256));
+}
+
+// ---- the side stream the weight-gradient consumer runs on (one per device, created on first use) ----
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static int side_stream(SideStream** out) {
+  static SideStream table[kMaxDevices];
+  int dev = 0;
+  RN_CUDA_CHECK(cudaGetDevice(&dev));
+  SideStream& s = table[dev & (kMaxDevices - 1)];
+  if (!s.st) {
+    RN_CUDA_CHECK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    RN_CUDA_CHECK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    RN_CUDA_CHECK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return RN_OK;
 }
 
 static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimension of H[l]
@@ -83,6 +106,9 @@ static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimen
 #ifdef RN_EXPERIMENTS
 int g_chain_dbg = 0;
 #endif
+// rn_set_flag(9, n): n > 0 = the weight gradients run BESIDE the data-gradient chain on n SMs (wgrad_stream.cu), taking each
+// block of dH out of L2 as the chain publishes it; 0 = one split-K launch per layer after the chain
+int g_wgrad_stream_sms = 0;
 int g_chain_bwd = 1;      // rn_set_flag(3, v): 1 = data gradients as one CTA-pair chain launch (chain_pair.cu), 0 = one launch per layer
 // rn_set_flag(0, v): 0 = one launch per layer (gemm_tcgen05.cu: the building-block kernels, kept as the cross-check of the
 // chain), 2 = CTA-pair chain with shared-memory-resident activations (chain_pair.cu; default).  (Round 1's third variant,
@@ -177,6 +203,7 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   auto scratch_k = [&]() { return w.scratch + (size_t)(tn_k++) * region; };
   // heads: dHC, dFS[:, 256:272], rgb_linear grads
   RN_TRY(launch_heads_bwd(g_raw, w.HC, M, F, w.dHC, w.dFS, 272, w.heads_scratch, G + kG_WRgb, G + kG_BRgb, st));
+  const bool overlapped = g_chain_bwd && g_wgrad_stream_sms >= 24 && g_wgrad_stream_sms <= num_sms() - 24;
   if (g_chain_bwd) {
     // ---- all data gradients in one launch: dHC -> dF -> dH7 -> ... -> dH0 ----
     BwdLayerHost L[9];
@@ -187,7 +214,59 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
       L[9 - l] = BwdLayerHost{W + trunk_w(l), skip ? 320 : 256, skip ? 320 : 256, 256, skip ? 64 : 0, w.dH[l - 1], 256,
                               w.MB[l - 1], 0, 0};
     }
-    RN_TRY(mlp_chain_pair_backward(L, 9, M, w.dHC, 128, 128, w.dFS, 272, 272, st));
+    if (overlapped) {
+      // ---- ... with every weight gradient in a second launch beside it (wgrad_stream.cu) ----
+      // chain layer c writes: 0 -> dFS[:, 0:256], 1 -> dH7, ..., 8 -> dH0; dHC comes from heads_bwd (complete already)
+      WsHostProblem P[kWsMaxProblems];
+      int np = 0;
+      P[np++] = WsHostProblem{w.dHC, 128, 128, 0, 128, w.FD, 320, 320, 320, -1};           // dir_linear
+      P[np++] = WsHostProblem{w.dFS, 272, 272, 0, 256, w.H[7], 256, 256, 256, 0};           // feature_linear
+      P[np++] = WsHostProblem{w.dFS, 272, 272, 256, 16, w.H[7], 256, 256, 256, -1};         // sigma_linear (dsigma is heads_bwd's)
+      for (int l = 7; l >= 1; --l)
+        P[np++] = (l == 5) ? WsHostProblem{w.dH[5], 256, 256, 0, 256, w.XC, 320, 320, 320, 8 - 5}
+                           : WsHostProblem{w.dH[l], 256, 256, 0, 256, w.H[l - 1], ld_of(l - 1), 256, 256, 8 - l};
+      P[np++] = WsHostProblem{w.dH[0], 256, 256, 0, 256, w.XC, 320, 64, 64, 8};             // layer 0: x_enc only
+      const int ws_sms = g_wgrad_stream_sms & ~1;
+      SideStream* side;
+      RN_TRY(side_stream(&side));
+      RN_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, flags_bytes(M), st));
+      // measurement hook: the two launches are timed as ONE span on the main stream (their own records would overlap)
+      double span_flops = 0.0;
+      for (int l = 0; l < 9; ++l) span_flops += 2.0 * (double)M * 256 * L[l].k;
+      for (int i = 0; i < np; ++i) span_flops += 2.0 * (double)M * P[i].N * P[i].Mo;
+      g_prof_next_flops = span_flops;
+      int slot;
+      prof_begin(3, st, &slot);
+      ++g_prof_suppress;
+      RN_CUDA_CHECK(cudaEventRecord(side->fork, st));
+      RN_CUDA_CHECK(cudaStreamWaitEvent(side->st, side->fork, 0));
+      int rc = mlp_chain_pair_backward(L, 9, M, w.dHC, 128, 128, w.dFS, 272, 272, st, w.flags, num_sms() - ws_sms);
+      TnInfo infos[kWsMaxProblems];
+      if (rc == RN_OK) rc = wgrad_stream_launch(P, np, M, w.flags, ws_sms, w.scratch, region, infos, side->st);
+      --g_prof_suppress;
+      // join even after a failed launch: a stream capture must not end with the side stream still forked
+      cudaError_t e1 = cudaEventRecord(side->join, side->st);
+      cudaError_t e2 = cudaStreamWaitEvent(st, side->join, 0);
+      prof_end(slot, st);
+      RN_TRY(rc);
+      RN_CUDA_CHECK(e1);
+      RN_CUDA_CHECK(e2);
+      int k = 0;
+      RN_TRY(tn_batch_add(&batch, infos[k++], 0, 128, 0, 283, G + kG_WD, 283, G + kG_BD));
+      RN_TRY(tn_batch_add(&batch, infos[k++], 0, 256, 0, 256, G + kG_WF, 256, G + kG_BF));
+      RN_TRY(tn_batch_add(&batch, infos[k++], 0, 1, 0, 256, G + kG_WSig, 256, G + kG_BSig));
+      for (int l = 7; l >= 1; --l) {
+        if (l == 5) {
+          RN_TRY(tn_batch_add(&batch, infos[k], 0, 256, 0, 63, G + trunk_gw(5), 319, nullptr));
+          RN_TRY(tn_batch_add(&batch, infos[k++], 0, 256, 64, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5)));
+        } else {
+          RN_TRY(tn_batch_add(&batch, infos[k++], 0, 256, 0, 256, G + trunk_gw(l), 256, G + trunk_gb(l)));
+        }
+      }
+      RN_TRY(tn_batch_add(&batch, infos[k++], 0, 256, 0, 63, G + trunk_gw(0), 63, G + trunk_gb(0)));
+    } else {
+      RN_TRY(mlp_chain_pair_backward(L, 9, M, w.dHC, 128, 128, w.dFS, 272, 272, st));
+    }
   } else {
     RN_TRY(gemm_nn(w.dHC, 128, W + kWD, 320, w.dFS, 272, M, 256, 128, nullptr, st));
     RN_TRY(gemm_nn(w.dFS, 272, W + kWFS, 256, w.dH[7], 256, M, 256, 272, w.MB[7], st));
@@ -195,6 +274,7 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
       RN_TRY(gemm_nn(w.dH[l], 256, W + trunk_w(l) + (l == 5 ? 64 : 0), l == 5 ? 320 : 256, w.dH[l - 1], 256, M, 256, 256,
                      w.MB[l - 1], st));
   }
+  if (!overlapped) {
   // ---- weight / bias gradients: one split-K GEMM per layer, reduced together below ----
   // dir_linear: one launch over the whole 320-wide input [feat(256) | d_enc(27) | 0]
   RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
@@ -218,6 +298,7 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   RN_TRY(gemm_tn_launch(w.dH[0], 256, 256, w.XC, 320, 64, M, scratch_k(), w.scratch_bytes, &ti, st));
   RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(0), 63, G + trunk_gb(0)));
   RN_REQUIRE(tn_k <= kTnLaunches);
+  }
   RN_TRY(gemm_tn_reduce_batch(batch, st));
   if (need_in) {
     // gradients w.r.t. the encodings (pose optimisation only): three 64-wide data-gradient GEMMs
@@ -252,7 +333,25 @@ int rn_set_flag(int flag, int value) {
   if (flag == 4) { g_pe_fused = value; return RN_OK; }
   if (flag == 5) { g_pdl = value ? 1 : 0; return RN_OK; }
   if (flag == 6) { g_l2_hints = value & 3; return RN_OK; }
+  if (flag == 7) { g_sm_limit_dgrad = value; return RN_OK; }
+  if (flag == 8) { g_sm_limit_wgrad = value; return RN_OK; }
+  if (flag == 9) { g_wgrad_stream_sms = value; return RN_OK; }
   return RN_ERR_INVALID_ARG;
+}
+
+int rn_get_flag(int flag, int* value_host) {
+  RN_REQUIRE(value_host);
+  switch (flag) {
+    case 0: *value_host = g_chain_fwd; return RN_OK;
+    case 3: *value_host = g_chain_bwd; return RN_OK;
+    case 4: *value_host = g_pe_fused; return RN_OK;
+    case 5: *value_host = g_pdl; return RN_OK;
+    case 6: *value_host = g_l2_hints; return RN_OK;
+    case 7: *value_host = g_sm_limit_dgrad; return RN_OK;
+    case 8: *value_host = g_sm_limit_wgrad; return RN_OK;
+    case 9: *value_host = g_wgrad_stream_sms; return RN_OK;
+    default: return RN_ERR_INVALID_ARG;
+  }
 }
 
 size_t rn_mlp_workspace_bytes(int64_t M, int training) { return M > 0 ? workspace_bytes(M, training) : 0; }

@@ -1,0 +1,341 @@
+// wgrad_stream.cu -- every weight / bias gradient of one network's backward pass (the autograd backward of
+// noisy_src/model.py:169-194: dW_l = dH_l^T H_{l-1}, db_l = column sums of dH_l) in ONE persistent launch that runs
+// CONCURRENTLY with the data-gradient chain (chain_pair.cu) on its own share of the SMs.
+//
+// Why: run one after the other, the data-gradient chain is paced by its epilogues (HBM at 4.5 TB/s) and the split-K
+// weight-gradient GEMMs by HBM (6.1 TB/s, tensor pipe 16-42 %), and the weight gradients re-read from HBM every dH_l the
+// chain has just written (5.2 GB per step).  Side by side they share the machine by what each one needs -- and the
+// consumer takes each 128-point block of dH_l out of L2 as soon as the chain has published it:
+//   * the chain's store warp publishes flag[layer][block] (st.release.gpu) once the TMA store of that block has completed;
+//   * every CTA PAIR here (cluster of 2, tcgen05 cta_group::2, M = 256) owns one (GEMM, split) for the whole launch:
+//     CTA r holds output features [128 r, 128 r + 128) of dW with its fp32 accumulator resident in TMEM, streams its
+//     half of dH_l^T (16 KiB per 64 points) and HALF of H_{l-1}'s columns (16 KiB): 32 KiB per SM and chunk where a
+//     single-CTA tile pulls 48 -- the consumer is paced by what one SM can take in from L2 (~95 GB/s measured), so bytes
+//     per SM are what counts;
+//   * split s of S takes the point blocks s, s+S, s+2S, ... in the order the chain produces them; the TMA warp polls
+//     the flags of its next 32 blocks at once (ld.acquire.gpu, one per lane) so the flag latency is off the load path;
+//   * the bias gradient is one more N=16 MMA against a tile of ones (column sums of dH_l);
+//   * tensor cores accumulate with truncation, so an accumulator is not kept for the whole launch: every kWsFlushChunks
+//     chunks (1,024 accumulation steps, about as many as one split of the split-K kernels sees) the epilogue warps
+//     add it into the fp32 partial tile in global memory (round-to-nearest) and the MMAs start a fresh one;
+//   * the partial tiles use the [split][m_tile] layout of the split-K kernels and are summed by the same deterministic
+//     reduce kernel (gemm_tcgen05.cu) -- the assignment is static, so a step stays bit-reproducible.
+// Widths that are not 256: N = 320 ([x_enc | H4], [feat | d_enc]) is a second MMA of N = 128 whose upper half lies beyond
+// the tensor (TMA zero fill, no traffic); N = 64 (x_enc) is one MMA of N = 128 likewise; M = 128 (dHC) and the sigma row
+// of dFS are M = 256 with the missing features out of bounds.
+// Both kernels are launched as clusters of two CTAs (whole TPCs), one CTA per SM, and together they ask for no more SMs
+// than the device has, so they are co-resident whatever order the hardware starts them in; a wait on a flag that never
+// comes traps after 4 s instead of hanging the device.
+//
+// Warp roles (192 threads): 0 = flag polling + TMA producer, 1 = TMEM owner + MMA issuer (leader CTA), 2..5 = epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "gemm.h"
+#include <cuda_bf16.h>
+#include <stdio.h>
+
+namespace rn {
+
+using namespace ptx;
+
+int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer);
+void prof_begin(int mode, cudaStream_t st, int* slot);
+void prof_end(int slot, cudaStream_t st);
+extern double g_prof_next_flops;
+extern int g_l2_hints;
+
+constexpr int kWsThreads = 192;
+constexpr int kWsSmem = 231424;                 // 226 KiB
+constexpr int kWsOnes = 2048;                   // 16 k-rows x 128 B of bf16 1.0 (first 2 KiB of the aligned buffer)
+constexpr int kWsRing = kWsSmem - 1024 /*alignment slack*/ - kWsOnes - 1024 /*barriers*/;
+constexpr int kWsABytes = 16384;                // [64 points][128 output features]
+constexpr int kWsMaxStages = 8;
+constexpr int kWsFlushChunks = 256;             // accumulator flushed to the fp32 partial every 256 chunks (16,384 points)
+
+struct WsProblem {
+  CUtensorMap tmA, tmB;      // boxes of [64 points][64 columns], SWIZZLE_128B
+  float* partial;            // [splits][m_tiles][128 * (BN + 1)] fp32
+  int BN;                    // columns of dW (64, 256 or 320)
+  int m_tiles;               // 128-row tiles of dW that exist (1 or 2); CTA rank >= m_tiles computes zeros and writes nothing
+  int splits;
+  int a_col0;                // first column of A this problem reads
+  int flag_row;              // row of the flag table the A operand waits on, or -1 (A was complete before the launch)
+  int pair0;                 // first CTA pair of this problem
+};
+struct WsParams {
+  WsProblem prob[kWsMaxProblems];
+  int n_prob, n_pairs, n_blocks;      // n_blocks: 128-point blocks
+  int64_t m_rows;
+  const uint32_t* flags;              // [flag rows][n_blocks], zeroed before the launch, 1 = block published
+  int l2_hints;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+static __device__ __noinline__ void flag_timeout_trap(int block) {
+  printf("rnerf_b200: weight-gradient stream timed out waiting for point block %d (CTA %d)\n", block, (int)blockIdx.x);
+  __trap();
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWsThreads, 1)
+wgrad_stream_kernel(const __grid_constant__ WsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_ones = smem;
+  uint8_t* s_ring = smem + kWsOnes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOnes + kWsRing);
+  uint64_t* full = bars;                     // [8]  leader: bytes of both CTAs' loads
+  uint64_t* empty = bars + 8;                // [8]  each CTA (multicast commit)
+  uint64_t* tmem_full = bars + 16;           //      each CTA (multicast commit)
+  uint64_t* tmem_empty = bars + 17;          //      leader: 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)blockIdx.x >> 1;
+  int pi = 0;
+  while (pi + 1 < p.n_prob && pair >= p.prob[pi + 1].pair0) ++pi;
+  const WsProblem& P = p.prob[pi];
+  const int BN = P.BN;
+  const int split = pair - P.pair0;
+  const int S = P.splits;
+  // MMA 1: N1 columns (both CTAs hold N1 / 2 of them); MMA 2 (BN = 320 only): columns 256.. as N = 128, upper half out of bounds
+  const int N1 = BN == 64 ? 128 : 256;
+  const int N2 = BN == 320 ? 128 : 0;
+  const int nb1 = N1 / 128;                                  // 64-column boxes of B per CTA for MMA 1
+  const int nb = nb1 + (N2 ? 1 : 0);
+  const int stage_bytes = kWsABytes + nb * 8192;
+  const int ns_raw = kWsRing / stage_bytes;
+  const int NS = ns_raw > kWsMaxStages ? kWsMaxStages : ns_raw;
+  const int bias_col = N1 + N2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&P.tmA); prefetch_tmap(&P.tmB);
+    for (int i = 0; i < kWsMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  if (warp >= 2) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(s_ones);
+    for (int i = threadIdx.x - 64; i < kWsOnes / 4; i += 128) ones[i] = 0x3F803F80u;   // bf16 1.0 x2
+    fence_proxy_async_smem();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // 64-point K chunks of this pair: blocks split, split + S, ...; the last block of the network may hold one chunk only
+  const int last_block_chunks = (int)((p.m_rows - (int64_t)(p.n_blocks - 1) * 128 + 63) / 64);     // 1 or 2
+  int my_blocks = 0;
+  if (split < p.n_blocks) my_blocks = (p.n_blocks - 1 - split) / S + 1;
+  const bool has_last = my_blocks > 0 && (split + (my_blocks - 1) * S == p.n_blocks - 1);
+  const int n_chunks = my_blocks * 2 - ((has_last && last_block_chunks == 1) ? 1 : 0);
+  const int n_flush = (n_chunks + kWsFlushChunks - 1) / kWsFlushChunks;
+
+  if (warp == 0) {
+    // ---------------- flag polling + TMA producer (both CTAs, each for its own halves) ----------------
+    const uint32_t full_leader = mapa_u32(smem_u32(full), 0);
+    const uint64_t pol = l2_policy(p.l2_hints ? 1 : 0);
+    const uint32_t* frow = P.flag_row >= 0 ? p.flags + (size_t)P.flag_row * p.n_blocks : nullptr;
+    const int a_c = P.a_col0 + (int)rank * 128;
+    int s = 0; uint32_t ph = 0; int issued = 0;
+    int b = split;
+    unsigned long long t0 = 0; uint32_t idle = 0;
+    while (b < p.n_blocks) {
+      // the next 32 blocks of this split, one flag per lane: how many are published, counting from the first?
+      int nready = 32;
+      if (frow) {
+        const int bb = b + lane * S;
+        const uint32_t f = bb < p.n_blocks ? ld_acquire_gpu(frow + bb) : 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
+        nready = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+        if (nready == 0) {
+          __nanosleep(100);
+          if ((++idle & 63u) == 0) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) flag_timeout_trap(b);
+          }
+          continue;
+        }
+        idle = 0; t0 = 0;
+        // (no proxy fence: the loads below are issued after the acquire -- ordered for lane 0 by the ballot -- and read L2,
+        // the point of coherence the producer's completed bulk stores went through; a fence.proxy.async here drains the
+        // CTA's outstanding TMA loads and cost 2/3 of the kernel's rate, profiles/r02_ab_log.md block 19)
+      }
+      for (int i = 0; i < nready && b < p.n_blocks; ++i, b += S) {
+        for (int h = 0; h < 2 && issued < n_chunks; ++h, ++issued) {
+          const int kc = b * 2 + h;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (lane == 0) {
+            uint8_t* a_s = s_ring + s * stage_bytes;
+            uint8_t* b_s = a_s + kWsABytes;
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
+            const uint32_t bar = full_leader + s * 8;
+            tma_load_2d_pair_hint(a_s, &P.tmA, bar, a_c, kc * 64, pol);                      // [64 pts][64 features]
+            tma_load_2d_pair_hint(a_s + 8192, &P.tmA, bar, a_c + 64, kc * 64, pol);
+            for (int j = 0; j < nb1; ++j)
+              tma_load_2d_pair_hint(b_s + j * 8192, &P.tmB, bar, (int)rank * (N1 / 2) + j * 64, kc * 64, pol);
+            if (N2) tma_load_2d_pair_hint(b_s + nb1 * 8192, &P.tmB, bar, 256 + (int)rank * 64, kc * 64, pol);
+          }
+          __syncwarp();
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (leader CTA) ----------------
+    if (rank == 0) {
+      const uint32_t idesc_a = make_idesc_bf16(256, N1, 1, 1);
+      constexpr uint32_t idesc_b = make_idesc_bf16(256, 128, 1, 1);
+      constexpr uint32_t idesc_1 = make_idesc_bf16(256, 16, 1, 1);
+      constexpr uint32_t kHi = desc_hi_sw128(1024);
+      const uint32_t a_lo0 = desc_lo_sw128(smem_u32(s_ring), 8192);
+      const uint32_t o_lo = desc_lo_sw128(smem_u32(s_ones), 8192);
+      int s = 0; uint32_t ph = 0;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int in_flush = c % kWsFlushChunks;
+        if (in_flush == 0 && c > 0) mbar_wait(tmem_empty, ((c / kWsFlushChunks) - 1) & 1u);   // accumulator drained
+        mbar_wait(&full[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t al = a_lo0 + s * (stage_bytes >> 4), bl = al + (kWsABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accum = (k != 0) ? 1u : (uint32_t)(in_flush != 0);
+            const uint64_t adesc = pack64(al + k * 128, kHi);
+            umma_bf16_pair(tmem_base, adesc, pack64(bl + k * 128, kHi), idesc_a, accum);
+            if (N2) umma_bf16_pair(tmem_base + 256, adesc, pack64(bl + nb1 * 512 + k * 128, kHi), idesc_b, accum);
+            umma_bf16_pair(tmem_base + bias_col, adesc, pack64(o_lo, kHi), idesc_1, accum);   // column sums of A (bias gradient)
+          }
+          umma_commit_pair(&empty[s]);
+          if (in_flush == kWsFlushChunks - 1 || c == n_chunks - 1) umma_commit_pair(tmem_full);
+        }
+        __syncwarp();
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: accumulator -> (+=) fp32 partial tile, once per flush ----------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool writes = (int)rank < P.m_tiles;
+    float* out = P.partial + ((size_t)split * P.m_tiles + rank) * ((size_t)128 * (BN + 1));
+    const uint32_t tmem_empty_leader = mapa_u32(smem_u32(tmem_empty), 0);
+    if (n_chunks == 0 && writes) {
+      for (int c = 0; c < BN; ++c) out[(size_t)row * BN + c] = 0.f;
+      out[(size_t)128 * BN + row] = 0.f;
+    }
+    for (int f = 0; f < n_flush; ++f) {
+      mbar_wait(tmem_full, f & 1u);
+      tcgen05_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      if (writes) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_base + c * 32, v);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)row * BN + c * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float4 a = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                   __uint_as_float(v[4 * e + 3]));
+            if (f > 0) { const float4 o = dst[e]; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+            dst[e] = a;
+          }
+        }
+        uint32_t v16[16];
+        tmem_ld_x16(t_base + bias_col, v16);
+        tmem_ld_wait();
+        float bsum = __uint_as_float(v16[0]);
+        if (f > 0) bsum += out[(size_t)128 * BN + row];
+        out[(size_t)128 * BN + row] = bsum;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+// bytes one SM pulls per 64-point chunk for this problem (the busier CTA of the pair): what sets a split's pace
+static int ws_bytes_per_chunk(const WsHostProblem& h) {
+  const int a0 = h.a_cols - h.a_col0;                               // in-bounds features of CTA 0's A half
+  const int a = (a0 >= 128 ? 128 : (a0 > 0 ? a0 : 0)) * 128;
+  const int b = (h.N == 64 ? 64 : (h.N == 320 ? 192 : 128)) * 128;
+  return a + b;
+}
+
+// Splits per problem: the slowest pair sets the pace, so hand out pairs one at a time to whichever problem has the most
+// bytes per split.
+int wgrad_stream_plan(const WsHostProblem* probs, int n, int pairs, int* splits_out) {
+  RN_REQUIRE(probs && n > 0 && n <= kWsMaxProblems && splits_out && pairs >= n);
+  for (int i = 0; i < n; ++i) splits_out[i] = 1;
+  for (int used = n; used < pairs; ++used) {
+    int best = 0; double worst = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double load = (double)ws_bytes_per_chunk(probs[i]) / splits_out[i];
+      if (load > worst) { worst = load; best = i; }
+    }
+    splits_out[best] += 1;
+  }
+  return RN_OK;
+}
+
+int wgrad_stream_launch(const WsHostProblem* probs, int n, int64_t M, const uint32_t* flags, int ctas, float* scratch,
+                        size_t region_floats, TnInfo* infos, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != RN_OK) return rc;
+  RN_REQUIRE(probs && n > 0 && n <= kWsMaxProblems && M > 0 && flags && scratch && infos && ctas >= 2 * n);
+  static thread_local WsParams p;
+  int splits[kWsMaxProblems];
+  if ((rc = wgrad_stream_plan(probs, n, ctas / 2, splits)) != RN_OK) return rc;
+  int pair = 0;
+  double flops = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const WsHostProblem& h = probs[i];
+    RN_REQUIRE(h.A && h.B && h.Mo > 0 && h.Mo <= 256 && (h.N == 320 || h.N == 256 || h.N == 64) && h.a_col0 % 64 == 0 &&
+               h.a_col0 + h.Mo <= h.a_cols + 63 && h.b_cols >= h.N);
+    WsProblem& P = p.prob[i];
+    if ((rc = make_tmap(&P.tmA, h.A, h.a_cols, M, h.lda, 64)) != RN_OK) return rc;
+    if ((rc = make_tmap(&P.tmB, h.B, h.b_cols, M, h.ldb, 64)) != RN_OK) return rc;
+    P.BN = h.N; P.m_tiles = (h.Mo + 127) / 128; P.splits = splits[i]; P.a_col0 = h.a_col0; P.flag_row = h.flag_row;
+    P.pair0 = pair;
+    P.partial = scratch + (size_t)i * region_floats;
+    RN_REQUIRE((size_t)P.splits * P.m_tiles * 128 * (h.N + 1) <= region_floats);
+    pair += P.splits;
+    infos[i].m_tiles = P.m_tiles; infos[i].splits = P.splits; infos[i].N = h.N; infos[i].scratch = P.partial;
+    flops += 2.0 * (double)M * h.N * h.Mo;
+  }
+  p.n_prob = n; p.n_pairs = pair; p.n_blocks = (int)ceil_div(M, 128); p.m_rows = M; p.flags = flags;
+  p.l2_hints = (g_l2_hints >> 1) & 1;
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured))
+    RN_CUDA_CHECK(cudaFuncSetAttribute(wgrad_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem));
+  g_prof_next_flops = flops;
+  int slot;
+  prof_begin(2 /*MODE_TN*/, st, &slot);
+  wgrad_stream_kernel<<<dim3(2 * pair), dim3(kWsThreads), kWsSmem, st>>>(p);
+  prof_end(slot, st);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+}  // namespace rn

@@ -30,7 +30,7 @@ def timed(fn, n=3):
     lib.rn_prof_enable(1)
     for _ in range(n):
         fn()
-    ms3, fl3, n3 = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_int * 3)()
+    ms3, fl3, n3 = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_int * 4)()
     lib.rn_prof_collect(ms3, fl3, n3)
     lib.rn_prof_enable(0)
     return ms3[0] / n

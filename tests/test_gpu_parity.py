@@ -4,6 +4,7 @@ CPU oracle (oracle/nerf_oracle.py) and the committed golden vectors of the unmod
 Tolerances (north_star): bit-exact for indices / pixel bookkeeping / z-values; 1e-5 relative for
 fp32 rays, weights and compositing; bf16 tensor-core MLP within 1e-2 max-abs RGB and 0.05 dB PSNR.
 """
+import ctypes
 import numpy as np
 import pytest
 import torch
@@ -780,6 +781,9 @@ def test_chained_data_gradients_equal_per_layer(rn, dev):
     w = O.make_weights(17, sharpen=True)
     net = load_net(rn, w, dev)
     rng = np.random.default_rng(9)
+    stream_sms = ctypes.c_int(0)
+    lib.rn_get_flag(9, ctypes.byref(stream_sms))
+    lib.rn_set_flag(9, 0)          # the weight-gradient stream sums its splits in another order (its own test below)
     try:
         for M in (1, 255, 256, 257, 1000, 40000, 151808):
             pts = T(rng.uniform(-3, 3, (M, 3)).astype(np.float32), dev)
@@ -803,6 +807,47 @@ def test_chained_data_gradients_equal_per_layer(rn, dev):
             assert outs[("grad", 1)].abs().max().item() > 0
     finally:
         lib.rn_set_flag(3, 1)
+        lib.rn_set_flag(9, stream_sms.value)
+
+
+def test_weight_gradient_stream_beside_the_chain(rn, dev):
+    """The weight gradients computed BESIDE the data-gradient chain (wgrad_stream.cu: one persistent launch on its own
+    SMs, taking every block of dH out of L2 as the chain's store warp publishes it) against the split-K launches that
+    run after the chain.  Same operands, same MMAs; only the assignment of point blocks to splits differs, so parameter
+    gradients agree to fp32 summation order (bound: 2e-6 of the tensor's largest entry per 1,000 points summed), the
+    gradients w.r.t. points and directions are bit-identical, and two runs of the stream are bit-identical to each
+    other (static assignment -- a stale or early read of a block would show up here)."""
+    from robust_nerf_b200 import _lib
+    lib = _lib.lib()
+    w = O.make_weights(17, sharpen=True)
+    net = load_net(rn, w, dev)
+    rng = np.random.default_rng(19)
+    prev = ctypes.c_int(0)
+    lib.rn_get_flag(9, ctypes.byref(prev))
+    names = [n for n, _ in net.named_parameters()]
+    try:
+        for M, sms in ((1, 72), (255, 72), (257, 24), (1000, 100), (40000, 72), (151808, 64), (786432, 80)):
+            pts = T(rng.uniform(-3, 3, (M, 3)).astype(np.float32), dev)
+            dirs = T(rng.standard_normal((M, 3)).astype(np.float32), dev)
+            gout = T(rng.standard_normal((M, 4)).astype(np.float32), dev)
+            outs = {}
+            for tag, flag in (("seq", 0), ("str", sms), ("str2", sms)):
+                lib.rn_set_flag(9, flag)
+                net.zero_grad()
+                x = pts.clone().requires_grad_(True)
+                d = dirs.clone().requires_grad_(True)
+                raw = net.forward_raw(x, d, 1)
+                (raw * gout).sum().backward()
+                outs[tag] = ([p.grad.clone() for p in net.parameters()], x.grad.clone(), d.grad.clone())
+            torch.cuda.synchronize()
+            assert torch.equal(outs["seq"][1], outs["str"][1]) and torch.equal(outs["seq"][2], outs["str"][2]), M
+            for n, a, b, c in zip(names, outs["seq"][0], outs["str"][0], outs["str2"][0]):
+                assert torch.isfinite(b).all(), (M, n)
+                assert torch.equal(b, c), (M, n, "two runs of the stream differ", (b - c).abs().max().item())
+                tol = 2e-6 * max(1.0, M / 1000.0) ** 0.5 * 4 * max(a.abs().max().item(), 1e-6)
+                assert (a - b).abs().max().item() <= tol, (M, n, (a - b).abs().max().item(), tol)
+    finally:
+        lib.rn_set_flag(9, prev.value)
 
 
 def test_trainer_state_dict_and_module_semantics(rn, dev):
