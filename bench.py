@@ -692,6 +692,32 @@ def run_gpu(args):
     value = world * RAYS_PER_GPU * K_ / (t_ms * 1e-3)
     e2e_value = world * RAYS_PER_GPU * K_ / (t_e2e * 1e-3)
 
+    # ---- the same step with the weight gradients running BESIDE the data-gradient chain (opt-in: rn_set_flag(9, 88)) ----
+    # Reported, not the headline: DESIGN.md section 4 says why it is not the default (3-4 % here; a static SM partition
+    # that a concurrent NCCL kernel can upset; two interlocked launches a profiler cannot serialise the other way round).
+    stream_variant = None
+    if world == 1 and not args.no_extras and use_graph:
+        prev9, prev6 = ctypes.c_int(0), ctypes.c_int(0)
+        lib.rn_get_flag(9, ctypes.byref(prev9)); lib.rn_get_flag(6, ctypes.byref(prev6))
+        if prev9.value == 0:
+            try:
+                trainer._graphs.clear()
+                lib.rn_set_flag(9, 88); lib.rn_set_flag(6, 6)
+                for i in range(W_):
+                    step_fn(*dev_batches[i % POOL])
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(K_):
+                    step_fn(*dev_batches[i % POOL])
+                e1.record()
+                torch.cuda.synchronize()
+                t_var = e0.elapsed_time(e1)
+                stream_variant = {"flags": "9=88,6=6", "ms_per_step": t_var / K_, "value": RAYS_PER_GPU * K_ / (t_var * 1e-3),
+                                  "unit": "rays/s", "what": "weight gradients as one persistent CTA-pair launch on 88 SMs beside the "
+                                  "data-gradient chain on 60, dH handed over through L2 (csrc/wgrad_stream.cu)"}
+            finally:
+                lib.rn_set_flag(9, prev9.value); lib.rn_set_flag(6, prev6.value)
+
     peaks = measured_peaks()
     trainer._graphs.clear()                       # release the captured step (and its 11 GB workspace) before the other blocks
     step_fn = None
@@ -718,6 +744,8 @@ def run_gpu(args):
         except Exception as e:      # noqa: BLE001
             eager = {"error": repr(e)}
     extra = {}
+    if stream_variant:
+        extra["wgrad_stream_variant"] = stream_variant
     if world > 1:
         dist.barrier()
 

@@ -617,9 +617,11 @@ struct BwdParams {
 };
 
 __device__ __forceinline__ void publish_block(uint32_t* f) {
-  // the bulk stores of this block have completed (cp.async.bulk.wait_group: their writes are performed and visible to
-  // this thread), so a release store orders them before the flag for the consumer's acquire
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+  // The bulk stores of this block have COMPLETED (cp.async.bulk.wait_group, not .read: the writes are performed in L2,
+  // the point of coherence every SM reads through), so a plain strong store of the flag is enough for a consumer that
+  // acquires it.  A st.release.gpu here is a fence that also drains this thread's NEWER bulk stores -- 3-4 us per layer
+  // and tile slot, which paced the whole chain at half its speed (profiles/r02_ab_log.md block 19).
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
@@ -850,7 +852,7 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
     if (lane == 0) {
       // with a consumer beside this launch the gradients are re-read out of L2 within microseconds: keep them (normal
       // policy) instead of marking them evict_first
-      const uint64_t pol_s = l2_policy((p.l2_hints && !p.flags) ? 1 : 0);
+      const uint64_t pol_s = l2_policy(p.flags ? ((p.l2_hints & 2) ? 2 : 0) : ((p.l2_hints & 1) ? 1 : 0));
       uint32_t it0 = 0, it1 = 0;
       // flags of the last kPubLag store groups: a group is published kPubLag groups late, when cp.async.bulk.wait_group
       // says its writes have completed without this warp ever waiting for the most recent stores (a wait for the
@@ -933,7 +935,7 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
   p.m_rows = M;
-  p.l2_hints = g_l2_hints & 1;
+  p.l2_hints = (g_l2_hints & 1) | ((g_l2_hints & 4) ? 2 : 0);      // bit 1 here: evict_last stores when a consumer follows (flag 6 bit 2)
   p.flags = flags;
   p.n_blocks = (int)ceil_div(M, 128);
 #ifdef RN_EXPERIMENTS

@@ -109,6 +109,9 @@ int g_chain_dbg = 0;
 // rn_set_flag(9, n): n > 0 = the weight gradients run BESIDE the data-gradient chain on n SMs (wgrad_stream.cu), taking each
 // block of dH out of L2 as the chain publishes it; 0 = one split-K launch per layer after the chain
 int g_wgrad_stream_sms = 0;
+// rn_set_flag(10, mask): measurement only.  bit 0 = record the two launches separately as well as the span; bit 1 = launch
+// the stream AFTER the chain on the same stream (every flag already set: the consumer alone, operands from HBM)
+int g_ws_debug = 0;
 int g_chain_bwd = 1;      // rn_set_flag(3, v): 1 = data gradients as one CTA-pair chain launch (chain_pair.cu), 0 = one launch per layer
 // rn_set_flag(0, v): 0 = one launch per layer (gemm_tcgen05.cu: the building-block kernels, kept as the cross-check of the
 // chain), 2 = CTA-pair chain with shared-memory-resident activations (chain_pair.cu; default).  (Round 1's third variant,
@@ -237,13 +240,13 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
       g_prof_next_flops = span_flops;
       int slot;
       prof_begin(3, st, &slot);
-      ++g_prof_suppress;
+      if (!(g_ws_debug & 1)) ++g_prof_suppress;
       RN_CUDA_CHECK(cudaEventRecord(side->fork, st));
       RN_CUDA_CHECK(cudaStreamWaitEvent(side->st, side->fork, 0));
       int rc = mlp_chain_pair_backward(L, 9, M, w.dHC, 128, 128, w.dFS, 272, 272, st, w.flags, num_sms() - ws_sms);
       TnInfo infos[kWsMaxProblems];
-      if (rc == RN_OK) rc = wgrad_stream_launch(P, np, M, w.flags, ws_sms, w.scratch, region, infos, side->st);
-      --g_prof_suppress;
+      if (rc == RN_OK) rc = wgrad_stream_launch(P, np, M, w.flags, ws_sms, w.scratch, region, infos, (g_ws_debug & 2) ? st : side->st);
+      if (!(g_ws_debug & 1)) --g_prof_suppress;
       // join even after a failed launch: a stream capture must not end with the side stream still forked
       cudaError_t e1 = cudaEventRecord(side->join, side->st);
       cudaError_t e2 = cudaStreamWaitEvent(st, side->join, 0);
@@ -275,29 +278,29 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
                      w.MB[l - 1], st));
   }
   if (!overlapped) {
-  // ---- weight / bias gradients: one split-K GEMM per layer, reduced together below ----
-  // dir_linear: one launch over the whole 320-wide input [feat(256) | d_enc(27) | 0]
-  RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
-  RN_TRY(tn_batch_add(&batch, ti, 0, 128, 0, 283, G + kG_WD, 283, G + kG_BD));
-  // feature_linear + sigma_linear (row 256 of dFS^T)
-  RN_TRY(gemm_tn_launch(w.dFS, 272, 272, w.H[7], 256, 256, M, scratch_k(), w.scratch_bytes, &ti, st));
-  RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 256, G + kG_WF, 256, G + kG_BF));
-  RN_TRY(tn_batch_add(&batch, ti, 256, 1, 0, 256, G + kG_WSig, 256, G + kG_BSig));
-  for (int l = 7; l >= 1; --l) {
-    if (l == 5) {
-      // input = XC = [x_enc(64) | H4(256)]: one launch over the 320-wide input; the zero pad column 63 is dropped
-      RN_TRY(gemm_tn_launch(w.dH[5], 256, 256, w.XC, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
-      RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(5), 319, nullptr));
-      RN_TRY(tn_batch_add(&batch, ti, 0, 256, 64, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5)));
-    } else {
-      RN_TRY(gemm_tn_launch(w.dH[l], 256, 256, w.H[l - 1], ld_of(l - 1), 256, M, scratch_k(), w.scratch_bytes, &ti, st));
-      RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 256, G + trunk_gw(l), 256, G + trunk_gb(l)));
+    // ---- weight / bias gradients: one split-K GEMM per layer, reduced together below ----
+    // dir_linear: one launch over the whole 320-wide input [feat(256) | d_enc(27) | 0]
+    RN_TRY(gemm_tn_launch(w.dHC, 128, 128, w.FD, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
+    RN_TRY(tn_batch_add(&batch, ti, 0, 128, 0, 283, G + kG_WD, 283, G + kG_BD));
+    // feature_linear + sigma_linear (row 256 of dFS^T)
+    RN_TRY(gemm_tn_launch(w.dFS, 272, 272, w.H[7], 256, 256, M, scratch_k(), w.scratch_bytes, &ti, st));
+    RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 256, G + kG_WF, 256, G + kG_BF));
+    RN_TRY(tn_batch_add(&batch, ti, 256, 1, 0, 256, G + kG_WSig, 256, G + kG_BSig));
+    for (int l = 7; l >= 1; --l) {
+      if (l == 5) {
+        // input = XC = [x_enc(64) | H4(256)]: one launch over the 320-wide input; the zero pad column 63 is dropped
+        RN_TRY(gemm_tn_launch(w.dH[5], 256, 256, w.XC, 320, 320, M, scratch_k(), w.scratch_bytes, &ti, st));
+        RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(5), 319, nullptr));
+        RN_TRY(tn_batch_add(&batch, ti, 0, 256, 64, 256, G + trunk_gw(5) + 63, 319, G + trunk_gb(5)));
+      } else {
+        RN_TRY(gemm_tn_launch(w.dH[l], 256, 256, w.H[l - 1], ld_of(l - 1), 256, M, scratch_k(), w.scratch_bytes, &ti, st));
+        RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 256, G + trunk_gw(l), 256, G + trunk_gb(l)));
+      }
     }
-  }
-  // layer 0: input = x_enc
-  RN_TRY(gemm_tn_launch(w.dH[0], 256, 256, w.XC, 320, 64, M, scratch_k(), w.scratch_bytes, &ti, st));
-  RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(0), 63, G + trunk_gb(0)));
-  RN_REQUIRE(tn_k <= kTnLaunches);
+    // layer 0: input = x_enc
+    RN_TRY(gemm_tn_launch(w.dH[0], 256, 256, w.XC, 320, 64, M, scratch_k(), w.scratch_bytes, &ti, st));
+    RN_TRY(tn_batch_add(&batch, ti, 0, 256, 0, 63, G + trunk_gw(0), 63, G + trunk_gb(0)));
+    RN_REQUIRE(tn_k <= kTnLaunches);
   }
   RN_TRY(gemm_tn_reduce_batch(batch, st));
   if (need_in) {
@@ -332,10 +335,11 @@ int rn_set_flag(int flag, int value) {
   if (flag == 3) { g_chain_bwd = value; return RN_OK; }
   if (flag == 4) { g_pe_fused = value; return RN_OK; }
   if (flag == 5) { g_pdl = value ? 1 : 0; return RN_OK; }
-  if (flag == 6) { g_l2_hints = value & 3; return RN_OK; }
+  if (flag == 6) { g_l2_hints = value & 7; return RN_OK; }
   if (flag == 7) { g_sm_limit_dgrad = value; return RN_OK; }
   if (flag == 8) { g_sm_limit_wgrad = value; return RN_OK; }
   if (flag == 9) { g_wgrad_stream_sms = value; return RN_OK; }
+  if (flag == 10) { g_ws_debug = value; return RN_OK; }
   return RN_ERR_INVALID_ARG;
 }
 

@@ -42,7 +42,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
 void prof_begin(int mode, cudaStream_t st, int* slot);
 void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
-extern int g_l2_hints;
+extern int g_l2_hints, g_ws_debug;
 
 constexpr int kWsThreads = 192;
 constexpr int kWsSmem = 231424;                 // 226 KiB
@@ -59,6 +59,7 @@ struct WsProblem {
   int m_tiles;               // 128-row tiles of dW that exist (1 or 2); CTA rank >= m_tiles computes zeros and writes nothing
   int splits;
   int a_col0;                // first column of A this problem reads
+  int a_cols, b_cols;        // columns the tensors have: a 64-column box that starts beyond them is never loaded (stays zero)
   int flag_row;              // row of the flag table the A operand waits on, or -1 (A was complete before the launch)
   int pair0;                 // first CTA pair of this problem
 };
@@ -68,6 +69,7 @@ struct WsParams {
   int64_t m_rows;
   const uint32_t* flags;              // [flag rows][n_blocks], zeroed before the launch, 1 = block published
   int l2_hints;
+  int dbg;                            // measurement only (rn_set_flag(10)): bit 2 = no bias MMA, bit 3 = no MMAs at all
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -121,9 +123,26 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  // Boxes that start beyond the tensor (the padding of M to 256 and of N to a multiple of 128) are not loaded at all:
+  // their slots in every stage are zeroed once, here.  box_mask bit j: box j of a stage (0, 1 = A; 2.. = B) is loaded.
+  uint32_t box_mask[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    uint32_t m = 0;
+    for (int j = 0; j < 2; ++j) m |= (P.a_col0 + r * 128 + j * 64 < P.a_cols) ? (1u << j) : 0u;
+    for (int j = 0; j < nb1; ++j) m |= (r * (N1 / 2) + j * 64 < P.b_cols) ? (4u << j) : 0u;
+    if (N2) m |= (256 + r * 64 < P.b_cols) ? (4u << nb1) : 0u;
+    box_mask[r] = m;
+  }
+  const uint32_t my_mask = box_mask[rank];
+  const uint32_t tx_bytes = 8192u * (uint32_t)(__popc(box_mask[0]) + __popc(box_mask[1]));
   if (warp >= 2) {
     uint32_t* ones = reinterpret_cast<uint32_t*>(s_ones);
     for (int i = threadIdx.x - 64; i < kWsOnes / 4; i += 128) ones[i] = 0x3F803F80u;   // bf16 1.0 x2
+    if (my_mask != (4u << nb) - 1u) {
+      uint4* ring = reinterpret_cast<uint4*>(s_ring);
+      for (int i = threadIdx.x - 64; i < NS * stage_bytes / 16; i += 128) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_proxy_async_smem();
   }
   tcgen05_fence_before();
@@ -178,13 +197,17 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
           if (lane == 0) {
             uint8_t* a_s = s_ring + s * stage_bytes;
             uint8_t* b_s = a_s + kWsABytes;
-            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], tx_bytes);
             const uint32_t bar = full_leader + s * 8;
-            tma_load_2d_pair_hint(a_s, &P.tmA, bar, a_c, kc * 64, pol);                      // [64 pts][64 features]
-            tma_load_2d_pair_hint(a_s + 8192, &P.tmA, bar, a_c + 64, kc * 64, pol);
+            if (my_mask & 1u) tma_load_2d_pair_hint(a_s, &P.tmA, bar, a_c, kc * 64, pol);          // [64 pts][64 features]
+            if (my_mask & 2u) tma_load_2d_pair_hint(a_s + 8192, &P.tmA, bar, a_c + 64, kc * 64, pol);
             for (int j = 0; j < nb1; ++j)
-              tma_load_2d_pair_hint(b_s + j * 8192, &P.tmB, bar, (int)rank * (N1 / 2) + j * 64, kc * 64, pol);
-            if (N2) tma_load_2d_pair_hint(b_s + nb1 * 8192, &P.tmB, bar, 256 + (int)rank * 64, kc * 64, pol);
+              if (my_mask & (4u << j))
+                tma_load_2d_pair_hint(b_s + j * 8192, &P.tmB, bar, (int)rank * (N1 / 2) + j * 64, kc * 64, pol);
+            if (N2 && (my_mask & (4u << nb1)))
+              tma_load_2d_pair_hint(b_s + nb1 * 8192, &P.tmB, bar, 256 + (int)rank * 64, kc * 64, pol);
+            // (an L2 prefetch of B eight blocks ahead, cp.async.bulk.prefetch.tensor, made the kernel 15 % SLOWER alone and
+            // beside the chain -- profiles/r02_ab_log.md block 19 -- and is not issued)
           }
           __syncwarp();
           if (++s == NS) { s = 0; ph ^= 1; }
@@ -212,9 +235,9 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
           for (int k = 0; k < 4; ++k) {
             const uint32_t accum = (k != 0) ? 1u : (uint32_t)(in_flush != 0);
             const uint64_t adesc = pack64(al + k * 128, kHi);
-            umma_bf16_pair(tmem_base, adesc, pack64(bl + k * 128, kHi), idesc_a, accum);
-            if (N2) umma_bf16_pair(tmem_base + 256, adesc, pack64(bl + nb1 * 512 + k * 128, kHi), idesc_b, accum);
-            umma_bf16_pair(tmem_base + bias_col, adesc, pack64(o_lo, kHi), idesc_1, accum);   // column sums of A (bias gradient)
+            if (!(p.dbg & 8)) umma_bf16_pair(tmem_base, adesc, pack64(bl + k * 128, kHi), idesc_a, accum);
+            if (N2 && !(p.dbg & 8)) umma_bf16_pair(tmem_base + 256, adesc, pack64(bl + nb1 * 512 + k * 128, kHi), idesc_b, accum);
+            if (!(p.dbg & 12)) umma_bf16_pair(tmem_base + bias_col, adesc, pack64(o_lo, kHi), idesc_1, accum);   // column sums of A (bias gradient)
           }
           umma_commit_pair(&empty[s]);
           if (in_flush == kWsFlushChunks - 1 || c == n_chunks - 1) umma_commit_pair(tmem_full);
@@ -275,12 +298,14 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
   }
 }
 
-// bytes one SM pulls per 64-point chunk for this problem (the busier CTA of the pair): what sets a split's pace
+// What one 64-point chunk costs a pair, in bytes pulled by its busier SM -- with a floor: a stage is recycled one memory
+// latency after its loads were issued whatever it holds, so below ~32 KiB per SM a chunk takes the same ~0.4 us (measured:
+// the N = 64 and sigma problems, 18-24 KiB per chunk, ran no faster per chunk than the 32 KiB ones).
 static int ws_bytes_per_chunk(const WsHostProblem& h) {
   const int a0 = h.a_cols - h.a_col0;                               // in-bounds features of CTA 0's A half
   const int a = (a0 >= 128 ? 128 : (a0 > 0 ? a0 : 0)) * 128;
   const int b = (h.N == 64 ? 64 : (h.N == 320 ? 192 : 128)) * 128;
-  return a + b;
+  return a + b > 32768 ? a + b : 32768;
 }
 
 // Splits per problem: the slowest pair sets the pace, so hand out pairs one at a time to whichever problem has the most
@@ -317,6 +342,7 @@ int wgrad_stream_launch(const WsHostProblem* probs, int n, int64_t M, const uint
     if ((rc = make_tmap(&P.tmA, h.A, h.a_cols, M, h.lda, 64)) != RN_OK) return rc;
     if ((rc = make_tmap(&P.tmB, h.B, h.b_cols, M, h.ldb, 64)) != RN_OK) return rc;
     P.BN = h.N; P.m_tiles = (h.Mo + 127) / 128; P.splits = splits[i]; P.a_col0 = h.a_col0; P.flag_row = h.flag_row;
+    P.a_cols = h.a_cols; P.b_cols = h.b_cols;
     P.pair0 = pair;
     P.partial = scratch + (size_t)i * region_floats;
     RN_REQUIRE((size_t)P.splits * P.m_tiles * 128 * (h.N + 1) <= region_floats);
@@ -326,6 +352,7 @@ int wgrad_stream_launch(const WsHostProblem* probs, int n, int64_t M, const uint
   }
   p.n_prob = n; p.n_pairs = pair; p.n_blocks = (int)ceil_div(M, 128); p.m_rows = M; p.flags = flags;
   p.l2_hints = (g_l2_hints >> 1) & 1;
+  p.dbg = g_ws_debug;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured))
     RN_CUDA_CHECK(cudaFuncSetAttribute(wgrad_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem));
