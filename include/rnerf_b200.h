@@ -44,12 +44,16 @@ unsigned long long rn_launch_count(void);
  * stream; rn_prof_collect synchronises and returns, per mode (0 NT fwd, 1 NN dgrad, 2 TN wgrad,
  * 3 = NN chain and TN stream running side by side, timed as one span), the summed kernel
  * milliseconds, executed FLOPs (2*M*N*K incl. padding) and launch counts: arrays of FOUR. */
-/* tuning flags: flag 0 = run the MLP forward as ONE layer-chained persistent launch (default 1)
- * instead of ten per-layer GEMM launches (0). Results are identical.
- * flag 2 = operand ring depths of the chained kernel: 0 -> (A,B) = (5,2) stages, 1 -> (3,3).
- * flag 1 exists only in builds made with RN_EXPERIMENTS=1 (bottleneck experiments of
- * scripts/chain_experiments.py: switches parts of the pipeline off, results are then wrong);
- * the shipped library rejects it. */
+/* Kernel-variant flags (A/B timing and cross-checks; every variant is parity-tested against the others):
+ *   0: MLP forward as one launch per layer (0) or as the CTA-pair chain (2, default)
+ *   3: data gradients as one launch per layer (0) or as the CTA-pair chain (1, default)
+ *   4: inference encodes the points inside the forward chain (1, default) or in a separate kernel (0)
+ *   5: programmatic dependent launch for the GEMM-family kernels (default 0)
+ *   6: L2 cache hints, bit mask: 1 chains, 2 weight-gradient loads evict_first, 4 chain stores evict_last (default 0)
+ *   9: SMs given to the weight-gradient stream that runs beside the data-gradient chain (0 = off, default)
+ *   7, 8, 10: measurement only (SM limit of the data-gradient chain / of the split-K kernels; bit mask of
+ *             timing options for the overlapped backward).  Flag 1 exists only in RN_EXPERIMENTS builds.
+ * rn_get_flag reads a flag back.  Unknown flags return RN_ERR_INVALID_ARG. */
 int rn_set_flag(int flag, int value);
 int rn_get_flag(int flag, int* value_host);
 int rn_prof_enable(int on);
