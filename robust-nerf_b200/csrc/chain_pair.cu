@@ -671,7 +671,6 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int n_groups = (p.n_ptiles + 1) >> 1;
-
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     const uint32_t full_b_leader = mapa_u32(smem_u32(full_b), 0);

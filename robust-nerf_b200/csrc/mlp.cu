@@ -354,6 +354,7 @@ int rn_get_flag(int flag, int* value_host) {
     case 7: *value_host = g_sm_limit_dgrad; return RN_OK;
     case 8: *value_host = g_sm_limit_wgrad; return RN_OK;
     case 9: *value_host = g_wgrad_stream_sms; return RN_OK;
+    case 10: *value_host = g_ws_debug; return RN_OK;
     default: return RN_ERR_INVALID_ARG;
   }
 }
