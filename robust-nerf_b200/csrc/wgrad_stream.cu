@@ -27,7 +27,8 @@
 // than the device has, so they are co-resident whatever order the hardware starts them in; a wait on a flag that never
 // comes traps after 4 s instead of hanging the device.
 //
-// Warp roles (192 threads): 0 = flag polling + TMA producer, 1 = TMEM owner + MMA issuer (leader CTA), 2..5 = epilogue.
+// Warp roles (224 threads): 0 = flag polling + A producer, 1 = TMEM owner + MMA issuer (leader CTA), 2..5 = epilogue,
+// 6 = B producer.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "gemm.h"
@@ -44,12 +45,13 @@ void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
 extern int g_l2_hints, g_ws_debug;
 
-constexpr int kWsThreads = 192;
+constexpr int kWsThreads = 224;                 // 7 warps
 constexpr int kWsSmem = 231424;                 // 226 KiB
 constexpr int kWsOnes = 2048;                   // 16 k-rows x 128 B of bf16 1.0 (first 2 KiB of the aligned buffer)
 constexpr int kWsRing = kWsSmem - 1024 /*alignment slack*/ - kWsOnes - 1024 /*barriers*/;
 constexpr int kWsABytes = 16384;                // [64 points][128 output features]
-constexpr int kWsMaxStages = 8;
+constexpr int kWsAStages = 5;                   // dH tiles: out of L2 when the consumer keeps up (short latency)
+constexpr int kWsMaxBStages = 12;               // H tiles: always from HBM -> the deep ring, and it runs ahead of the flags
 constexpr int kWsFlushChunks = 256;             // accumulator flushed to the fp32 partial every 256 chunks (16,384 points)
 
 struct WsProblem {
@@ -89,11 +91,13 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
   uint8_t* s_ones = smem;
   uint8_t* s_ring = smem + kWsOnes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOnes + kWsRing);
-  uint64_t* full = bars;                     // [8]  leader: bytes of both CTAs' loads
-  uint64_t* empty = bars + 8;                // [8]  each CTA (multicast commit)
-  uint64_t* tmem_full = bars + 16;           //      each CTA (multicast commit)
-  uint64_t* tmem_empty = bars + 17;          //      leader: 8 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* full_a = bars;                   // [8]   leader: bytes of both CTAs' A loads
+  uint64_t* empty_a = bars + 8;              // [8]   each CTA (multicast commit)
+  uint64_t* full_b = bars + 16;              // [12]  leader: bytes of both CTAs' B loads
+  uint64_t* empty_b = bars + 28;             // [12]  each CTA
+  uint64_t* tmem_full = bars + 40;           //       each CTA (multicast commit)
+  uint64_t* tmem_empty = bars + 41;          //       leader: 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,14 +114,22 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
   const int N2 = BN == 320 ? 128 : 0;
   const int nb1 = N1 / 128;                                  // 64-column boxes of B per CTA for MMA 1
   const int nb = nb1 + (N2 ? 1 : 0);
-  const int stage_bytes = kWsABytes + nb * 8192;
-  const int ns_raw = kWsRing / stage_bytes;
-  const int NS = ns_raw > kWsMaxStages ? kWsMaxStages : ns_raw;
+  // Two rings.  The B operand (H_{l-1}, written by the forward pass) needs no flag and always comes from HBM: its ring
+  // is deep and its producer warp runs as far ahead as the ring allows.  The A operand (dH_l) is loaded only once its
+  // block is published: a shallower ring.  (Measured against one combined ring of 6 stages: no difference, alone or beside
+  // the chain -- what paces a pair is what one SM can take in, ~65 GB/s of HBM-sourced bytes, not the depth of its ring;
+  // profiles/r02_ab_log.md block 19.  Kept because the B stream no longer stalls behind a flag.)
+  const int NA = kWsAStages;
+  const int b_stage = nb * 8192;
+  const int nb_raw = (kWsRing - NA * kWsABytes) / b_stage;
+  const int NB = nb_raw > kWsMaxBStages ? kWsMaxBStages : nb_raw;
+  uint8_t* s_ring_b = s_ring + NA * kWsABytes;
   const int bias_col = N1 + N2;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&P.tmA); prefetch_tmap(&P.tmB);
-    for (int i = 0; i < kWsMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < kWsMaxBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 8);
     fence_mbar_init();
@@ -135,13 +147,14 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
     box_mask[r] = m;
   }
   const uint32_t my_mask = box_mask[rank];
-  const uint32_t tx_bytes = 8192u * (uint32_t)(__popc(box_mask[0]) + __popc(box_mask[1]));
-  if (warp >= 2) {
+  const uint32_t tx_a = 8192u * (uint32_t)(__popc(box_mask[0] & 3u) + __popc(box_mask[1] & 3u));
+  const uint32_t tx_b = 8192u * (uint32_t)(__popc(box_mask[0] >> 2) + __popc(box_mask[1] >> 2));
+  if (warp >= 2 && warp < 6) {
     uint32_t* ones = reinterpret_cast<uint32_t*>(s_ones);
     for (int i = threadIdx.x - 64; i < kWsOnes / 4; i += 128) ones[i] = 0x3F803F80u;   // bf16 1.0 x2
     if (my_mask != (4u << nb) - 1u) {
       uint4* ring = reinterpret_cast<uint4*>(s_ring);
-      for (int i = threadIdx.x - 64; i < NS * stage_bytes / 16; i += 128) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = threadIdx.x - 64; i < (NA * kWsABytes + NB * b_stage) / 16; i += 128) ring[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();
   }
@@ -160,8 +173,8 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
   const int n_flush = (n_chunks + kWsFlushChunks - 1) / kWsFlushChunks;
 
   if (warp == 0) {
-    // ---------------- flag polling + TMA producer (both CTAs, each for its own halves) ----------------
-    const uint32_t full_leader = mapa_u32(smem_u32(full), 0);
+    // ---------------- flag polling + A producer (both CTAs, each for its own 128 features) ----------------
+    const uint32_t full_leader = mapa_u32(smem_u32(full_a), 0);
     const uint64_t pol = l2_policy(p.l2_hints ? 1 : 0);
     const uint32_t* frow = P.flag_row >= 0 ? p.flags + (size_t)P.flag_row * p.n_blocks : nullptr;
     const int a_c = P.a_col0 + (int)rank * 128;
@@ -193,24 +206,39 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
       for (int i = 0; i < nready && b < p.n_blocks; ++i, b += S) {
         for (int h = 0; h < 2 && issued < n_chunks; ++h, ++issued) {
           const int kc = b * 2 + h;
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait(&empty_a[s], ph ^ 1);
           if (lane == 0) {
-            uint8_t* a_s = s_ring + s * stage_bytes;
-            uint8_t* b_s = a_s + kWsABytes;
-            if (rank == 0) mbar_arrive_expect_tx(&full[s], tx_bytes);
+            uint8_t* a_s = s_ring + s * kWsABytes;
+            if (rank == 0) mbar_arrive_expect_tx(&full_a[s], tx_a);
             const uint32_t bar = full_leader + s * 8;
             if (my_mask & 1u) tma_load_2d_pair_hint(a_s, &P.tmA, bar, a_c, kc * 64, pol);          // [64 pts][64 features]
             if (my_mask & 2u) tma_load_2d_pair_hint(a_s + 8192, &P.tmA, bar, a_c + 64, kc * 64, pol);
-            for (int j = 0; j < nb1; ++j)
-              if (my_mask & (4u << j))
-                tma_load_2d_pair_hint(b_s + j * 8192, &P.tmB, bar, (int)rank * (N1 / 2) + j * 64, kc * 64, pol);
-            if (N2 && (my_mask & (4u << nb1)))
-              tma_load_2d_pair_hint(b_s + nb1 * 8192, &P.tmB, bar, 256 + (int)rank * 64, kc * 64, pol);
-            // (an L2 prefetch of B eight blocks ahead, cp.async.bulk.prefetch.tensor, made the kernel 15 % SLOWER alone and
-            // beside the chain -- profiles/r02_ab_log.md block 19 -- and is not issued)
           }
           __syncwarp();
-          if (++s == NS) { s = 0; ph ^= 1; }
+          if (++s == NA) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ---------------- B producer (both CTAs, each for its half of the columns): no flags, as far ahead as the ring goes ----------------
+    // (an L2 prefetch of B instead, cp.async.bulk.prefetch.tensor eight blocks ahead, made the kernel 15 % slower)
+    if (lane == 0) {
+      const uint32_t full_leader = mapa_u32(smem_u32(full_b), 0);
+      const uint64_t pol = l2_policy(p.l2_hints ? 1 : 0);
+      int s = 0; uint32_t ph = 0; int issued = 0;
+      for (int b = split; b < p.n_blocks; b += S) {
+        for (int h = 0; h < 2 && issued < n_chunks; ++h, ++issued) {
+          const int kc = b * 2 + h;
+          mbar_wait(&empty_b[s], ph ^ 1);
+          uint8_t* b_s = s_ring_b + s * b_stage;
+          if (rank == 0) mbar_arrive_expect_tx(&full_b[s], tx_b);
+          const uint32_t bar = full_leader + s * 8;
+          for (int j = 0; j < nb1; ++j)
+            if (my_mask & (4u << j))
+              tma_load_2d_pair_hint(b_s + j * 8192, &P.tmB, bar, (int)rank * (N1 / 2) + j * 64, kc * 64, pol);
+          if (N2 && (my_mask & (4u << nb1)))
+            tma_load_2d_pair_hint(b_s + nb1 * 8192, &P.tmB, bar, 256 + (int)rank * 64, kc * 64, pol);
+          if (++s == NB) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -222,15 +250,17 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
       constexpr uint32_t idesc_1 = make_idesc_bf16(256, 16, 1, 1);
       constexpr uint32_t kHi = desc_hi_sw128(1024);
       const uint32_t a_lo0 = desc_lo_sw128(smem_u32(s_ring), 8192);
+      const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_ring_b), 8192);
       const uint32_t o_lo = desc_lo_sw128(smem_u32(s_ones), 8192);
-      int s = 0; uint32_t ph = 0;
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       for (int c = 0; c < n_chunks; ++c) {
         const int in_flush = c % kWsFlushChunks;
         if (in_flush == 0 && c > 0) mbar_wait(tmem_empty, ((c / kWsFlushChunks) - 1) & 1u);   // accumulator drained
-        mbar_wait(&full[s], ph);
+        mbar_wait(&full_b[sb], phb);
+        mbar_wait(&full_a[sa], pha);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t al = a_lo0 + s * (stage_bytes >> 4), bl = al + (kWsABytes >> 4);
+          const uint32_t al = a_lo0 + sa * (kWsABytes >> 4), bl = b_lo0 + sb * (b_stage >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t accum = (k != 0) ? 1u : (uint32_t)(in_flush != 0);
@@ -239,14 +269,16 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
             if (N2 && !(p.dbg & 8)) umma_bf16_pair(tmem_base + 256, adesc, pack64(bl + nb1 * 512 + k * 128, kHi), idesc_b, accum);
             if (!(p.dbg & 12)) umma_bf16_pair(tmem_base + bias_col, adesc, pack64(o_lo, kHi), idesc_1, accum);   // column sums of A (bias gradient)
           }
-          umma_commit_pair(&empty[s]);
+          umma_commit_pair(&empty_a[sa]);
+          umma_commit_pair(&empty_b[sb]);
           if (in_flush == kWsFlushChunks - 1 || c == n_chunks - 1) umma_commit_pair(tmem_full);
         }
         __syncwarp();
-        if (++s == NS) { s = 0; ph ^= 1; }
+        if (++sa == NA) { sa = 0; pha ^= 1; }
+        if (++sb == NB) { sb = 0; phb ^= 1; }
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ---------------- epilogue warps: accumulator -> (+=) fp32 partial tile, once per flush ----------------
     const int q = warp & 3;
     const int row = q * 32 + lane;
