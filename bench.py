@@ -692,17 +692,16 @@ def run_gpu(args):
     value = world * RAYS_PER_GPU * K_ / (t_ms * 1e-3)
     e2e_value = world * RAYS_PER_GPU * K_ / (t_e2e * 1e-3)
 
-    # ---- the same step with the weight gradients running BESIDE the data-gradient chain (opt-in: rn_set_flag(9, 88)) ----
-    # Reported, not the headline: DESIGN.md section 4 says why it is not the default (3-4 % here; a static SM partition
-    # that a concurrent NCCL kernel can upset; two interlocked launches a profiler cannot serialise the other way round).
-    stream_variant = None
+    # ---- the same step with the weight gradients AFTER the data-gradient chain (rn_set_flag(9, 0): 20 split-K launches per step
+    # instead of the persistent stream beside the chain, csrc/wgrad_stream.cu) -- the A/B behind that default, same box ----
+    seq_variant = None
     if world == 1 and not args.no_extras and use_graph:
-        prev9, prev6 = ctypes.c_int(0), ctypes.c_int(0)
-        lib.rn_get_flag(9, ctypes.byref(prev9)); lib.rn_get_flag(6, ctypes.byref(prev6))
-        if prev9.value == 0:
+        prev9 = ctypes.c_int(0)
+        lib.rn_get_flag(9, ctypes.byref(prev9))
+        if prev9.value > 0:
             try:
                 trainer._graphs.clear()
-                lib.rn_set_flag(9, 88); lib.rn_set_flag(6, 6)
+                lib.rn_set_flag(9, 0)
                 for i in range(W_):
                     step_fn(*dev_batches[i % POOL])
                 torch.cuda.synchronize()
@@ -712,11 +711,12 @@ def run_gpu(args):
                 e1.record()
                 torch.cuda.synchronize()
                 t_var = e0.elapsed_time(e1)
-                stream_variant = {"flags": "9=88,6=6", "ms_per_step": t_var / K_, "value": RAYS_PER_GPU * K_ / (t_var * 1e-3),
-                                  "unit": "rays/s", "what": "weight gradients as one persistent CTA-pair launch on 88 SMs beside the "
-                                  "data-gradient chain on 60, dH handed over through L2 (csrc/wgrad_stream.cu)"}
+                seq_variant = {"flags": "9=0", "ms_per_step": t_var / K_, "value": RAYS_PER_GPU * K_ / (t_var * 1e-3), "unit": "rays/s",
+                               "what": "weight gradients as 20 split-K launches after the data-gradient chain (timed after the "
+                               "headline regions, i.e. on the warmer part)"}
             finally:
-                lib.rn_set_flag(9, prev9.value); lib.rn_set_flag(6, prev6.value)
+                lib.rn_set_flag(9, prev9.value)
+                trainer._graphs.clear()
 
     peaks = measured_peaks()
     trainer._graphs.clear()                       # release the captured step (and its 11 GB workspace) before the other blocks
@@ -744,8 +744,8 @@ def run_gpu(args):
         except Exception as e:      # noqa: BLE001
             eager = {"error": repr(e)}
     extra = {}
-    if stream_variant:
-        extra["wgrad_stream_variant"] = stream_variant
+    if seq_variant:
+        extra["wgrad_sequential_variant"] = seq_variant
     if world > 1:
         dist.barrier()
 
@@ -793,7 +793,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": RAYS_PER_GPU * 9 * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / K_},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM kernels of the MLP: rn::mlp_chain_pair_kernel (forward chain), rn::mlp_chain_pair_bwd_kernel (data-gradient chain), rn::gemm_kernel<BN,2> (split-K weight gradients)",
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM kernels of the MLP: rn::mlp_chain_pair_kernel (forward chain), rn::mlp_chain_pair_bwd_kernel (data-gradient chain) with rn::wgrad_stream_kernel (weight gradients) beside it",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic,
                          "peak_source": peaks["source"],

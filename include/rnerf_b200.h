@@ -49,8 +49,10 @@ unsigned long long rn_launch_count(void);
  *   3: data gradients as one launch per layer (0) or as the CTA-pair chain (1, default)
  *   4: inference encodes the points inside the forward chain (1, default) or in a separate kernel (0)
  *   5: programmatic dependent launch for the GEMM-family kernels (default 0)
- *   6: L2 cache hints, bit mask: 1 chains, 2 weight-gradient loads evict_first, 4 chain stores evict_last (default 0)
- *   9: SMs given to the weight-gradient stream that runs beside the data-gradient chain (0 = off, default)
+ *   6: L2 cache hints, bit mask: 1 chains, 2 split-K loads evict_first (default 0), 8 = no policies on the hand-off
+ *      between the data-gradient chain and the weight-gradient stream (they are on by default)
+ *   9: SMs given to the weight-gradient stream that runs beside the data-gradient chain (default: 88 on a 148-SM
+ *      part; 0 = off: one split-K launch per layer after the chain)
  *   7, 8, 10: measurement only (SM limit of the data-gradient chain / of the split-K kernels; bit mask of
  *             timing options for the overlapped backward).  Flag 1 exists only in RN_EXPERIMENTS builds.
  * rn_get_flag reads a flag back.  Unknown flags return RN_ERR_INVALID_ARG. */

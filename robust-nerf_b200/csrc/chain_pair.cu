@@ -934,7 +934,7 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   p.n_layers = n_layers;
   p.n_ptiles = (int)ceil_div(M, 256);
   p.m_rows = M;
-  p.l2_hints = (g_l2_hints & 1) | ((g_l2_hints & 4) ? 2 : 0);      // bit 1 here: evict_last stores when a consumer follows (flag 6 bit 2)
+  p.l2_hints = (g_l2_hints & 1) | ((flags && !(g_l2_hints & 8)) ? 2 : 0);      // bit 1 here: evict_last stores, a consumer follows
   p.flags = flags;
   p.n_blocks = (int)ceil_div(M, 128);
 #ifdef RN_EXPERIMENTS

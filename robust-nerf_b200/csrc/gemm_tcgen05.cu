@@ -563,7 +563,7 @@ static std::vector<ProfRec> g_prof;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
 double g_prof_next_flops = 0.0;
 int g_sm_limit_dgrad = 0, g_sm_limit_wgrad = 0;    // rn_set_flag(7 / 8, n): experiments -- run that kernel family on n SMs
-int g_l2_hints = 0;          // rn_set_flag(6, v): bit 0 = chain kernels, bit 1 = split-K weight-gradient kernels
+int g_l2_hints = 0;          // rn_set_flag(6, v): bit 0 = chain kernels, bit 1 = split-K weight-gradient kernels, bit 3 = NO policies on the chain -> stream hand-off
 
 void prof_begin(int mode, cudaStream_t st, int* slot) {
   *slot = -1;

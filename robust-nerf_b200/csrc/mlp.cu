@@ -106,9 +106,15 @@ static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimen
 #ifdef RN_EXPERIMENTS
 int g_chain_dbg = 0;
 #endif
-// rn_set_flag(9, n): n > 0 = the weight gradients run BESIDE the data-gradient chain on n SMs (wgrad_stream.cu), taking each
-// block of dH out of L2 as the chain publishes it; 0 = one split-K launch per layer after the chain
-int g_wgrad_stream_sms = 0;
+// rn_set_flag(9, n): the weight gradients run BESIDE the data-gradient chain on n SMs (wgrad_stream.cu), taking each block
+// of dH out of L2 as the chain publishes it.  -1 (default) = 88 of 148 SMs, the measured optimum (44 pairs = 4 splits for
+// each of the 11 GEMMs; the chain keeps 60), off on a part with another SM count; 0 = off: one split-K launch per layer
+// after the chain (2.5-4 % more time per step, profiles/r02_ab_log.md block 19).
+int g_wgrad_stream_sms = -1;
+static int wgrad_stream_sms() {
+  if (g_wgrad_stream_sms >= 0) return g_wgrad_stream_sms;
+  return num_sms() == 148 ? 88 : 0;
+}
 // rn_set_flag(10, mask): measurement only.  bit 0 = record the two launches separately as well as the span; bit 1 = launch
 // the stream AFTER the chain on the same stream (every flag already set: the consumer alone, operands from HBM)
 int g_ws_debug = 0;
@@ -206,7 +212,8 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   auto scratch_k = [&]() { return w.scratch + (size_t)(tn_k++) * region; };
   // heads: dHC, dFS[:, 256:272], rgb_linear grads
   RN_TRY(launch_heads_bwd(g_raw, w.HC, M, F, w.dHC, w.dFS, 272, w.heads_scratch, G + kG_WRgb, G + kG_BRgb, st));
-  const bool overlapped = g_chain_bwd && g_wgrad_stream_sms >= 24 && g_wgrad_stream_sms <= num_sms() - 24;
+  const int stream_sms = wgrad_stream_sms();
+  const bool overlapped = g_chain_bwd && stream_sms >= 24 && stream_sms <= num_sms() - 24;
   if (g_chain_bwd) {
     // ---- all data gradients in one launch: dHC -> dF -> dH7 -> ... -> dH0 ----
     BwdLayerHost L[9];
@@ -229,7 +236,7 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
         P[np++] = (l == 5) ? WsHostProblem{w.dH[5], 256, 256, 0, 256, w.XC, 320, 320, 320, 8 - 5}
                            : WsHostProblem{w.dH[l], 256, 256, 0, 256, w.H[l - 1], ld_of(l - 1), 256, 256, 8 - l};
       P[np++] = WsHostProblem{w.dH[0], 256, 256, 0, 256, w.XC, 320, 64, 64, 8};             // layer 0: x_enc only
-      const int ws_sms = g_wgrad_stream_sms & ~1;
+      const int ws_sms = stream_sms & ~1;
       SideStream* side;
       RN_TRY(side_stream(&side));
       RN_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, flags_bytes(M), st));
@@ -335,7 +342,7 @@ int rn_set_flag(int flag, int value) {
   if (flag == 3) { g_chain_bwd = value; return RN_OK; }
   if (flag == 4) { g_pe_fused = value; return RN_OK; }
   if (flag == 5) { g_pdl = value ? 1 : 0; return RN_OK; }
-  if (flag == 6) { g_l2_hints = value & 7; return RN_OK; }
+  if (flag == 6) { g_l2_hints = value & 11; return RN_OK; }
   if (flag == 7) { g_sm_limit_dgrad = value; return RN_OK; }
   if (flag == 8) { g_sm_limit_wgrad = value; return RN_OK; }
   if (flag == 9) { g_wgrad_stream_sms = value; return RN_OK; }
@@ -353,7 +360,7 @@ int rn_get_flag(int flag, int* value_host) {
     case 6: *value_host = g_l2_hints; return RN_OK;
     case 7: *value_host = g_sm_limit_dgrad; return RN_OK;
     case 8: *value_host = g_sm_limit_wgrad; return RN_OK;
-    case 9: *value_host = g_wgrad_stream_sms; return RN_OK;
+    case 9: *value_host = wgrad_stream_sms(); return RN_OK;
     case 10: *value_host = g_ws_debug; return RN_OK;
     default: return RN_ERR_INVALID_ARG;
   }

@@ -383,7 +383,7 @@ int wgrad_stream_launch(const WsHostProblem* probs, int n, int64_t M, const uint
     flops += 2.0 * (double)M * h.N * h.Mo;
   }
   p.n_prob = n; p.n_pairs = pair; p.n_blocks = (int)ceil_div(M, 128); p.m_rows = M; p.flags = flags;
-  p.l2_hints = (g_l2_hints >> 1) & 1;
+  p.l2_hints = (g_l2_hints & 8) ? 0 : 1;          // both operands are read once: evict_first (rn_set_flag(6, 8) switches it off)
   p.dbg = g_ws_debug;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured))
