@@ -53,12 +53,17 @@ unsigned long long rn_launch_count(void);
  *      between the data-gradient chain and the weight-gradient stream (they are on by default)
  *   9: SMs given to the weight-gradient stream that runs beside the data-gradient chain (default: 88 on a 148-SM
  *      part; 0 = off: one split-K launch per layer after the chain)
- *   7, 8, 10: measurement only (SM limit of the data-gradient chain / of the split-K kernels; bit mask of
- *             timing options for the overlapped backward).  Flag 1 exists only in RN_EXPERIMENTS builds.
+ *   7, 8, 10, 11: measurement only (SM limit of the data-gradient chain / of the split-K kernels; bit mask of
+ *             timing options for the overlapped backward, 32 = record hand-off lags for rn_debug_stream_lag;
+ *             microseconds over which the chain staggers the start of its clusters).  Flag 1 exists only in
+ *             RN_EXPERIMENTS builds.
  * rn_get_flag reads a flag back.  Unknown flags return RN_ERR_INVALID_ARG. */
 int rn_set_flag(int flag, int value);
 int rn_get_flag(int flag, int* value_host);
 int rn_prof_enable(int on);
+/* measurement hook: mean / max time in microseconds between the data-gradient chain publishing a 128-point block and
+ * the weight-gradient stream issuing its load, over the last stream launch made with rn_set_flag(10, 32) */
+int rn_debug_stream_lag(double* mean_us_host, double* max_us_host, int* ctas_host);
 int rn_prof_collect(double* ms4_host, double* flops4_host, int* launches4_host);
 
 /* ------------------------------------------------------------------------------------------

@@ -38,7 +38,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
 void prof_begin(int mode, cudaStream_t st, int* slot);
 void prof_end(int slot, cudaStream_t st);
 extern double g_prof_next_flops;
-extern int g_l2_hints, g_sm_limit_dgrad;
+extern int g_l2_hints, g_sm_limit_dgrad, g_ws_stagger_us;
 
 constexpr int kPairThreads = 608;         // 19 warps
 constexpr int kPairThreadsPE = 640;       // + one warp: with the (idle in inference) store warp, two encoder warps, one per tile slot
@@ -614,6 +614,7 @@ struct BwdParams {
   int l2_hints;
   uint32_t* flags;              // [n_layers][n_blocks] "block published" words for wgrad_stream.cu, or null
   int n_blocks;                 // 128-row blocks
+  int stagger_ns;               // measurement only (rn_set_flag(11, us)): cluster c starts c / n_clusters of this window late
 };
 
 __device__ __forceinline__ void publish_block(uint32_t* f) {
@@ -621,7 +622,10 @@ __device__ __forceinline__ void publish_block(uint32_t* f) {
   // the point of coherence every SM reads through), so a plain strong store of the flag is enough for a consumer that
   // acquires it.  A st.release.gpu here is a fence that also drains this thread's NEWER bulk stores -- 3-4 us per layer
   // and tile slot, which paced the whole chain at half its speed (profiles/r02_ab_log.md block 19).
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+  // The flag's value is the publication time (64 ns units, never 0): the consumer can report how long a block waited
+  // for it (rn_debug_stream_lag) -- what decides whether it is still in L2.
+  const uint32_t stamp = (uint32_t)(globaltimer_ns() >> 6) | 1u;
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(stamp) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
@@ -671,6 +675,11 @@ mlp_chain_pair_bwd_kernel(const __grid_constant__ BwdParams p) {
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int n_groups = (p.n_ptiles + 1) >> 1;
+  if (p.stagger_ns > 0) {
+    const long long delay = (long long)p.stagger_ns * cluster_id / n_clusters;
+    const unsigned long long t0 = globaltimer_ns();
+    while ((long long)(globaltimer_ns() - t0) < delay) __nanosleep(500);
+  }
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     const uint32_t full_b_leader = mapa_u32(smem_u32(full_b), 0);
@@ -937,6 +946,7 @@ int mlp_chain_pair_backward(const BwdLayerHost* layers, int n_layers, int64_t M,
   p.l2_hints = (g_l2_hints & 1) | ((flags && !(g_l2_hints & 8)) ? 2 : 0);      // bit 1 here: evict_last stores, a consumer follows
   p.flags = flags;
   p.n_blocks = (int)ceil_div(M, 128);
+  p.stagger_ns = flags ? g_ws_stagger_us * 1000 : 0;
 #ifdef RN_EXPERIMENTS
   p.timeline = g_pair_timeline_bwd;
 #else

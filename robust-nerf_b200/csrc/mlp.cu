@@ -118,6 +118,7 @@ static int wgrad_stream_sms() {
 // rn_set_flag(10, mask): measurement only.  bit 0 = record the two launches separately as well as the span; bit 1 = launch
 // the stream AFTER the chain on the same stream (every flag already set: the consumer alone, operands from HBM)
 int g_ws_debug = 0;
+int g_ws_stagger_us = 0;      // rn_set_flag(11, us): measurement only, staggered start of the chain's clusters
 int g_chain_bwd = 1;      // rn_set_flag(3, v): 1 = data gradients as one CTA-pair chain launch (chain_pair.cu), 0 = one launch per layer
 // rn_set_flag(0, v): 0 = one launch per layer (gemm_tcgen05.cu: the building-block kernels, kept as the cross-check of the
 // chain), 2 = CTA-pair chain with shared-memory-resident activations (chain_pair.cu; default).  (Round 1's third variant,
@@ -347,6 +348,7 @@ int rn_set_flag(int flag, int value) {
   if (flag == 8) { g_sm_limit_wgrad = value; return RN_OK; }
   if (flag == 9) { g_wgrad_stream_sms = value; return RN_OK; }
   if (flag == 10) { g_ws_debug = value; return RN_OK; }
+  if (flag == 11) { g_ws_stagger_us = value; return RN_OK; }
   return RN_ERR_INVALID_ARG;
 }
 
@@ -362,6 +364,7 @@ int rn_get_flag(int flag, int* value_host) {
     case 8: *value_host = g_sm_limit_wgrad; return RN_OK;
     case 9: *value_host = wgrad_stream_sms(); return RN_OK;
     case 10: *value_host = g_ws_debug; return RN_OK;
+    case 11: *value_host = g_ws_stagger_us; return RN_OK;
     default: return RN_ERR_INVALID_ARG;
   }
 }

@@ -71,8 +71,11 @@ struct WsParams {
   int64_t m_rows;
   const uint32_t* flags;              // [flag rows][n_blocks], zeroed before the launch, 1 = block published
   int l2_hints;
-  int dbg;                            // measurement only (rn_set_flag(10)): bit 2 = no bias MMA, bit 3 = no MMAs at all
+  int dbg;                            // measurement only (rn_set_flag(10)): bit 2 = no bias MMA, bit 3 = no MMAs at all, bit 5 = record hand-off lags
 };
+
+// measurement hook (rn_debug_stream_lag): per CTA, sum / count / max of (A-load issue time - publication time) in 64 ns units
+__device__ unsigned long long g_ws_lag[3 * 320];
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
@@ -181,12 +184,14 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
     int s = 0; uint32_t ph = 0; int issued = 0;
     int b = split;
     unsigned long long t0 = 0; uint32_t idle = 0;
+    unsigned long long lag_sum = 0, lag_n = 0, lag_max = 0;
     while (b < p.n_blocks) {
       // the next 32 blocks of this split, one flag per lane: how many are published, counting from the first?
       int nready = 32;
+      uint32_t f = 1u;
       if (frow) {
         const int bb = b + lane * S;
-        const uint32_t f = bb < p.n_blocks ? ld_acquire_gpu(frow + bb) : 1u;
+        f = bb < p.n_blocks ? ld_acquire_gpu(frow + bb) : 1u;
         const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
         nready = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
         if (nready == 0) {
@@ -204,9 +209,14 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
         // CTA's outstanding TMA loads and cost 2/3 of the kernel's rate, profiles/r02_ab_log.md block 19)
       }
       for (int i = 0; i < nready && b < p.n_blocks; ++i, b += S) {
+        const uint32_t stamp = __shfl_sync(0xffffffffu, f, i);
         for (int h = 0; h < 2 && issued < n_chunks; ++h, ++issued) {
           const int kc = b * 2 + h;
           mbar_wait(&empty_a[s], ph ^ 1);
+          if (frow && h == 0 && (p.dbg & 32)) {
+            const uint32_t lag = (uint32_t)(globaltimer_ns() >> 6) - stamp;
+            lag_sum += lag; lag_n += 1; lag_max = lag > lag_max ? lag : lag_max;
+          }
           if (lane == 0) {
             uint8_t* a_s = s_ring + s * kWsABytes;
             if (rank == 0) mbar_arrive_expect_tx(&full_a[s], tx_a);
@@ -218,6 +228,9 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
           if (++s == NA) { s = 0; ph ^= 1; }
         }
       }
+    }
+    if ((p.dbg & 32) && lane == 0 && blockIdx.x < 320) {
+      g_ws_lag[3 * blockIdx.x] = lag_sum; g_ws_lag[3 * blockIdx.x + 1] = lag_n; g_ws_lag[3 * blockIdx.x + 2] = lag_max;
     }
   } else if (warp == 6) {
     // ---------------- B producer (both CTAs, each for its half of the columns): no flags, as far ahead as the ring goes ----------------
@@ -398,3 +411,21 @@ int wgrad_stream_launch(const WsHostProblem* probs, int n, int64_t M, const uint
 }
 
 }  // namespace rn
+
+extern "C" int rn_debug_stream_lag(double* mean_us_host, double* max_us_host, int* ctas_host) {
+  // measurement hook: hand-off lag (publication of a block by the chain -> issue of its load by the stream) of the last
+  // wgrad_stream launch made with rn_set_flag(10, 32); synchronises the device
+  using namespace rn;
+  RN_REQUIRE(mean_us_host && max_us_host && ctas_host);
+  static unsigned long long host[3 * 320];
+  RN_CUDA_CHECK(cudaDeviceSynchronize());
+  RN_CUDA_CHECK(cudaMemcpyFromSymbol(host, g_ws_lag, sizeof(host)));
+  double sum = 0.0, n = 0.0, mx = 0.0; int ctas = 0;
+  for (int i = 0; i < 320; ++i) {
+    if (host[3 * i + 1] == 0) continue;
+    sum += (double)host[3 * i]; n += (double)host[3 * i + 1]; ++ctas;
+    if ((double)host[3 * i + 2] > mx) mx = (double)host[3 * i + 2];
+  }
+  *mean_us_host = n > 0 ? sum / n * 0.064 : 0.0; *max_us_host = mx * 0.064; *ctas_host = ctas;
+  return RN_OK;
+}
