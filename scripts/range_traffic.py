@@ -19,6 +19,19 @@ if len(sys.argv) > 1:
 if len(sys.argv) > 2:
     lib.rn_set_flag(11, int(sys.argv[2]))
 dev = torch.device("cuda", 0)
+torch.zeros(1, device=dev)
+if len(sys.argv) > 3 and int(sys.argv[3]) > 0:
+    # set aside part of L2 for lines written / read with the evict_last (persisting) priority
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    mx = ctypes.c_int(0)
+    rt.cudaDeviceGetAttribute(ctypes.byref(mx), ctypes.c_int(108), ctypes.c_int(0))      # cudaDevAttrMaxPersistingL2CacheSize
+    want = min(int(sys.argv[3]) << 20, mx.value)
+    rc = rt.cudaDeviceSetLimit(ctypes.c_int(0x06), ctypes.c_size_t(want))
+    got = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(got), ctypes.c_int(0x06))
+    rt.cudaGetLastError()
+    print("cudaLimitPersistingL2CacheSize: max", mx.value >> 20, "MB, rc", rc, "now", got.value >> 20, "MB", file=sys.stderr)
 scene = rn.make_scene(800, 800, 100, seed=0, device=dev)
 torch.manual_seed(42)
 coarse, fine = rn.create_nerf(rn.ModelConfig())
