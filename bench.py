@@ -718,6 +718,24 @@ def run_gpu(args):
                 lib.rn_set_flag(9, prev9.value)
                 trainer._graphs.clear()
 
+    # ---- strong scaling: the SAME global batch of 4096 rays split over the ranks ----
+    strong = None
+    if world > 1 and not args.no_extras and RAYS_PER_GPU % world == 0:
+        rs = RAYS_PER_GPU // world
+        small = [tuple(t[:rs].contiguous() for t in b) for b in dev_batches]
+        for i in range(W_):
+            step_fn(*small[i % POOL])
+        barrier()
+        e0.record()
+        for i in range(K_):
+            step_fn(*small[i % POOL])
+        e1.record()
+        barrier()
+        t_strong = reduce_max(e0.elapsed_time(e1))
+        strong = {"scaling": "strong", "global_batch_rays": RAYS_PER_GPU, "rays_per_gpu": rs, "ms_per_step": t_strong / K_,
+                  "value": RAYS_PER_GPU * K_ / (t_strong * 1e-3), "unit": "rays/s",
+                  "note": "same step, same global batch as the 1-GPU line; per-GPU work shrinks with N, the all-reduce does not"}
+
     peaks = measured_peaks()
     trainer._graphs.clear()                       # release the captured step (and its 11 GB workspace) before the other blocks
     step_fn = None
@@ -746,6 +764,8 @@ def run_gpu(args):
     extra = {}
     if seq_variant:
         extra["wgrad_sequential_variant"] = seq_variant
+    if strong:
+        extra["strong_scaling"] = strong
     if world > 1:
         dist.barrier()
 
