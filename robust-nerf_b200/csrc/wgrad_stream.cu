@@ -2,18 +2,22 @@
 // noisy_src/model.py:169-194: dW_l = dH_l^T H_{l-1}, db_l = column sums of dH_l) in ONE persistent launch that runs
 // CONCURRENTLY with the data-gradient chain (chain_pair.cu) on its own share of the SMs.
 //
-// Why: run one after the other, the data-gradient chain is paced by its epilogues (HBM at 4.5 TB/s) and the split-K
-// weight-gradient GEMMs by HBM (6.1 TB/s, tensor pipe 16-42 %), and the weight gradients re-read from HBM every dH_l the
-// chain has just written (5.2 GB per step).  Side by side they share the machine by what each one needs -- and the
-// consumer takes each 128-point block of dH_l out of L2 as soon as the chain has published it:
-//   * the chain's store warp publishes flag[layer][block] (st.release.gpu) once the TMA store of that block has completed;
+// Why: run one after the other, the data-gradient chain is paced by its epilogues (HBM at 4.5 TB/s, tensor pipe 48 %) and
+// the split-K weight-gradient GEMMs by HBM (6.1 TB/s, tensor pipe 16-42 %).  Side by side they share the machine by what
+// each one needs: 2.93-3.05 ms for both against 3.2 ms in sequence, 28 launches per step instead of 47, and 44 partial
+// tiles per GEMM to reduce instead of 148.  (The design also hands each block of dH_l over through L2 -- flags below -- but
+// measured, the blocks are 25-35 us old when they are read and have left the L2 by then: a step still reads all of dH
+// from HBM.  profiles/r02_ab_log.md blocks 19-22 have the whole story.)
+//   * the chain's store warp publishes flag[layer][block] (a strong store of the publication time, four store groups after
+//     the block's TMA store: cp.async.bulk.wait_group says its writes have completed);
 //   * every CTA PAIR here (cluster of 2, tcgen05 cta_group::2, M = 256) owns one (GEMM, split) for the whole launch:
 //     CTA r holds output features [128 r, 128 r + 128) of dW with its fp32 accumulator resident in TMEM, streams its
 //     half of dH_l^T (16 KiB per 64 points) and HALF of H_{l-1}'s columns (16 KiB): 32 KiB per SM and chunk where a
-//     single-CTA tile pulls 48 -- the consumer is paced by what one SM can take in from L2 (~95 GB/s measured), so bytes
-//     per SM are what counts;
-//   * split s of S takes the point blocks s, s+S, s+2S, ... in the order the chain produces them; the TMA warp polls
-//     the flags of its next 32 blocks at once (ld.acquire.gpu, one per lane) so the flag latency is off the load path;
+//     single-CTA tile pulls 48 -- a pair is paced by what one SM can take in (~65 GB/s of HBM-sourced TMA traffic,
+//     whatever the depth of its rings), so bytes per SM are what counts;
+//   * split s of S takes the point blocks s, s+S, s+2S, ... in that FIXED order (that is what keeps the sums
+//     bit-reproducible); the TMA warp polls the flags of its next 32 blocks at once (ld.acquire.gpu, one per lane) so the
+//     flag latency is off the load path;
 //   * the bias gradient is one more N=16 MMA against a tile of ones (column sums of dH_l);
 //   * tensor cores accumulate with truncation, so an accumulator is not kept for the whole launch: every kWsFlushChunks
 //     chunks (1,024 accumulation steps, about as many as one split of the split-K kernels sees) the epilogue warps
@@ -21,11 +25,12 @@
 //   * the partial tiles use the [split][m_tile] layout of the split-K kernels and are summed by the same deterministic
 //     reduce kernel (gemm_tcgen05.cu) -- the assignment is static, so a step stays bit-reproducible.
 // Widths that are not 256: N = 320 ([x_enc | H4], [feat | d_enc]) is a second MMA of N = 128 whose upper half lies beyond
-// the tensor (TMA zero fill, no traffic); N = 64 (x_enc) is one MMA of N = 128 likewise; M = 128 (dHC) and the sigma row
-// of dFS are M = 256 with the missing features out of bounds.
+// the tensor (those boxes are never loaded: their slots are zeroed once); N = 64 (x_enc) is one MMA of N = 128 likewise;
+// M = 128 (dHC) and the sigma row of dFS are M = 256 with the missing features out of bounds.
 // Both kernels are launched as clusters of two CTAs (whole TPCs), one CTA per SM, and together they ask for no more SMs
-// than the device has, so they are co-resident whatever order the hardware starts them in; a wait on a flag that never
-// comes traps after 4 s instead of hanging the device.
+// than the device has, so they are co-resident whatever order the hardware starts them in, and the dependency is one-way
+// (the chain never waits for this kernel), so other work on the GPU can delay the pair but not deadlock it; a wait on a
+// flag that never comes traps after 4 s instead of hanging the device.
 //
 // Warp roles (224 threads): 0 = flag polling + A producer, 1 = TMEM owner + MMA issuer (leader CTA), 2..5 = epilogue,
 // 6 = B producer.
@@ -50,8 +55,8 @@ constexpr int kWsSmem = 231424;                 // 226 KiB
 constexpr int kWsOnes = 2048;                   // 16 k-rows x 128 B of bf16 1.0 (first 2 KiB of the aligned buffer)
 constexpr int kWsRing = kWsSmem - 1024 /*alignment slack*/ - kWsOnes - 1024 /*barriers*/;
 constexpr int kWsABytes = 16384;                // [64 points][128 output features]
-constexpr int kWsAStages = 5;                   // dH tiles: out of L2 when the consumer keeps up (short latency)
-constexpr int kWsMaxBStages = 12;               // H tiles: always from HBM -> the deep ring, and it runs ahead of the flags
+constexpr int kWsAStages = 5;                   // dH tiles: loaded once their block is published
+constexpr int kWsMaxBStages = 12;               // H tiles: no flag to wait for -> the deeper ring, running ahead
 constexpr int kWsFlushChunks = 256;             // accumulator flushed to the fp32 partial every 256 chunks (16,384 points)
 
 struct WsProblem {
