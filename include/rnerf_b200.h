@@ -64,6 +64,8 @@ int rn_prof_enable(int on);
 /* measurement hook: mean / max time in microseconds between the data-gradient chain publishing a 128-point block and
  * the weight-gradient stream issuing its load, over the last stream launch made with rn_set_flag(10, 32) */
 int rn_debug_stream_lag(double* mean_us_host, double* max_us_host, int* ctas_host);
+/* ... and the microseconds each CTA pair's leader (entries 0, 2, 4, ...) spent on its chunks in that launch */
+int rn_debug_stream_busy(unsigned int* us_host, int n);
 int rn_prof_collect(double* ms4_host, double* flops4_host, int* launches4_host);
 
 /* ------------------------------------------------------------------------------------------

@@ -81,6 +81,7 @@ struct WsParams {
 
 // measurement hook (rn_debug_stream_lag): per CTA, sum / count / max of (A-load issue time - publication time) in 64 ns units
 __device__ unsigned long long g_ws_lag[3 * 320];
+__device__ unsigned int g_ws_busy_us[320];       // rn_set_flag(10, 32): microseconds each CTA spent between its first and last MMA wait
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
@@ -271,6 +272,7 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
       const uint32_t b_lo0 = desc_lo_sw128(smem_u32(s_ring_b), 8192);
       const uint32_t o_lo = desc_lo_sw128(smem_u32(s_ones), 8192);
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+      const unsigned long long t_begin = (p.dbg & 32) ? globaltimer_ns() : 0ull;
       for (int c = 0; c < n_chunks; ++c) {
         const int in_flush = c % kWsFlushChunks;
         if (in_flush == 0 && c > 0) mbar_wait(tmem_empty, ((c / kWsFlushChunks) - 1) & 1u);   // accumulator drained
@@ -295,6 +297,7 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
         if (++sa == NA) { sa = 0; pha ^= 1; }
         if (++sb == NB) { sb = 0; phb ^= 1; }
       }
+      if ((p.dbg & 32) && lane == 0 && blockIdx.x < 320) g_ws_busy_us[blockIdx.x] = (unsigned int)((globaltimer_ns() - t_begin) / 1000);
     }
   } else if (warp < 6) {
     // ---------------- epilogue warps: accumulator -> (+=) fp32 partial tile, once per flush ----------------
@@ -432,5 +435,15 @@ extern "C" int rn_debug_stream_lag(double* mean_us_host, double* max_us_host, in
     if ((double)host[3 * i + 2] > mx) mx = (double)host[3 * i + 2];
   }
   *mean_us_host = n > 0 ? sum / n * 0.064 : 0.0; *max_us_host = mx * 0.064; *ctas_host = ctas;
+  return RN_OK;
+}
+
+extern "C" int rn_debug_stream_busy(unsigned int* us_host, int n) {
+  // measurement hook: microseconds between the first and the last MMA wait of CTA pair i's leader (entry 2 i) in the last
+  // wgrad_stream launch made with rn_set_flag(10, 32): which GEMM's pairs set the pace
+  using namespace rn;
+  RN_REQUIRE(us_host && n > 0 && n <= 320);
+  RN_CUDA_CHECK(cudaDeviceSynchronize());
+  RN_CUDA_CHECK(cudaMemcpyFromSymbol(us_host, g_ws_busy_us, sizeof(unsigned int) * n));
   return RN_OK;
 }

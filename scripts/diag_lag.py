@@ -17,7 +17,7 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 net = rn.NeRF().to(dev)
 rng = np.random.default_rng(3)
-for stagger, sms in ((0, 88), (40, 88), (0, 110), (40, 110)):
+for stagger, sms, mode in ((0, 88, 32), (0, 88, 35)):      # 32: beside the chain; 35: after it (alone, every flag set)
     lib.rn_set_flag(11, stagger)
     lib.rn_set_flag(9, sms)
     for M in (786432,):
@@ -25,7 +25,7 @@ for stagger, sms in ((0, 88), (40, 88), (0, 110), (40, 110)):
         dirs = torch.as_tensor(rng.standard_normal((M, 3)).astype(np.float32), device=dev)
         gout = torch.as_tensor(rng.standard_normal((M, 4)).astype(np.float32), device=dev)
         for rep in range(3):
-            lib.rn_set_flag(10, 32 if rep == 2 else 0)
+            lib.rn_set_flag(10, mode if rep == 2 else (mode & 3))
             net.zero_grad()
             raw = net.forward_raw(pts, dirs, 1)
             torch.cuda.synchronize()
@@ -36,5 +36,11 @@ for stagger, sms in ((0, 88), (40, 88), (0, 110), (40, 110)):
             torch.cuda.synchronize()
         mean, mx, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
         lib.rn_debug_stream_lag(ctypes.byref(mean), ctypes.byref(mx), ctypes.byref(n))
-        print(f"stagger {stagger} us, stream SMs {sms}, M={M}: backward {e0.elapsed_time(e1):.3f} ms; hand-off lag mean {mean.value:.1f} us, max {mx.value:.1f} us over {n.value} CTAs")
+        busy = (ctypes.c_uint * 176)()
+        lib.rn_debug_stream_busy(busy, 176)
+        # 44 pairs in problem order: dir, feature, sigma, L7, L6, L5, L4, L3, L2, L1, L0 (4 each at 88 SMs)
+        names = ["dir", "feat", "sigma", "L7", "L6", "L5", "L4", "L3", "L2", "L1", "L0"]
+        per = [[busy[2 * (4 * i + j)] for j in range(4)] for i in range(11)]
+        print("busy us per pair:", {n: p_ for n, p_ in zip(names, per)})
+        print(f"mode {mode}, stream SMs {sms}, M={M}: backward {e0.elapsed_time(e1):.3f} ms; hand-off lag mean {mean.value:.1f} us, max {mx.value:.1f} us over {n.value} CTAs")
 lib.rn_set_flag(10, 0); lib.rn_set_flag(11, 0); lib.rn_set_flag(9, 88)
