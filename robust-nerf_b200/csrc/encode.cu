@@ -231,13 +231,19 @@ encode_bwd_dirs_kernel(const float* __restrict__ dirs, int64_t R, int group, con
 // ------------------------------------------------------------------------------------------
 constexpr int kHeadsBwdThreads = 256;
 constexpr int kHeadsBwdCtasPerSm = 4;
+constexpr int kHeadsBwdPartial = 648;       // per CTA: dW_rgb 384 | db_rgb 3 | pad | dW_sigma 256 (at 388) | db_sigma (at 644) | pad
 
+// SIGMA: also the sigma_linear gradients, dW_sigma[j] += dsigma[m] * H7[m, j] and db_sigma += dsigma[m] with dsigma rounded
+// to bf16 exactly as the tensor-core path sees it (dFS[m, 256]) -- 16 columns of H7 per thread.  The weight-gradient
+// stream (wgrad_stream.cu) would need a CTA pair per split for this one row of dFS^T; here it costs 256 B per point of
+// extra reads in a kernel that is already streaming HC.
+template <bool SIGMA>
 __global__ void __launch_bounds__(kHeadsBwdThreads)
-heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restrict__ HC, int64_t M,
-                 const float* __restrict__ f32sec, __nv_bfloat16* __restrict__ dHC, __nv_bfloat16* __restrict__ dFS,
-                 int ldfs, float* __restrict__ partial /*[grid][388]*/) {
+heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restrict__ HC, const __nv_bfloat16* __restrict__ H7,
+                 int64_t M, const float* __restrict__ f32sec, __nv_bfloat16* __restrict__ dHC,
+                 __nv_bfloat16* __restrict__ dFS, int ldfs, float* __restrict__ partial /*[grid][kHeadsBwdPartial]*/) {
   __shared__ float s_red[kHeadsBwdThreads / 16][16][25];
-  const int cg = threadIdx.x & 15;            // column group: columns 8*cg .. 8*cg+7
+  const int cg = threadIdx.x & 15;            // column group: columns 8*cg .. 8*cg+7 of HC (16*cg .. 16*cg+15 of H7)
   const int pl = threadIdx.x >> 4;            // point lane inside the CTA
   float w[3][8];
 #pragma unroll
@@ -245,23 +251,31 @@ heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restri
 #pragma unroll
     for (int e = 0; e < 8; ++e) w[c][e] = f32sec[kWRgb + c * 128 + cg * 8 + e];
   float acc[3][8], bacc[3] = {0.f, 0.f, 0.f};
+  float sacc[SIGMA ? 16 : 1], sbias = 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < (SIGMA ? 16 : 1); ++e) sacc[e] = 0.f;
   const int64_t pstride = (int64_t)gridDim.x * (kHeadsBwdThreads / 16);
-  // four points per thread and iteration, all loads issued before any dependent math: one uint4 per thread in flight
+  // several points per thread and iteration, all loads issued before any dependent math: one uint4 per thread in flight
   // (16 KB per SM) left this HBM-bound kernel at half of its bandwidth floor
-  constexpr int kU = 4;
+  constexpr int kU = SIGMA ? 2 : 4;
   for (int64_t m0 = (int64_t)blockIdx.x * (kHeadsBwdThreads / 16) + pl; m0 < M; m0 += kU * pstride) {
     float4 gv[kU];
     uint4 hvv[kU];
+    uint4 h7v[SIGMA ? kU : 1][2];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int64_t m = m0 + u * pstride;
       if (m < M) {
         gv[u] = __ldg(g_raw + m);
         hvv[u] = __ldcs(reinterpret_cast<const uint4*>(HC + m * 128 + cg * 8));
+        if (SIGMA) {
+          h7v[u][0] = __ldcs(reinterpret_cast<const uint4*>(H7 + m * 256 + cg * 16));
+          h7v[u][1] = __ldcs(reinterpret_cast<const uint4*>(H7 + m * 256 + cg * 16 + 8));
+        }
       }
     }
 #pragma unroll
@@ -282,9 +296,20 @@ heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restri
         outw[e2] = pack_bf16(d0, d1);
       }
       *reinterpret_cast<uint4*>(dHC + m * 128 + cg * 8) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+      const uint32_t ds_packed = pack_bf16(g.w, 0.f);
+      if (SIGMA) {
+        const float ds = bf16_lo(ds_packed);               // what dFS[m, 256] holds
+        const uint32_t w7[8] = {h7v[u][0].x, h7v[u][0].y, h7v[u][0].z, h7v[u][0].w, h7v[u][1].x, h7v[u][1].y, h7v[u][1].z, h7v[u][1].w};
+#pragma unroll
+        for (int e2 = 0; e2 < 8; ++e2) {
+          sacc[2 * e2] = fmaf(ds, bf16_lo(w7[e2]), sacc[2 * e2]);
+          sacc[2 * e2 + 1] = fmaf(ds, bf16_hi(w7[e2]), sacc[2 * e2 + 1]);
+        }
+        if (cg == 0) sbias += ds;
+      }
       if (cg == 0) {
         bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z;
-        *reinterpret_cast<uint4*>(dFS + m * ldfs + 256) = make_uint4(pack_bf16(g.w, 0.f), 0, 0, 0);
+        *reinterpret_cast<uint4*>(dFS + m * ldfs + 256) = make_uint4(ds_packed, 0, 0, 0);
       } else if (cg == 1) {
         *reinterpret_cast<uint4*>(dFS + m * ldfs + 264) = make_uint4(0, 0, 0, 0);
       }
@@ -295,9 +320,9 @@ heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restri
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int e = 0; e < 8; ++e) s_red[pl][cg][c * 8 + e] = acc[c][e];
-  s_red[pl][cg][24] = (cg == 0) ? 0.f : 0.f;
+  s_red[pl][cg][24] = 0.f;
   __syncthreads();
-  float* p = partial + (size_t)blockIdx.x * 388;
+  float* p = partial + (size_t)blockIdx.x * kHeadsBwdPartial;
   for (int o = threadIdx.x; o < 384; o += kHeadsBwdThreads) {
     const int c = o / 128, j = o % 128;
     float a = 0.f;
@@ -305,23 +330,48 @@ heads_bwd_kernel(const float4* __restrict__ g_raw, const __nv_bfloat16* __restri
     p[o] = a;
   }
   __syncthreads();
-  if (cg == 0) { s_red[pl][0][0] = bacc[0]; s_red[pl][0][1] = bacc[1]; s_red[pl][0][2] = bacc[2]; }
+  if (cg == 0) { s_red[pl][0][0] = bacc[0]; s_red[pl][0][1] = bacc[1]; s_red[pl][0][2] = bacc[2]; s_red[pl][0][3] = sbias; }
   __syncthreads();
   if (threadIdx.x < 3) {
     float a = 0.f;
     for (int l = 0; l < kHeadsBwdThreads / 16; ++l) a += s_red[l][0][threadIdx.x];
     p[384 + threadIdx.x] = a;
   }
+  if (SIGMA) {
+    if (threadIdx.x == 3) {
+      float a = 0.f;
+      for (int l = 0; l < kHeadsBwdThreads / 16; ++l) a += s_red[l][0][3];
+      p[644] = a;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s_red[pl][cg][e] = sacc[e];
+    __syncthreads();
+    {
+      const int j = threadIdx.x;               // 256 threads <-> 256 columns of H7
+      float a = 0.f;
+      for (int l = 0; l < kHeadsBwdThreads / 16; ++l) a += s_red[l][j >> 4][j & 15];
+      p[388 + j] = a;
+    }
+  }
 }
-// one warp per output, lanes over the per-CTA partials, fixed shuffle tree
+// one warp per output, lanes over the per-CTA partials, fixed shuffle tree.  Outputs 0..383 dW_rgb, 384..386 db_rgb and, when
+// gWsig is given, 387..642 dW_sigma, 643 db_sigma.
 __global__ void heads_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ gWrgb,
-                                        float* __restrict__ gBrgb) {
+                                        float* __restrict__ gBrgb, float* __restrict__ gWsig, float* __restrict__ gBsig) {
   const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (o >= 387) return;
+  const int n_out = gWsig ? 644 : 387;
+  if (o >= n_out) return;
+  const int src = o < 387 ? o : (o < 643 ? 388 + (o - 387) : 644);
   float acc = 0.f;
-  for (int b = lane; b < nblk; b += 32) acc += partial[(size_t)b * 388 + o];
+  for (int b = lane; b < nblk; b += 32) acc += partial[(size_t)b * kHeadsBwdPartial + src];
   acc = warp_sum(acc);
-  if (lane == 0) { if (o < 384) gWrgb[o] = acc; else gBrgb[o - 384] = acc; }
+  if (lane == 0) {
+    if (o < 384) gWrgb[o] = acc;
+    else if (o < 387) gBrgb[o - 384] = acc;
+    else if (o < 643) gWsig[o - 387] = acc;
+    else gBsig[0] = acc;
+  }
 }
 
 // model.py:181,194 activations for the NeRF.forward API
@@ -411,14 +461,23 @@ int launch_dir_bias(const float* dirs, int64_t R, const void* packed, float* dir
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
-size_t heads_bwd_scratch_bytes(int64_t M) { return (size_t)num_sms() * kHeadsBwdCtasPerSm * 388 * sizeof(float) + 256; }
+size_t heads_bwd_scratch_bytes(int64_t M) { return (size_t)num_sms() * kHeadsBwdCtasPerSm * kHeadsBwdPartial * sizeof(float) + 256; }
+// H7 != null: also the sigma_linear gradients (gWsig[256], gBsig[1]) -- the path taken when the weight-gradient stream runs
 int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,
-                     float* scratch, float* gWrgb, float* gBrgb, cudaStream_t st) {
+                     float* scratch, float* gWrgb, float* gBrgb, cudaStream_t st, const void* H7, float* gWsig, float* gBsig) {
   const int nblk = num_sms() * kHeadsBwdCtasPerSm;
-  heads_bwd_kernel<<<nblk, kHeadsBwdThreads, 0, st>>>((const float4*)g_raw, (const __nv_bfloat16*)HC, M, f32sec,
-                                                      (__nv_bfloat16*)dHC, (__nv_bfloat16*)dFS, ldfs, scratch);
+  if (H7) {
+    RN_REQUIRE(gWsig && gBsig);
+    heads_bwd_kernel<true><<<nblk, kHeadsBwdThreads, 0, st>>>((const float4*)g_raw, (const __nv_bfloat16*)HC,
+                                                              (const __nv_bfloat16*)H7, M, f32sec, (__nv_bfloat16*)dHC,
+                                                              (__nv_bfloat16*)dFS, ldfs, scratch);
+  } else {
+    heads_bwd_kernel<false><<<nblk, kHeadsBwdThreads, 0, st>>>((const float4*)g_raw, (const __nv_bfloat16*)HC, nullptr, M, f32sec,
+                                                               (__nv_bfloat16*)dHC, (__nv_bfloat16*)dFS, ldfs, scratch);
+  }
   RN_LAUNCH_CHECK();
-  heads_bwd_reduce_kernel<<<(387 * 32 + 255) / 256, 256, 0, st>>>(scratch, nblk, gWrgb, gBrgb);
+  const int n_out = H7 ? 644 : 387;
+  heads_bwd_reduce_kernel<<<(n_out * 32 + 255) / 256, 256, 0, st>>>(scratch, nblk, gWrgb, gBrgb, H7 ? gWsig : nullptr, gBsig);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -83,7 +83,8 @@ int launch_view_rays(const float* pose, int W, float focal, float cx, float cy, 
 int launch_encode(const float* pts, const float* dirs, int64_t M, int group, void* XC, int ldx, void* FD, int ldf, cudaStream_t st);
 size_t heads_bwd_scratch_bytes(int64_t M);
 int launch_heads_bwd(const float* g_raw, const void* HC, int64_t M, const float* f32sec, void* dHC, void* dFS, int ldfs,
-                     float* scratch, float* gWrgb, float* gBrgb, cudaStream_t st);
+                     float* scratch, float* gWrgb, float* gBrgb, cudaStream_t st, const void* H7 = nullptr,
+                     float* gWsig = nullptr, float* gBsig = nullptr);
 int launch_encode_bwd(const float* pts, const float* dirs, int64_t M, int group, const void* dXE0, const void* dXE5,
                       const void* dDE, float* g_pts, float* g_dirs, cudaStream_t st);
 }  // namespace rn

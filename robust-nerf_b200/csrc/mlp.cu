@@ -107,9 +107,9 @@ static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimen
 int g_chain_dbg = 0;
 #endif
 // rn_set_flag(9, n): the weight gradients run BESIDE the data-gradient chain on n SMs (wgrad_stream.cu), taking each block
-// of dH out of L2 as the chain publishes it.  -1 (default) = 88 of 148 SMs, the measured optimum (44 pairs = 4 splits for
-// each of the 11 GEMMs; the chain keeps 60), off on a part with another SM count; 0 = off: one split-K launch per layer
-// after the chain (2.5-4 % more time per step, profiles/r02_ab_log.md block 19).
+// of dH as the chain publishes it.  -1 (default) = 88 of 148 SMs, the measured optimum (44 pairs: 4 or 5 splits for each of
+// the 10 GEMMs; the chain keeps 60), off on a part with another SM count; 0 = off: one split-K launch per layer after the
+// chain (1.3-4.3 % more time per step, profiles/r02_ab_log.md blocks 19-23).
 int g_wgrad_stream_sms = -1;
 static int wgrad_stream_sms() {
   if (g_wgrad_stream_sms >= 0) return g_wgrad_stream_sms;
@@ -211,10 +211,12 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
   int tn_k = 0;
   const size_t region = align_up(w.scratch_bytes, 256) / sizeof(float);
   auto scratch_k = [&]() { return w.scratch + (size_t)(tn_k++) * region; };
-  // heads: dHC, dFS[:, 256:272], rgb_linear grads
-  RN_TRY(launch_heads_bwd(g_raw, w.HC, M, F, w.dHC, w.dFS, 272, w.heads_scratch, G + kG_WRgb, G + kG_BRgb, st));
   const int stream_sms = wgrad_stream_sms();
   const bool overlapped = g_chain_bwd && stream_sms >= 24 && stream_sms <= num_sms() - 24;
+  // heads: dHC, dFS[:, 256:272], rgb_linear grads -- and, when the weight-gradient stream runs, the sigma_linear gradients
+  // too (one row of dFS^T: a CTA pair per split in the stream, 256 B per point of extra reads here)
+  RN_TRY(launch_heads_bwd(g_raw, w.HC, M, F, w.dHC, w.dFS, 272, w.heads_scratch, G + kG_WRgb, G + kG_BRgb, st,
+                          overlapped ? w.H[7] : nullptr, G + kG_WSig, G + kG_BSig));
   if (g_chain_bwd) {
     // ---- all data gradients in one launch: dHC -> dF -> dH7 -> ... -> dH0 ----
     BwdLayerHost L[9];
@@ -232,7 +234,6 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
       int np = 0;
       P[np++] = WsHostProblem{w.dHC, 128, 128, 0, 128, w.FD, 320, 320, 320, -1};           // dir_linear
       P[np++] = WsHostProblem{w.dFS, 272, 272, 0, 256, w.H[7], 256, 256, 256, 0};           // feature_linear
-      P[np++] = WsHostProblem{w.dFS, 272, 272, 256, 16, w.H[7], 256, 256, 256, -1};         // sigma_linear (dsigma is heads_bwd's)
       for (int l = 7; l >= 1; --l)
         P[np++] = (l == 5) ? WsHostProblem{w.dH[5], 256, 256, 0, 256, w.XC, 320, 320, 320, 8 - 5}
                            : WsHostProblem{w.dH[l], 256, 256, 0, 256, w.H[l - 1], ld_of(l - 1), 256, 256, 8 - l};
@@ -265,7 +266,6 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
       int k = 0;
       RN_TRY(tn_batch_add(&batch, infos[k++], 0, 128, 0, 283, G + kG_WD, 283, G + kG_BD));
       RN_TRY(tn_batch_add(&batch, infos[k++], 0, 256, 0, 256, G + kG_WF, 256, G + kG_BF));
-      RN_TRY(tn_batch_add(&batch, infos[k++], 0, 1, 0, 256, G + kG_WSig, 256, G + kG_BSig));
       for (int l = 7; l >= 1; --l) {
         if (l == 5) {
           RN_TRY(tn_batch_add(&batch, infos[k], 0, 256, 0, 63, G + trunk_gw(5), 319, nullptr));

@@ -26,7 +26,8 @@
 //     reduce kernel (gemm_tcgen05.cu) -- the assignment is static, so a step stays bit-reproducible.
 // Widths that are not 256: N = 320 ([x_enc | H4], [feat | d_enc]) is a second MMA of N = 128 whose upper half lies beyond
 // the tensor (those boxes are never loaded: their slots are zeroed once); N = 64 (x_enc) is one MMA of N = 128 likewise;
-// M = 128 (dHC) and the sigma row of dFS are M = 256 with the missing features out of bounds.
+// M = 128 (dHC) is M = 256 with the missing features out of bounds.  (The one-row sigma_linear gradient is not a problem
+// of this kernel: heads_bwd_kernel<true> sums it while it streams HC -- a CTA pair per split for one row cost more.)
 // Both kernels are launched as clusters of two CTAs (whole TPCs), one CTA per SM, and together they ask for no more SMs
 // than the device has, so they are co-resident whatever order the hardware starts them in, and the dependency is one-way
 // (the chain never waits for this kernel), so other work on the GPU can delay the pair but not deadlock it; a wait on a

@@ -38,9 +38,7 @@ for stagger, sms, mode in ((0, 88, 32), (0, 88, 35)):      # 32: beside the chai
         lib.rn_debug_stream_lag(ctypes.byref(mean), ctypes.byref(mx), ctypes.byref(n))
         busy = (ctypes.c_uint * 176)()
         lib.rn_debug_stream_busy(busy, 176)
-        # 44 pairs in problem order: dir, feature, sigma, L7, L6, L5, L4, L3, L2, L1, L0 (4 each at 88 SMs)
-        names = ["dir", "feat", "sigma", "L7", "L6", "L5", "L4", "L3", "L2", "L1", "L0"]
-        per = [[busy[2 * (4 * i + j)] for j in range(4)] for i in range(11)]
-        print("busy us per pair:", {n: p_ for n, p_ in zip(names, per)})
+        # pairs in problem order (dir, feature, L7 .. L1, L0), 4 or 5 pairs per problem at 88 SMs
+        print("busy us per pair (leader CTAs):", [busy[2 * i] for i in range(44)])
         print(f"mode {mode}, stream SMs {sms}, M={M}: backward {e0.elapsed_time(e1):.3f} ms; hand-off lag mean {mean.value:.1f} us, max {mx.value:.1f} us over {n.value} CTAs")
 lib.rn_set_flag(10, 0); lib.rn_set_flag(11, 0); lib.rn_set_flag(9, 88)
