@@ -249,9 +249,10 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
       g_prof_next_flops = span_flops;
       int slot;
       prof_begin(3, st, &slot);
-      if (!(g_ws_debug & 1)) ++g_prof_suppress;
+      // fork; once the side stream depends on the caller's stream it MUST join again, whatever fails in between
       RN_CUDA_CHECK(cudaEventRecord(side->fork, st));
       RN_CUDA_CHECK(cudaStreamWaitEvent(side->st, side->fork, 0));
+      if (!(g_ws_debug & 1)) ++g_prof_suppress;
       int rc = mlp_chain_pair_backward(L, 9, M, w.dHC, 128, 128, w.dFS, 272, 272, st, w.flags, num_sms() - ws_sms);
       TnInfo infos[kWsMaxProblems];
       if (rc == RN_OK) rc = wgrad_stream_launch(P, np, M, w.flags, ws_sms, w.scratch, region, infos, (g_ws_debug & 2) ? st : side->st);
