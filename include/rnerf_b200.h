@@ -66,6 +66,8 @@ int rn_prof_enable(int on);
 int rn_debug_stream_lag(double* mean_us_host, double* max_us_host, int* ctas_host);
 /* ... and the microseconds each CTA pair's leader (entries 0, 2, 4, ...) spent on its chunks in that launch */
 int rn_debug_stream_busy(unsigned int* us_host, int n);
+/* host logic only: splits per GEMM (splits_out[<= 11]) the stream would use on `sms` SMs; RN_ERR_INVALID_ARG if too few */
+int rn_debug_stream_plan(int sms, int* splits_out, int* n_problems_out);
 int rn_prof_collect(double* ms4_host, double* flops4_host, int* launches4_host);
 
 /* ------------------------------------------------------------------------------------------

@@ -34,6 +34,7 @@ _SIGS = {
     "rn_get_flag": (c_int, [c_int, POINTER(c_int)]),
     "rn_debug_stream_lag": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     "rn_debug_stream_busy": (c_int, [POINTER(ctypes.c_uint), c_int]),
+    "rn_debug_stream_plan": (c_int, [c_int, POINTER(c_int), POINTER(c_int)]),
     "rn_prof_enable": (c_int, [c_int]),
     "rn_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     "rn_se3_poses_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),

@@ -70,6 +70,7 @@ struct WsHostProblem {
   const void* B; int64_t ldb; int b_cols, N;
   int flag_row;
 };
+int wgrad_stream_plan(const WsHostProblem* probs, int n, int pairs, int* splits_out);
 int wgrad_stream_launch(const WsHostProblem* probs, int n, int64_t M, const uint32_t* flags, int ctas, float* scratch,
                         size_t region_floats, TnInfo* infos, cudaStream_t st);
 

@@ -97,6 +97,20 @@ static int side_stream(SideStream** out) {
 
 static inline int ld_of(int l) { return l == 4 ? 320 : 256; }   // leading dimension of H[l]
 
+// The ten weight-gradient GEMMs of one backward pass as problems of the stream (wgrad_stream.cu), in the order their
+// partial-tile regions and reduce descriptors use.  Chain layer c writes: 0 -> dFS[:, 0:256], 1 -> dH7, ..., 8 -> dH0; dHC
+// comes from heads_bwd (complete before the launch), which also sums the one-row sigma_linear gradient.
+static int stream_problems(const TrainWs& w, WsHostProblem* P) {
+  int np = 0;
+  P[np++] = WsHostProblem{w.dHC, 128, 128, 0, 128, w.FD, 320, 320, 320, -1};           // dir_linear
+  P[np++] = WsHostProblem{w.dFS, 272, 272, 0, 256, w.H[7], 256, 256, 256, 0};           // feature_linear
+  for (int l = 7; l >= 1; --l)
+    P[np++] = (l == 5) ? WsHostProblem{w.dH[5], 256, 256, 0, 256, w.XC, 320, 320, 320, 8 - 5}
+                       : WsHostProblem{w.dH[l], 256, 256, 0, 256, w.H[l - 1], ld_of(l - 1), 256, 256, 8 - l};
+  P[np++] = WsHostProblem{w.dH[0], 256, 256, 0, 256, w.XC, 320, 64, 64, 8};             // layer 0: x_enc only
+  return np;
+}
+
 #define RN_TRY(expr)              \
   do {                            \
     int _rc = (expr);             \
@@ -231,13 +245,7 @@ static int mlp_backward(const void* packed, const float* pts, const float* dirs,
       // ---- ... with every weight gradient in a second launch beside it (wgrad_stream.cu) ----
       // chain layer c writes: 0 -> dFS[:, 0:256], 1 -> dH7, ..., 8 -> dH0; dHC comes from heads_bwd (complete already)
       WsHostProblem P[kWsMaxProblems];
-      int np = 0;
-      P[np++] = WsHostProblem{w.dHC, 128, 128, 0, 128, w.FD, 320, 320, 320, -1};           // dir_linear
-      P[np++] = WsHostProblem{w.dFS, 272, 272, 0, 256, w.H[7], 256, 256, 256, 0};           // feature_linear
-      for (int l = 7; l >= 1; --l)
-        P[np++] = (l == 5) ? WsHostProblem{w.dH[5], 256, 256, 0, 256, w.XC, 320, 320, 320, 8 - 5}
-                           : WsHostProblem{w.dH[l], 256, 256, 0, 256, w.H[l - 1], ld_of(l - 1), 256, 256, 8 - l};
-      P[np++] = WsHostProblem{w.dH[0], 256, 256, 0, 256, w.XC, 320, 64, 64, 8};             // layer 0: x_enc only
+      const int np = stream_problems(w, P);
       const int ws_sms = stream_sms & ~1;
       SideStream* side;
       RN_TRY(side_stream(&side));
@@ -368,6 +376,16 @@ int rn_get_flag(int flag, int* value_host) {
     case 11: *value_host = g_ws_stagger_us; return RN_OK;
     default: return RN_ERR_INVALID_ARG;
   }
+}
+
+int rn_debug_stream_plan(int sms, int* splits_out, int* n_problems_out) {
+  // host logic only (no device work): how the weight-gradient stream would split its GEMMs over `sms` SMs
+  RN_REQUIRE(splits_out && n_problems_out);
+  TrainWs w{};
+  WsHostProblem P[kWsMaxProblems];
+  const int np = stream_problems(w, P);
+  *n_problems_out = np;
+  return wgrad_stream_plan(P, np, sms / 2, splits_out);
 }
 
 size_t rn_mlp_workspace_bytes(int64_t M, int training) { return M > 0 ? workspace_bytes(M, training) : 0; }

@@ -49,6 +49,23 @@ def test_sass_uses_blackwell_tensor_path(rn):
     assert "HMMA.16816" not in sass        # no legacy mma.sync path
 
 
+def test_weight_gradient_stream_plan(rn):
+    """Host logic of csrc/wgrad_stream.cu: the ten weight-gradient GEMMs of a backward pass share the stream's CTA pairs
+    so that the slowest pair (bytes per 64-point chunk / splits) is as fast as possible; every GEMM gets at least one
+    pair and all pairs are used.  No device work."""
+    import ctypes
+    from robust_nerf_b200 import _lib
+    lib = _lib.lib()
+    splits, n = (ctypes.c_int * 11)(), ctypes.c_int(0)
+    assert lib.rn_debug_stream_plan(88, splits, ctypes.byref(n)) == 0
+    assert n.value == 10                                   # dir, feature, L7 .. L1, L0 (sigma_linear is heads_bwd's)
+    s = list(splits)[:10]
+    assert sum(s) == 44 and min(s) >= 4, s
+    assert s[0] >= 5 and s[4] >= 5, s                      # the two 320-wide GEMMs (dir_linear, layer 5) pull the most bytes per chunk
+    assert lib.rn_debug_stream_plan(20, splits, ctypes.byref(n)) == 0 and list(splits)[:10] == [1] * 10
+    assert lib.rn_debug_stream_plan(18, splits, ctypes.byref(n)) != 0          # fewer pairs than GEMMs
+
+
 def test_configs_match_reference_defaults(rn):
     for ours, ref in ((rn.ModelConfig(), O.ModelConfig()), (rn.RenderConfig(), O.RenderConfig())):
         assert vars(ours) == vars(ref)
