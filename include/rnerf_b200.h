@@ -51,7 +51,7 @@ unsigned long long rn_launch_count(void);
  *   5: programmatic dependent launch for the GEMM-family kernels (default 0)
  *   6: L2 cache hints, bit mask: 1 chains, 2 split-K loads evict_first (default 0), 8 = no policies on the hand-off
  *      between the data-gradient chain and the weight-gradient stream (they are on by default)
- *   9: SMs given to the weight-gradient stream that runs beside the data-gradient chain (default: 88 on a 148-SM
+ *   9: SMs given to the weight-gradient stream that runs beside the data-gradient chain (default: 84 on a 148-SM
  *      part; 0 = off: one split-K launch per layer after the chain)
  *   7, 8, 10, 11: measurement only (SM limit of the data-gradient chain / of the split-K kernels; bit mask of
  *             timing options for the overlapped backward, 32 = record hand-off lags for rn_debug_stream_lag;

@@ -121,13 +121,13 @@ static int stream_problems(const TrainWs& w, WsHostProblem* P) {
 int g_chain_dbg = 0;
 #endif
 // rn_set_flag(9, n): the weight gradients run BESIDE the data-gradient chain on n SMs (wgrad_stream.cu), taking each block
-// of dH as the chain publishes it.  -1 (default) = 88 of 148 SMs, the measured optimum (44 pairs: 4 or 5 splits for each of
-// the 10 GEMMs; the chain keeps 60), off on a part with another SM count; 0 = off: one split-K launch per layer after the
-// chain (1.3-4.3 % more time per step, profiles/r02_ab_log.md blocks 19-23).
+// of dH as the chain publishes it.  -1 (default) = 84 of 148 SMs, the measured optimum (42 pairs: 5 splits for the two
+// 320-wide GEMMs, 4 for the other eight; the chain keeps 64), off on a part with another SM count; 0 = off: one split-K
+// launch per layer after the chain (more time per step, profiles/r02_ab_log.md blocks 19-24).
 int g_wgrad_stream_sms = -1;
 static int wgrad_stream_sms() {
   if (g_wgrad_stream_sms >= 0) return g_wgrad_stream_sms;
-  return num_sms() == 148 ? 88 : 0;
+  return num_sms() == 148 ? 84 : 0;
 }
 // rn_set_flag(10, mask): measurement only.  bit 0 = record the two launches separately as well as the span; bit 1 = launch
 // the stream AFTER the chain on the same stream (every flag already set: the consumer alone, operands from HBM)

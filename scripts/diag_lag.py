@@ -17,7 +17,7 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 net = rn.NeRF().to(dev)
 rng = np.random.default_rng(3)
-for stagger, sms, mode in ((0, 88, 32), (0, 88, 35)):      # 32: beside the chain; 35: after it (alone, every flag set)
+for stagger, sms, mode in ((0, 84, 32), (0, 84, 35)):      # 32: beside the chain; 35: after it (alone, every flag set)
     lib.rn_set_flag(11, stagger)
     lib.rn_set_flag(9, sms)
     for M in (786432,):
@@ -36,9 +36,9 @@ for stagger, sms, mode in ((0, 88, 32), (0, 88, 35)):      # 32: beside the chai
             torch.cuda.synchronize()
         mean, mx, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
         lib.rn_debug_stream_lag(ctypes.byref(mean), ctypes.byref(mx), ctypes.byref(n))
-        busy = (ctypes.c_uint * 176)()
-        lib.rn_debug_stream_busy(busy, 176)
-        # pairs in problem order (dir, feature, L7 .. L1, L0), 4 or 5 pairs per problem at 88 SMs
-        print("busy us per pair (leader CTAs):", [busy[2 * i] for i in range(44)])
+        busy = (ctypes.c_uint * 168)()
+        lib.rn_debug_stream_busy(busy, 168)
+        # pairs in problem order (dir, feature, L7 .. L1, L0), 4 or 5 pairs per problem at 84 SMs
+        print("busy us per pair (leader CTAs):", [busy[2 * i] for i in range(42)])
         print(f"mode {mode}, stream SMs {sms}, M={M}: backward {e0.elapsed_time(e1):.3f} ms; hand-off lag mean {mean.value:.1f} us, max {mx.value:.1f} us over {n.value} CTAs")
-lib.rn_set_flag(10, 0); lib.rn_set_flag(11, 0); lib.rn_set_flag(9, 88)
+lib.rn_set_flag(10, 0); lib.rn_set_flag(11, 0); lib.rn_set_flag(9, 84)
