@@ -736,6 +736,42 @@ def run_gpu(args):
                   "value": RAYS_PER_GPU * K_ / (t_strong * 1e-3), "unit": "rays/s",
                   "note": "same step, same global batch as the 1-GPU line; per-GPU work shrinks with N, the all-reduce does not"}
 
+    # ---- what the collectives cost: the same K steps with the two all-reduces skipped ----
+    allreduce = None
+    if world > 1 and not args.no_extras:
+        saved = [t.clone() for t in (trainer.flat, trainer.exp_avg, trainer.exp_avg_sq)]
+
+        def timed_steps():
+            trainer._graphs.clear()
+            for i in range(W_):
+                step_fn(*dev_batches[i % POOL])
+            barrier()
+            e0.record()
+            for i in range(K_):
+                step_fn(*dev_batches[i % POOL])
+            e1.record()
+            barrier()
+            return reduce_max(e0.elapsed_time(e1)) / K_
+
+        try:
+            t_with = timed_steps()                       # back to back with the run below: same clocks
+            trainer.skip_allreduce = True
+            t_no = timed_steps()
+        finally:
+            trainer.skip_allreduce = False
+            trainer._graphs.clear()
+            for t, sv in zip((trainer.flat, trainer.exp_avg, trainer.exp_avg_sq), saved):
+                t.copy_(sv)                     # the replicas diverged while the gradients were not averaged
+            for m in trainer.nets:
+                m._packed.key = None
+        nbytes = 4 * int(trainer.gflat.numel())
+        allreduce = {"collective": "ncclAllReduce(SUM) of the flat fp32 gradient buffer in two pieces: the fine network's slice on a "
+                                   "side stream as soon as its backward has finished, the rest after the coarse backward",
+                     "bytes_per_step": nbytes, "ms_per_step_with": t_with, "ms_per_step_without": t_no,
+                     "exposed_us_per_step": (t_with - t_no) * 1e3,
+                     "note": "exposed = step time with the collectives - step time without (same run, max over ranks); it "
+                             "includes waiting for the slowest rank"}
+
     peaks = measured_peaks()
     trainer._graphs.clear()                       # release the captured step (and its 11 GB workspace) before the other blocks
     step_fn = None
@@ -766,6 +802,8 @@ def run_gpu(args):
         extra["wgrad_sequential_variant"] = seq_variant
     if strong:
         extra["strong_scaling"] = strong
+    if allreduce:
+        extra["allreduce"] = allreduce
     if world > 1:
         dist.barrier()
 

@@ -253,6 +253,7 @@ class Trainer:
         _flatten_into(self.pose_params, self.flat, self.gflat, n_net)
         self._side = torch.cuda.Stream(device=dev) if self._early else None
         self._early_issued = False
+        self.skip_allreduce = False        # measurement only (bench.py: exposed time of the collectives); replicas diverge while set
         self.norms = torch.zeros(2 * (8 + 8 * 64), device=dev)    # two rn_clip_adam_step scratch areas
         # [lr, 1-b1^t, sqrt(1-b2^t)] for the nets and for the poses: read by the Adam kernel from device memory so
         # a captured CUDA graph can be replayed while the schedule advances
@@ -286,6 +287,8 @@ class Trainer:
     def _allreduce_early(self):
         """Called by the fine network's backward as soon as its gradient slice is final: all-reduce it on a side stream,
         underneath the coarse network's backward (captured into the step's CUDA graph like everything else)."""
+        if self.skip_allreduce:
+            return
         lo, hi = self._early
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
@@ -310,7 +313,7 @@ class Trainer:
     def _allreduce(self):
         """SUM over ranks of whatever has not been reduced yet; the 1 / world of the mean is applied by the clip + Adam
         kernel on load (`grad_scale`), not by another launch."""
-        if self.world <= 1:
+        if self.world <= 1 or self.skip_allreduce:
             return
         if self._early_issued:
             lo = self._early[1]
