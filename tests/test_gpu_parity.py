@@ -846,7 +846,23 @@ def test_weight_gradient_stream_beside_the_chain(rn, dev):
                 assert torch.equal(b, c), (M, n, "two runs of the stream differ", (b - c).abs().max().item())
                 tol = 2e-6 * max(1.0, M / 1000.0) ** 0.5 * 4 * max(a.abs().max().item(), 1e-6)
                 assert (a - b).abs().max().item() <= tol, (M, n, (a - b).abs().max().item(), tol)
+        # the measurement hooks of the hand-off (rn_set_flag(10, 32)): lag between a block's publication and its load, and
+        # the time every pair's leader spent on its chunks
+        lib.rn_set_flag(9, 84)
+        lib.rn_set_flag(10, 32)
+        net.zero_grad()
+        raw = net.forward_raw(pts.clone().requires_grad_(True), dirs.clone().requires_grad_(True), 1)
+        (raw * gout).sum().backward()
+        mean, mx, n = ctypes.c_double(-1), ctypes.c_double(-1), ctypes.c_int(0)
+        assert lib.rn_debug_stream_lag(ctypes.byref(mean), ctypes.byref(mx), ctypes.byref(n)) == 0
+        assert n.value == 2 * (42 - 5) and 0.0 <= mean.value <= mx.value < 4e6, (n.value, mean.value, mx.value)     # dir_linear's 5 pairs wait for no flag
+        busy = (ctypes.c_uint * 84)()
+        assert lib.rn_debug_stream_busy(busy, 84) == 0
+        assert all(busy[2 * i] > 0 for i in range(42)), list(busy)
+        print(f"\n[stream] hand-off lag at {M} points: mean {mean.value:.1f} us, max {mx.value:.1f} us; pair busy times "
+              f"{min(busy[2 * i] for i in range(42))}-{max(busy[2 * i] for i in range(42))} us")
     finally:
+        lib.rn_set_flag(10, 0)
         lib.rn_set_flag(9, prev.value)
 
 
