@@ -13,8 +13,11 @@
 //   dir         FD[:, 0:320] x WD^T   -> HC            (N=128, K=320)
 //   heads       sigma = H7 . w_sigma and rgb = HC . W_rgb^T are fp32 dot products fused into the
 //               epilogues of L7 and of the view-branch GEMM -> raw[M,4]
-// Backward mirrors it: heads_bwd, then per layer one TN GEMM (weight + bias gradient, split-K over
-// points) and one NN GEMM (data gradient with the ReLU mask of the layer input fused in).
+// Backward: heads_bwd (dHC, dsigma, the rgb_linear and -- with the stream -- sigma_linear gradients), then ONE data-gradient
+// chain launch (chain_pair.cu: dHC -> dF -> dH7 -> ... -> dH0 with the ReLU masks fused in) and BESIDE it, on its own SMs and
+// a second stream, ONE weight-gradient launch for all ten GEMMs (wgrad_stream.cu), then one deterministic reduce of their
+// partial tiles.  rn_set_flag(9, 0) / rn_set_flag(3, 0) fall back to one TN (split-K) / NN launch per layer
+// (gemm_tcgen05.cu), which are also the cross-checks of the parity tests.
 #include "common.cuh"
 #include "gemm.h"
 #include "mlp_layout.h"
