@@ -124,9 +124,9 @@ static int stream_problems(const TrainWs& w, WsHostProblem* P) {
 int g_chain_dbg = 0;
 #endif
 // rn_set_flag(9, n): the weight gradients run BESIDE the data-gradient chain on n SMs (wgrad_stream.cu), taking each block
-// of dH as the chain publishes it.  -1 (default) = 84 of 148 SMs, the measured optimum (42 pairs: 5 splits for the two
-// 320-wide GEMMs, 4 for the other eight; the chain keeps 64), off on a part with another SM count; 0 = off: one split-K
-// launch per layer after the chain (more time per step, profiles/r02_ab_log.md blocks 19-24).
+// of dH as the chain publishes it.  -1 (default) = 84 of 148 SMs, the measured optimum (42 pairs: 5 splits for dir_linear
+// and layer 5, 4 for the other eight GEMMs; the chain keeps 64; 82 measures the same), off on a part with another SM
+// count; 0 = off: one split-K launch per layer after the chain (more time per step, profiles/r02_ab_log.md blocks 19-26).
 int g_wgrad_stream_sms = -1;
 static int wgrad_stream_sms() {
   if (g_wgrad_stream_sms >= 0) return g_wgrad_stream_sms;

@@ -135,6 +135,10 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
   const int NB = nb_raw > kWsMaxBStages ? kWsMaxBStages : nb_raw;
   uint8_t* s_ring_b = s_ring + NA * kWsABytes;
   const int bias_col = N1 + N2;
+  // MMA 2's real 64 columns (256..319) are one CTA's box, the other CTA's box lies beyond the tensor.  Normally CTA 0 holds
+  // them; when CTA 1 has no A features to load (M = 128: dir_linear) it takes them instead, which evens out what the two
+  // SMs pull per chunk (32 / 24 KiB instead of 40 / 16) -- the output columns then sit 64 TMEM columns further right.
+  const int swap2 = (N2 && P.a_col0 + 128 >= P.a_cols) ? 1 : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&P.tmA); prefetch_tmap(&P.tmB);
@@ -153,7 +157,7 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
     uint32_t m = 0;
     for (int j = 0; j < 2; ++j) m |= (P.a_col0 + r * 128 + j * 64 < P.a_cols) ? (1u << j) : 0u;
     for (int j = 0; j < nb1; ++j) m |= (r * (N1 / 2) + j * 64 < P.b_cols) ? (4u << j) : 0u;
-    if (N2) m |= (256 + r * 64 < P.b_cols) ? (4u << nb1) : 0u;
+    if (N2) m |= (256 + (r ^ swap2) * 64 < P.b_cols) ? (4u << nb1) : 0u;
     box_mask[r] = m;
   }
   const uint32_t my_mask = box_mask[rank];
@@ -257,7 +261,7 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
             if (my_mask & (4u << j))
               tma_load_2d_pair_hint(b_s + j * 8192, &P.tmB, bar, (int)rank * (N1 / 2) + j * 64, kc * 64, pol);
           if (N2 && (my_mask & (4u << nb1)))
-            tma_load_2d_pair_hint(b_s + nb1 * 8192, &P.tmB, bar, 256 + (int)rank * 64, kc * 64, pol);
+            tma_load_2d_pair_hint(b_s + nb1 * 8192, &P.tmB, bar, 256 + ((int)rank ^ swap2) * 64, kc * 64, pol);
           if (++s == NB) { s = 0; ph ^= 1; }
         }
       }
@@ -319,7 +323,7 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
-          tmem_ld_x32(t_base + c * 32, v);
+          tmem_ld_x32(t_base + c * 32 + ((swap2 && c >= 8) ? 64 : 0), v);
           tmem_ld_wait();
           float4* dst = reinterpret_cast<float4*>(out + (size_t)row * BN + c * 32);
 #pragma unroll
@@ -356,10 +360,16 @@ wgrad_stream_kernel(const __grid_constant__ WsParams p) {
 // latency after its loads were issued whatever it holds, so below ~32 KiB per SM a chunk takes the same ~0.4 us (measured:
 // the N = 64 and sigma problems, 18-24 KiB per chunk, ran no faster per chunk than the 32 KiB ones).
 static int ws_bytes_per_chunk(const WsHostProblem& h) {
-  const int a0 = h.a_cols - h.a_col0;                               // in-bounds features of CTA 0's A half
-  const int a = (a0 >= 128 ? 128 : (a0 > 0 ? a0 : 0)) * 128;
-  const int b = (h.N == 64 ? 64 : (h.N == 320 ? 192 : 128)) * 128;
-  return a + b > 32768 ? a + b : 32768;
+  const int a0 = h.a_cols - h.a_col0;                               // in-bounds features from a_col0 on
+  const int a_r0 = (a0 >= 128 ? 128 : (a0 > 0 ? a0 : 0)) * 128;
+  const int a_r1 = (a0 >= 256 ? 128 : (a0 > 128 ? a0 - 128 : 0)) * 128;
+  const int half = (h.N == 64 ? 64 : 128) * 128;                    // MMA 1: each CTA's half of the columns (x_enc: CTA 0 only)
+  const int extra = h.N == 320 ? 64 * 128 : 0;                      // MMA 2: the real 64 columns, held by one CTA
+  const bool swap2 = h.N == 320 && a_r1 == 0;                       // ... by CTA 1 when it has no A to load (the kernel's swap2)
+  const int r0 = a_r0 + half + (swap2 ? 0 : extra);
+  const int r1 = a_r1 + (h.N == 64 ? 0 : half) + (swap2 ? extra : 0);
+  const int m = r0 > r1 ? r0 : r1;
+  return m > 32768 ? m : 32768;
 }
 
 // Splits per problem: the slowest pair sets the pace, so hand out pairs one at a time to whichever problem has the most
